@@ -1,0 +1,218 @@
+/*
+ * sktopt_b200.h -- C ABI of the B200-native hot path of scikit-topt's
+ * per-iteration FEA + sensitivity loop.
+ *
+ * The reference (kevin-tofu/scikit-topt, pure Python) has no FFI; this header is
+ * the boundary a maintainer would bind with ctypes.  Each
+ * entry point names the reference call site it replaces (paths relative to
+ * /root/reference/scikit-topt/sktopt/).
+ *
+ * Conventions
+ *  - Every function returns 0 on success, non-zero on failure;
+ *    sktb_last_error() returns a thread-local message for the last failure.
+ *  - Pointers suffixed _h are HOST pointers, everything else is a DEVICE pointer
+ *    (fp64 / int32 / uint8) on the CUDA device the mesh was created on.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    All work is enqueued asynchronously unless the doc says "synchronises".
+ *  - Element types: 0 = hex8 (trilinear), 1 = tet4 (linear).  dofs-per-node
+ *    (dpn) is 3 for elasticity and 1 for scalar (heat / Helmholtz) problems.
+ *    DOF numbering is dpn*node + comp (reference mesh/task_elastic.py:72).
+ *  - CSR: int32 row_ptr[n_rows+1], int32 col_idx[nnz] (sorted per row),
+ *    fp64 vals[nnz]; the pattern is the union of element couplings.
+ */
+#ifndef SKTOPT_B200_H
+#define SKTOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKTB_HEX8 0
+#define SKTB_TET4 1
+
+#define SKTB_KE_ELASTIC 0 /* fea/composer.py:88-98  lam tr(e)tr(e) + 2 mu e:e, E=1 */
+#define SKTB_KE_LAPLACE 1 /* fea/composer.py:139-141 grad u . grad v, k=1         */
+#define SKTB_KE_MASS 2    /* filters/helmholtz_filter_nodal.py:136-138  u v         */
+
+const char *sktb_last_error(void);
+int sktb_version(void);
+
+/* ------------------------------------------------------------------ mesh --
+ * Connectivity-derived structures shared by every operator on one mesh:
+ * node graph (union of element couplings), node->element adjacency and the
+ * per-(row node, column node) contributor lists ("scatter map") that make the
+ * assembly a deterministic gather.
+ * Replaces the index bookkeeping hidden inside skfem.asm / COO->CSR
+ * (fea/composer.py:100,144) and the Python loops at
+ * filters/helmholtz_filter_nodal.py:47-52, mesh/utils.py:210-212.            */
+typedef struct sktb_mesh sktb_mesh;
+
+int sktb_mesh_create(sktb_mesh **out, int elem_type, int64_t n_elem,
+                     int64_t n_nodes,
+                     const int32_t *conn_h,  /* [nen][n_elem] */
+                     const double *coords_h, /* [3][n_nodes]  */
+                     int device);
+void sktb_mesh_destroy(sktb_mesh *m);
+int64_t sktb_mesh_node_nnz(const sktb_mesh *m);
+/* copies the node graph (CSR over nodes) to host buffers */
+int sktb_mesh_node_graph_h(const sktb_mesh *m, int32_t *row_ptr_h,
+                           int32_t *col_idx_h);
+/* dof-level CSR pattern for dpn dofs per node, written to device buffers:
+ * row_ptr[dpn*n_nodes+1], col_idx[dpn*dpn*node_nnz]                          */
+int sktb_mesh_dof_pattern(const sktb_mesh *m, int dpn, int32_t *row_ptr,
+                          int32_t *col_idx, void *stream);
+
+/* Unit element matrices Ke0 (material coefficient = 1) for `n_class` geometry
+ * classes; class c is represented by element class_rep_h[c].
+ * out: [n_class][nde][nde], nde = nen*dpn (dpn = 3 for ELASTIC else 1).
+ * Quadrature (X_h[3][nqp] on the reference element, W_h[nqp]) is the basis
+ * quadrature of the reference (skfem Basis(intorder)).                         */
+int sktb_unit_ke(const sktb_mesh *m, int kind, double nu, int nqp,
+                 const double *X_h, const double *W_h, int64_t n_class,
+                 const int32_t *class_rep_h, double *out, void *stream);
+
+/* K2: vals = sum_e scale[e] * Ke0[class[e]] gathered into CSR order.
+ * elem_class may be NULL (class == element), scale may be NULL (all ones).
+ * If dir_mask (uint8 per dof) is given the Dirichlet rows/cols are written as
+ * identity (skfem.enforce semantics, fea/solver_elastic.py:211).
+ * Replaces composer.assemble_stiffness_matrix / assemble_conduction_matrix.   */
+int sktb_assemble(const sktb_mesh *m, int dpn, const double *unit_ke,
+                  const int32_t *elem_class, const double *scale,
+                  const uint8_t *dir_mask, double *vals, void *stream);
+
+/* K3 helpers (skfem.enforce): zero rows/cols of masked dofs, unit diagonal.   */
+int sktb_csr_enforce(int64_t n_rows, const int32_t *row_ptr,
+                     const int32_t *col_idx, double *vals,
+                     const uint8_t *dir_mask, void *stream);
+/* out[r] = 1 / K[r,r]  (Jacobi preconditioner, fea/solver_elastic.py:85-86)   */
+int sktb_csr_inv_diag(int64_t n_rows, const int32_t *row_ptr,
+                      const int32_t *col_idx, const double *vals, double *out,
+                      void *stream);
+/* K4: y = A x  (the SpMV inside scipy.sparse.linalg.cg,
+ * fea/solver_elastic.py:89,101)                                               */
+int sktb_spmv(int64_t n_rows, int dpn_hint, const int32_t *row_ptr,
+              const int32_t *col_idx, const double *vals, const double *x,
+              double *y, void *stream);
+
+/* --------------------------------------------------------------- PCG ------
+ * K4-K6: Jacobi-preconditioned conjugate gradients, all scalars device
+ * resident, convergence test ||r||_2 <= rtol*||b||_2 (scipy cg, atol=0).
+ * Replaces solve_u(... 'cg_jacobi' / 'cg_pyamg') fea/solver_elastic.py:61-143.
+ * The workspace holds r, z, p, q and the reduction scratch.                   */
+typedef struct sktb_pcg sktb_pcg;
+int sktb_pcg_create(sktb_pcg **out, int64_t n_rows, int device);
+void sktb_pcg_destroy(sktb_pcg *s);
+/* x holds the initial guess on entry (use_x0 != 0) or is overwritten (x0 = 0).
+ * Synchronises the stream.  info_h: [0]=iterations, [1]=converged(0/1);
+ * relres_h: final ||r||/||b||.                                                */
+int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
+                   const int32_t *col_idx, const double *vals,
+                   const double *inv_diag, const double *b, double *x,
+                   int use_x0, double rtol, int maxiter, int check_every,
+                   int32_t *info_h, double *relres_h, void *stream);
+
+/* ------------------------------------------------------ element kernels ---*/
+/* K1: E = Emin + (E0-Emin) rho^p (fea/composer.py:19-22); ramp != 0 gives
+ * Emin + (E0-Emin) rho/(1+p(1-rho)) (fea/composer.py:25-39)                   */
+int sktb_interpolate_modulus(int64_t n, const double *rho, double E0,
+                             double Emin, double p, int ramp, double *out,
+                             void *stream);
+/* K7: U_e = 1/2 scale[e] u_e^T Ke0[class[e]] u_e
+ * (fea/solver_elastic.py:470-537, fea/solver_heat.py:256-303)                 */
+int sktb_element_energy(const sktb_mesh *m, int dpn, const double *unit_ke,
+                        const int32_t *elem_class, const double *scale,
+                        const double *u, double *out, void *stream);
+/* K8: g = -2 U dE/drho / max(E,1e-12) * dH  (core/derivatives.py:42-68,
+ * core/projection.py:80-118, common_density.py:1083-1097); dH may be NULL.    */
+int sktb_dc_drho(int64_t n, const double *rho_proj, const double *energy,
+                 double E0, double Emin, double p, int ramp, const double *dH,
+                 double *out, void *stream);
+/* K13a: out = H_beta(x), dH = dH/dx (core/projection.py:27-118); either output
+ * may be NULL.                                                                 */
+int sktb_heaviside(int64_t n, const double *x, double beta, double eta,
+                   double *out, double *dH, void *stream);
+
+/* K9: Helmholtz filter transfer operators
+ * (filters/helmholtz_filter_nodal.py:26-56).
+ * e2n: out[n] = sum_{e in n} w[e]*v(e) / wsum[n], v(e) = val[e] if
+ *      design[e] (or design == NULL) else fixed_value; wsum from
+ *      sktb_e2n_wsum (sum of w over the node's elements, 0 -> 1).
+ * n2e: out[e] = mean of x over the element's nodes; clamp_max0 != 0 applies
+ *      min(.,0) (helmholtz_filter_nodal.py:232).                               */
+int sktb_e2n(const sktb_mesh *m, const double *w, const double *val,
+             const uint8_t *design, double fixed_value, const double *wsum,
+             double *out, void *stream);
+int sktb_e2n_wsum(const sktb_mesh *m, const double *w, double *out,
+                      void *stream);
+int sktb_n2e_mean(const sktb_mesh *m, const double *x, int clamp_max0,
+                  double *out, void *stream);
+
+/* ------------------------------------------------------ update kernels ----*/
+/* K12: OC candidate (core/optimizers/oc.py:50-68).  rho_e, dC over design
+ * elements; writes scaling_rate, rho_cand (design) and scatters rho_cand into
+ * rho_full_cand[design_idx].                                                   */
+int sktb_oc_candidate(int64_t n_design, const double *dC, const double *rho_e,
+                      double lmid, double eps, double eta, double move_limit,
+                      double rho_min, double rho_max, double sr_min,
+                      double sr_max, const int32_t *design_idx,
+                      double *scaling_rate, double *rho_cand,
+                      double *rho_full_cand, void *stream);
+/* K14: log-space MOC step (core/optimizers/logmoc.py:36-66), rho in/out.      */
+int sktb_logmoc_update(int64_t n, double *rho, const double *dL, double eta,
+                       double move_limit, double rho_min, double rho_max,
+                       double clip, double *scaling_rate, double *clip_lower,
+                       double *clip_upper, void *stream);
+/* K13b: deterministic single-kernel reductions; result written to out_h after
+ * synchronising the stream.  idx may be NULL (identity).
+ *   wsum : sum_i a[idx[i]] * (w ? w[i] : 1)
+ *   stats: out_h[0..3] = min, mean, max, std (population) of a[idx[i]]
+ *   absmax: max_i |a[i]|                                                      */
+int sktb_reduce_wsum_h(int64_t n, const double *a, const int32_t *idx,
+                       const double *w, double *out_h, void *stream);
+int sktb_reduce_stats_h(int64_t n, const double *a, const int32_t *idx,
+                        double *out_h, void *stream);
+int sktb_reduce_absmax_h(int64_t n, const double *a, double *out_h,
+                         void *stream);
+/* dot product (compliance F.u, fea/solver_elastic.py:236)                     */
+int sktb_dot_h(int64_t n, const double *a, const double *b, double *out_h,
+               void *stream);
+/* K15: np.percentile(np.abs(a), q) with linear interpolation
+ * (core/optimizers/oc.py:189, logmoc.py:167-174,220); work: >= n uint64 +
+ * 8192 bytes of scratch.  Synchronises.                                        */
+int sktb_abs_percentile_h(int64_t n, const double *a, double q, void *work,
+                          double *out_h, void *stream);
+/* gather / scatter by index (rho[design] <-> rho_design)                      */
+int sktb_gather(int64_t n, const double *src, const int32_t *idx, double *dst,
+                void *stream);
+int sktb_scatter(int64_t n, const double *src, const int32_t *idx, double *dst,
+                 void *stream);
+/* y = a*x + b*y elementwise helpers used by the filter RHS / LogMOC dL         */
+int sktb_axpby(int64_t n, double a, const double *x, double b, double *y,
+               void *stream);
+/* out = a*x + b*y + c (y may be NULL); out = a*x*y                             */
+int sktb_affine(int64_t n, double a, const double *x, double b,
+                const double *y, double c, double *out, void *stream);
+int sktb_hadamard(int64_t n, double a, const double *x, const double *y,
+                  double *out, void *stream);
+/* KKT residual (core/optimizers/oc.py:230-240, logmoc.py:227-236):
+ * out_h[0] = max |g + coef*dv| over lo < rho < hi, out_h[1] = how many such.  */
+int sktb_kkt_residual_h(int64_t n, const double *rho, const double *g,
+                        const double *dv, double coef, double lo, double hi,
+                        double *out_h, void *stream);
+/* max_i |a[idx[i]] - b[idx[i]]|  (rho_change_max, common_density.py:1137-1141) */
+int sktb_reduce_maxdiff_h(int64_t n, const double *a, const double *b,
+                          const int32_t *idx, double *out_h, void *stream);
+/* rhs for enforce with prescribed values: out = mask ? xD : b - t             */
+int sktb_enforce_rhs(int64_t n, const double *b, const double *t,
+                     const uint8_t *mask, const double *xD, double *out,
+                     void *stream);
+
+/* benchmark utility: overwrite a > L2-sized scratch buffer                     */
+int sktb_flush_l2(void *scratch, int64_t bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKTOPT_B200_H */

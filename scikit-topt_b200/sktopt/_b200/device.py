@@ -1,0 +1,461 @@
+"""Device-side objects built on the C ABI (``include/sktopt_b200.h``).
+
+PyTorch is used only as plumbing here: it owns the device buffers (fp64 /
+int32 / uint8 CUDA tensors) and the current stream; all arithmetic is done by
+the hand-written kernels in ``csrc/`` through ctypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+F64 = torch.float64
+I32 = torch.int32
+U8 = torch.uint8
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "sktopt (B200 build) needs a CUDA device; there is no CPU fallback"
+        )
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_dev(a, dtype=F64, device=None):
+    """numpy / torch -> contiguous CUDA tensor of `dtype`."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device or "cuda", dtype=dtype).contiguous()
+    np_dtype = {F64: np.float64, I32: np.int32, U8: np.uint8}[dtype]
+    arr = np.ascontiguousarray(np.asarray(a), dtype=np_dtype)
+    return torch.from_numpy(arr).to(device or "cuda")
+
+
+def element_classes(p: np.ndarray, t: np.ndarray, rel_tol: float = 1e-11):
+    """Group elements with congruent (translated) geometry.
+
+    Returns (elem_class int32 (n_elem,) or None, class_rep int32 (n_class,)).
+    ``None`` means "every element is its own class" (unstructured mesh).
+    The unit element matrix depends on geometry only (material factors out of
+    the reference's forms, fea/composer.py:80-98,136-141), so one matrix per
+    class is enough.
+    """
+    ne = t.shape[1]
+    x0 = p[:, t[0]]
+    d = p[:, t[1:]] - x0[:, None, :]
+    scale = float(np.abs(d).max())
+    q = np.rint(d.reshape(-1, ne) / (scale * rel_tol)).astype(np.int64)
+    rng = np.random.default_rng(12345)
+    h1 = np.zeros(ne, dtype=np.uint64)
+    h2 = np.zeros(ne, dtype=np.uint64)
+    mult1 = rng.integers(1, 2**63 - 1, size=q.shape[0], dtype=np.uint64) | np.uint64(1)
+    mult2 = rng.integers(1, 2**63 - 1, size=q.shape[0], dtype=np.uint64) | np.uint64(1)
+    qu = q.view(np.uint64)
+    with np.errstate(over="ignore"):
+        for r in range(q.shape[0]):
+            h1 += qu[r] * mult1[r]
+            h2 += (qu[r] ^ np.uint64(0x9E3779B97F4A7C15)) * mult2[r]
+    keys = np.empty(ne, dtype=[("a", np.uint64), ("b", np.uint64)])
+    keys["a"] = h1
+    keys["b"] = h2
+    _, rep, inv = np.unique(keys, return_index=True, return_inverse=True)
+    n_class = rep.size
+    if n_class > max(64, ne // 4):
+        return None, np.arange(ne, dtype=np.int32)
+    # number classes by first occurrence so the result is order-stable
+    order = np.argsort(rep, kind="stable")
+    remap = np.empty(n_class, dtype=np.int64)
+    remap[order] = np.arange(n_class)
+    return remap[inv].astype(np.int32), rep[order].astype(np.int32)
+
+
+class DeviceMesh:
+    """Device-resident connectivity structures of one mesh (``sktb_mesh``)."""
+
+    def __init__(self, mesh, device: int | None = None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.mesh = mesh
+        self.device = torch.cuda.current_device() if device is None else device
+        self.nen = mesh.t.shape[0]
+        self.elem_type = 0 if self.nen == 8 else 1
+        self.n_elem = int(mesh.t.shape[1])
+        self.n_nodes = int(mesh.p.shape[1])
+        conn = np.ascontiguousarray(mesh.t, dtype=np.int32)
+        coords = np.ascontiguousarray(mesh.p, dtype=np.float64)
+        handle = C.c_void_p()
+        _lib.check(
+            self.lib.sktb_mesh_create(
+                C.byref(handle), self.elem_type, self.n_elem, self.n_nodes,
+                conn.ctypes.data_as(C.c_void_p), coords.ctypes.data_as(C.c_void_p),
+                self.device,
+            )
+        )
+        self.handle = handle
+        self.node_nnz = int(self.lib.sktb_mesh_node_nnz(handle))
+        cls, rep = element_classes(coords, conn)
+        self.class_rep_h = np.ascontiguousarray(rep, dtype=np.int32)
+        self.n_class = int(rep.size)
+        self.elem_class = None if cls is None else to_dev(cls, I32)
+        self._unit_ke = {}
+        self._patterns = {}
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_mesh_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- graph / pattern -----------------------------------------------------
+    def node_graph(self):
+        rp = np.empty(self.n_nodes + 1, dtype=np.int32)
+        ci = np.empty(self.node_nnz, dtype=np.int32)
+        _lib.check(
+            self.lib.sktb_mesh_node_graph_h(
+                self.handle, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return rp, ci
+
+    def dof_pattern(self, dpn: int):
+        """(row_ptr, col_idx) int32 CUDA tensors of the dpn-dof CSR pattern."""
+        if dpn not in self._patterns:
+            n = dpn * self.n_nodes
+            rp = torch.empty(n + 1, dtype=I32, device="cuda")
+            ci = torch.empty(dpn * dpn * self.node_nnz, dtype=I32, device="cuda")
+            _lib.check(
+                self.lib.sktb_mesh_dof_pattern(self.handle, dpn, _ptr(rp), _ptr(ci), _stream())
+            )
+            self._patterns[dpn] = (rp, ci)
+        return self._patterns[dpn]
+
+    # -- unit element matrices ----------------------------------------------
+    def unit_ke(self, kind: int, X: np.ndarray, W: np.ndarray, nu: float = 0.0):
+        key = (kind, float(nu), X.shape[1], float(W.sum()), float(X.sum()))
+        if key not in self._unit_ke:
+            dpn = 3 if kind == 0 else 1
+            nde = self.nen * dpn
+            out = torch.empty((self.n_class, nde, nde), dtype=F64, device="cuda")
+            Xc = np.ascontiguousarray(X, dtype=np.float64)
+            Wc = np.ascontiguousarray(W, dtype=np.float64)
+            _lib.check(
+                self.lib.sktb_unit_ke(
+                    self.handle, kind, float(nu), int(Xc.shape[1]),
+                    Xc.ctypes.data_as(C.c_void_p), Wc.ctypes.data_as(C.c_void_p),
+                    self.n_class, self.class_rep_h.ctypes.data_as(C.c_void_p),
+                    _ptr(out), _stream(),
+                )
+            )
+            self._unit_ke[key] = out
+        return self._unit_ke[key]
+
+    # -- kernels ---------------------------------------------------------------
+    def assemble(self, dpn, unit_ke, scale=None, dir_mask=None, out=None):
+        if out is None:
+            out = torch.empty(dpn * dpn * self.node_nnz, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_assemble(
+                self.handle, dpn, _ptr(unit_ke), _ptr(self.elem_class), _ptr(scale),
+                _ptr(dir_mask), _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def element_energy(self, dpn, unit_ke, scale, u, out=None):
+        if out is None:
+            out = torch.empty(self.n_elem, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_element_energy(
+                self.handle, dpn, _ptr(unit_ke), _ptr(self.elem_class), _ptr(scale),
+                _ptr(u), _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def e2n_wsum(self, w):
+        out = torch.empty(self.n_nodes, dtype=F64, device="cuda")
+        _lib.check(self.lib.sktb_e2n_wsum(self.handle, _ptr(w), _ptr(out), _stream()))
+        return out
+
+    def e2n(self, w, val, design_u8, fixed_value, wsum, out=None):
+        if out is None:
+            out = torch.empty(self.n_nodes, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_e2n(
+                self.handle, _ptr(w), _ptr(val), _ptr(design_u8), float(fixed_value),
+                _ptr(wsum), _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def n2e_mean(self, x, clamp_max0=False, out=None):
+        if out is None:
+            out = torch.empty(self.n_elem, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_n2e_mean(self.handle, _ptr(x), int(bool(clamp_max0)), _ptr(out), _stream())
+        )
+        return out
+
+
+_MESH_CACHE: dict = {}
+
+
+def device_mesh(mesh) -> DeviceMesh:
+    """One DeviceMesh per host mesh object (keyed by identity, kept alive)."""
+    key = id(mesh)
+    ent = _MESH_CACHE.get(key)
+    if ent is None or ent[0] is not mesh:
+        ent = (mesh, DeviceMesh(mesh))
+        _MESH_CACHE[key] = ent
+    return ent[1]
+
+
+# ---------------------------------------------------------------- CSR / PCG --
+def spmv(row_ptr, col_idx, vals, x, dpn_hint, out=None):
+    n = row_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(n, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_spmv(n, dpn_hint, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(x), _ptr(out), _stream())
+    )
+    return out
+
+
+def csr_enforce(row_ptr, col_idx, vals, mask_u8):
+    n = row_ptr.numel() - 1
+    _lib.check(
+        _lib.load().sktb_csr_enforce(n, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(mask_u8), _stream())
+    )
+    return vals
+
+
+def csr_inv_diag(row_ptr, col_idx, vals, out=None):
+    n = row_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(n, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_csr_inv_diag(n, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(out), _stream())
+    )
+    return out
+
+
+class PcgSolver:
+    """Device-resident Jacobi-PCG workspace (``sktb_pcg``)."""
+
+    def __init__(self, n_rows: int, device: int | None = None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.n = int(n_rows)
+        dev = torch.cuda.current_device() if device is None else device
+        h = C.c_void_p()
+        _lib.check(self.lib.sktb_pcg_create(C.byref(h), self.n, dev))
+        self.handle = h
+        self.last_iters = 0
+        self.last_converged = True
+        self.last_relres = 0.0
+        self.total_iters = 0
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_pcg_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def solve(self, row_ptr, col_idx, vals, inv_diag, b, x, dpn_hint, rtol=1e-8,
+              maxiter=1000, use_x0=False, check_every=32):
+        info = (C.c_int32 * 2)()
+        relres = C.c_double()
+        _lib.check(
+            self.lib.sktb_pcg_solve(
+                self.handle, dpn_hint, _ptr(row_ptr), _ptr(col_idx), _ptr(vals),
+                _ptr(inv_diag), _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
+                int(maxiter), int(check_every), C.cast(info, C.c_void_p),
+                C.cast(C.byref(relres), C.c_void_p), _stream(),
+            )
+        )
+        self.last_iters = int(info[0])
+        self.last_converged = bool(info[1])
+        self.last_relres = float(relres.value)
+        self.total_iters += self.last_iters
+        return x
+
+
+# ------------------------------------------------------- elementwise kernels --
+def interpolate_modulus(rho, E0, Emin, p, ramp=False, out=None):
+    if out is None:
+        out = torch.empty_like(rho)
+    _lib.check(
+        _lib.load().sktb_interpolate_modulus(rho.numel(), _ptr(rho), float(E0), float(Emin), float(p), int(ramp), _ptr(out), _stream())
+    )
+    return out
+
+
+def dc_drho(rho_proj, energy, E0, Emin, p, ramp=False, dH=None, out=None):
+    if out is None:
+        out = torch.empty_like(rho_proj)
+    _lib.check(
+        _lib.load().sktb_dc_drho(rho_proj.numel(), _ptr(rho_proj), _ptr(energy), float(E0), float(Emin), float(p), int(ramp), _ptr(dH), _ptr(out), _stream())
+    )
+    return out
+
+
+def heaviside(x, beta, eta, out=None, dH=None):
+    _lib.check(
+        _lib.load().sktb_heaviside(x.numel(), _ptr(x), float(beta), float(eta), _ptr(out), _ptr(dH), _stream())
+    )
+    return out, dH
+
+
+def oc_candidate(dC, rho_e, lmid, eps, eta, move_limit, rho_min, rho_max, sr_min,
+                 sr_max, design_idx, scaling_rate, rho_cand, rho_full_cand):
+    _lib.check(
+        _lib.load().sktb_oc_candidate(
+            dC.numel(), _ptr(dC), _ptr(rho_e), float(lmid), float(eps), float(eta),
+            float(move_limit), float(rho_min), float(rho_max), float(sr_min),
+            float(sr_max), _ptr(design_idx), _ptr(scaling_rate), _ptr(rho_cand),
+            _ptr(rho_full_cand), _stream(),
+        )
+    )
+
+
+def logmoc_update(rho, dL, eta, move_limit, rho_min, rho_max, clip, scaling_rate,
+                  clip_lower, clip_upper):
+    _lib.check(
+        _lib.load().sktb_logmoc_update(
+            rho.numel(), _ptr(rho), _ptr(dL), float(eta), float(move_limit),
+            float(rho_min), float(rho_max), float(clip), _ptr(scaling_rate),
+            _ptr(clip_lower), _ptr(clip_upper), _stream(),
+        )
+    )
+
+
+def reduce_wsum(a, idx=None, w=None) -> float:
+    n = idx.numel() if idx is not None else a.numel()
+    out = C.c_double()
+    _lib.check(
+        _lib.load().sktb_reduce_wsum_h(n, _ptr(a), _ptr(idx), _ptr(w), C.cast(C.byref(out), C.c_void_p), _stream())
+    )
+    return float(out.value)
+
+
+def reduce_stats(a, idx=None):
+    """(min, mean, max, std) of a[idx]."""
+    n = idx.numel() if idx is not None else a.numel()
+    out = (C.c_double * 4)()
+    _lib.check(
+        _lib.load().sktb_reduce_stats_h(n, _ptr(a), _ptr(idx), C.cast(out, C.c_void_p), _stream())
+    )
+    return float(out[0]), float(out[1]), float(out[2]), float(out[3])
+
+
+def reduce_absmax(a) -> float:
+    out = C.c_double()
+    _lib.check(
+        _lib.load().sktb_reduce_absmax_h(a.numel(), _ptr(a), C.cast(C.byref(out), C.c_void_p), _stream())
+    )
+    return float(out.value)
+
+
+def dot(a, b) -> float:
+    out = C.c_double()
+    _lib.check(
+        _lib.load().sktb_dot_h(a.numel(), _ptr(a), _ptr(b), C.cast(C.byref(out), C.c_void_p), _stream())
+    )
+    return float(out.value)
+
+
+_PCT_WORK: dict = {}
+
+
+def abs_percentile(a, q: float) -> float:
+    n = a.numel()
+    key = (a.device.index, n)
+    work = _PCT_WORK.get(key)
+    if work is None:
+        work = torch.empty(n + 1024, dtype=torch.int64, device="cuda")
+        _PCT_WORK.clear()
+        _PCT_WORK[key] = work
+    out = C.c_double()
+    _lib.check(
+        _lib.load().sktb_abs_percentile_h(n, _ptr(a), float(q), _ptr(work), C.cast(C.byref(out), C.c_void_p), _stream())
+    )
+    return float(out.value)
+
+
+def gather(src, idx, out=None):
+    if out is None:
+        out = torch.empty(idx.numel(), dtype=F64, device="cuda")
+    _lib.check(_lib.load().sktb_gather(idx.numel(), _ptr(src), _ptr(idx), _ptr(out), _stream()))
+    return out
+
+
+def scatter(src, idx, dst):
+    _lib.check(_lib.load().sktb_scatter(idx.numel(), _ptr(src), _ptr(idx), _ptr(dst), _stream()))
+    return dst
+
+
+def axpby(a, x, b, y):
+    _lib.check(_lib.load().sktb_axpby(x.numel(), float(a), _ptr(x), float(b), _ptr(y), _stream()))
+    return y
+
+
+def affine(a, x, b, y, c, out):
+    """out = a*x + b*y + c  (y may be None)."""
+    _lib.check(
+        _lib.load().sktb_affine(x.numel(), float(a), _ptr(x), float(b), _ptr(y), float(c), _ptr(out), _stream())
+    )
+    return out
+
+
+def hadamard(a, x, y, out):
+    """out = a*x*y."""
+    _lib.check(_lib.load().sktb_hadamard(x.numel(), float(a), _ptr(x), _ptr(y), _ptr(out), _stream()))
+    return out
+
+
+def kkt_residual(rho, g, dv, coef, lo, hi):
+    """(max |g + coef*dv| over lo < rho < hi, count of interior entries)."""
+    out = (C.c_double * 2)()
+    _lib.check(
+        _lib.load().sktb_kkt_residual_h(rho.numel(), _ptr(rho), _ptr(g), _ptr(dv), float(coef), float(lo), float(hi), C.cast(out, C.c_void_p), _stream())
+    )
+    return float(out[0]), int(out[1])
+
+
+def reduce_maxdiff(a, b, idx=None) -> float:
+    n = idx.numel() if idx is not None else a.numel()
+    out = C.c_double()
+    _lib.check(
+        _lib.load().sktb_reduce_maxdiff_h(n, _ptr(a), _ptr(b), _ptr(idx), C.cast(C.byref(out), C.c_void_p), _stream())
+    )
+    return float(out.value)
+
+
+def enforce_rhs(b, t, mask_u8, xD, out=None):
+    if out is None:
+        out = torch.empty_like(b)
+    _lib.check(
+        _lib.load().sktb_enforce_rhs(b.numel(), _ptr(b), _ptr(t), _ptr(mask_u8), _ptr(xD), _ptr(out), _stream())
+    )
+    return out
+
+
+def flush_l2(scratch):
+    _lib.check(_lib.load().sktb_flush_l2(_ptr(scratch), scratch.numel() * scratch.element_size(), _stream()))

@@ -1,0 +1,98 @@
+"""ctypes binding of ``libsktopt_b200.so`` (C ABI in ``include/sktopt_b200.h``).
+
+There is no CPU fallback: if the shared library is missing the import of any
+GPU entry point raises, and every call checks the status code and raises
+``RuntimeError`` with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsktopt_b200.so")
+
+_lib = None
+
+c_i32p = C.c_void_p
+c_f64p = C.c_void_p
+c_u8p = C.c_void_p
+c_stream = C.c_void_p
+i64 = C.c_int64
+f64 = C.c_double
+i32 = C.c_int
+
+# name -> argtypes (restype is int unless listed in _RESTYPE)
+SIGNATURES = {
+    "sktb_last_error": [],
+    "sktb_version": [],
+    "sktb_mesh_create": [C.POINTER(C.c_void_p), i32, i64, i64, C.c_void_p, C.c_void_p, i32],
+    "sktb_mesh_destroy": [C.c_void_p],
+    "sktb_mesh_node_nnz": [C.c_void_p],
+    "sktb_mesh_node_graph_h": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "sktb_mesh_dof_pattern": [C.c_void_p, i32, c_i32p, c_i32p, c_stream],
+    "sktb_unit_ke": [C.c_void_p, i32, f64, i32, C.c_void_p, C.c_void_p, i64, C.c_void_p, c_f64p, c_stream],
+    "sktb_assemble": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_u8p, c_f64p, c_stream],
+    "sktb_csr_enforce": [i64, c_i32p, c_i32p, c_f64p, c_u8p, c_stream],
+    "sktb_csr_inv_diag": [i64, c_i32p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_spmv": [i64, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_pcg_create": [C.POINTER(C.c_void_p), i64, i32],
+    "sktb_pcg_destroy": [C.c_void_p],
+    "sktb_pcg_solve": [C.c_void_p, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
+    "sktb_interpolate_modulus": [i64, c_f64p, f64, f64, f64, i32, c_f64p, c_stream],
+    "sktb_element_energy": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_dc_drho": [i64, c_f64p, c_f64p, f64, f64, f64, i32, c_f64p, c_f64p, c_stream],
+    "sktb_heaviside": [i64, c_f64p, f64, f64, c_f64p, c_f64p, c_stream],
+    "sktb_e2n": [C.c_void_p, c_f64p, c_f64p, c_u8p, f64, c_f64p, c_f64p, c_stream],
+    "sktb_e2n_wsum": [C.c_void_p, c_f64p, c_f64p, c_stream],
+    "sktb_n2e_mean": [C.c_void_p, c_f64p, i32, c_f64p, c_stream],
+    "sktb_oc_candidate": [i64, c_f64p, c_f64p, f64, f64, f64, f64, f64, f64, f64, f64, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_logmoc_update": [i64, c_f64p, c_f64p, f64, f64, f64, f64, f64, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_reduce_wsum_h": [i64, c_f64p, c_i32p, c_f64p, C.c_void_p, c_stream],
+    "sktb_reduce_stats_h": [i64, c_f64p, c_i32p, C.c_void_p, c_stream],
+    "sktb_reduce_absmax_h": [i64, c_f64p, C.c_void_p, c_stream],
+    "sktb_dot_h": [i64, c_f64p, c_f64p, C.c_void_p, c_stream],
+    "sktb_abs_percentile_h": [i64, c_f64p, f64, C.c_void_p, C.c_void_p, c_stream],
+    "sktb_gather": [i64, c_f64p, c_i32p, c_f64p, c_stream],
+    "sktb_scatter": [i64, c_f64p, c_i32p, c_f64p, c_stream],
+    "sktb_axpby": [i64, f64, c_f64p, f64, c_f64p, c_stream],
+    "sktb_affine": [i64, f64, c_f64p, f64, c_f64p, f64, c_f64p, c_stream],
+    "sktb_hadamard": [i64, f64, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_kkt_residual_h": [i64, c_f64p, c_f64p, c_f64p, f64, f64, f64, C.c_void_p, c_stream],
+    "sktb_reduce_maxdiff_h": [i64, c_f64p, c_f64p, c_i32p, C.c_void_p, c_stream],
+    "sktb_enforce_rhs": [i64, c_f64p, c_f64p, c_u8p, c_f64p, c_f64p, c_stream],
+    "sktb_flush_l2": [C.c_void_p, i64, c_stream],
+}
+_RESTYPE = {
+    "sktb_last_error": C.c_char_p,
+    "sktb_mesh_destroy": None,
+    "sktb_pcg_destroy": None,
+    "sktb_mesh_node_nnz": C.c_int64,
+}
+
+
+def load():
+    """Load the shared library (once) and declare every signature."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `make -C scikit-topt_b200/csrc` "
+            "(or __graft_entry__.build()); there is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().sktb_last_error()
+        raise RuntimeError(
+            f"sktopt_b200: {msg.decode() if msg else 'unknown error'} (status {rc})"
+        )

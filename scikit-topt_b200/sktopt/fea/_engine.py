@@ -1,0 +1,109 @@
+"""Device-resident state of one FEA problem (mesh x physics x Dirichlet set).
+
+This is the glue between the reference-shaped Python API in ``solver_elastic``
+/ ``solver_heat`` and the kernels: it owns the CSR pattern, the value buffer,
+the Jacobi diagonal, the PCG workspace and the per-load solution vectors that
+are reused as warm starts.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from sktopt._b200 import device as dev
+from sktopt.tools.logconf import mylogger
+
+logger = mylogger(__name__)
+
+KE_ELASTIC, KE_LAPLACE, KE_MASS = 0, 1, 2
+
+
+def default_maxiter(n_dof: int) -> int:
+    """Jacobi-PCG needs more iterations than the reference's AMG-PCG budget
+    (``fea/solver_elastic.py:201-204``: min(1000, max(300, n_dof//5))); the
+    converged solution is the same, so the cap is only a safety net."""
+    return int(max(2000, min(60000, 40 * round(n_dof ** (1.0 / 3.0)) + 2000)))
+
+
+class FeaEngine:
+    def __init__(self, basis, dirichlet_dofs, kind: int, nu: float = 0.0):
+        dev.require_cuda()
+        self.basis = basis
+        self.kind = kind
+        self.dpn = 3 if kind == KE_ELASTIC else 1
+        self.dm = dev.device_mesh(basis.mesh)
+        self.n_dof = self.dpn * self.dm.n_nodes
+        self.n_elem = self.dm.n_elem
+        self.row_ptr, self.col_idx = self.dm.dof_pattern(self.dpn)
+        self.unit_ke = self.dm.unit_ke(kind, basis.X, basis.W, nu=nu)
+        mask = np.zeros(self.n_dof, dtype=np.uint8)
+        if dirichlet_dofs is not None and len(dirichlet_dofs):
+            mask[np.asarray(dirichlet_dofs, dtype=np.int64)] = 1
+        self.dir_mask = dev.to_dev(mask, dev.U8)
+        self.has_dirichlet = bool(mask.any())
+        nnz = self.dpn * self.dpn * self.dm.node_nnz
+        self.vals = torch.empty(nnz, dtype=dev.F64, device="cuda")
+        self.inv_diag = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
+        self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
+        self.rhs = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
+        self.pcg = dev.PcgSolver(self.n_dof)
+        self.u = {}  # load index -> device solution (warm start)
+        self.warm_start = True
+        self.pcg_log = []  # (iters, converged, relres) of every solve
+
+    # ------------------------------------------------------------------
+    def set_modulus(self, rho, c_max, c_min, p, ramp=False):
+        dev.interpolate_modulus(rho, c_max, c_min, p, ramp=ramp, out=self.scale)
+        return self.scale
+
+    def assemble(self, enforce: bool = True, out=None):
+        """K = sum_e scale_e Ke0_e (Dirichlet rows/cols as identity if enforce)."""
+        mask = self.dir_mask if (enforce and self.has_dirichlet) else None
+        return self.dm.assemble(self.dpn, self.unit_ke, scale=self.scale,
+                                dir_mask=mask, out=self.vals if out is None else out)
+
+    def update_preconditioner(self, vals=None):
+        dev.csr_inv_diag(self.row_ptr, self.col_idx,
+                         self.vals if vals is None else vals, out=self.inv_diag)
+
+    def solution(self, load: int):
+        if load not in self.u:
+            self.u[load] = torch.zeros(self.n_dof, dtype=dev.F64, device="cuda")
+        return self.u[load]
+
+    def solve(self, rhs, load: int, rtol: float, maxiter: int | None, vals=None):
+        """PCG on the enforced system; returns the device solution vector."""
+        x = self.solution(load)
+        mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
+        self.pcg.solve(self.row_ptr, self.col_idx,
+                       self.vals if vals is None else vals, self.inv_diag, rhs, x,
+                       dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
+                       use_x0=self.warm_start, check_every=32)
+        self.pcg_log.append((self.pcg.last_iters, self.pcg.last_converged,
+                             self.pcg.last_relres))
+        if not self.pcg.last_converged:
+            logger.warning(
+                f"PCG stopped at {self.pcg.last_iters} iterations with "
+                f"relres={self.pcg.last_relres:.3e} (rtol={rtol:g})")
+        return x
+
+    def spmv(self, x, vals=None, out=None):
+        return dev.spmv(self.row_ptr, self.col_idx,
+                        self.vals if vals is None else vals, x, self.dpn, out=out)
+
+    def energy(self, u, out=None):
+        return self.dm.element_energy(self.dpn, self.unit_ke, self.scale, u, out=out)
+
+
+_ENGINES: dict = {}
+
+
+def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0) -> FeaEngine:
+    d = None if dirichlet_dofs is None else np.asarray(dirichlet_dofs, dtype=np.int64)
+    key = (id(basis), kind, float(nu),
+           None if d is None else (d.size, int(d.sum()) if d.size else 0))
+    ent = _ENGINES.get(key)
+    if ent is None or ent[0] is not basis:
+        ent = (basis, FeaEngine(basis, d, kind, nu))
+        _ENGINES[key] = ent
+    return ent[1]
