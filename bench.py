@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: optimiser iterations / second on the 1M-element 3D
+cantilever (BASELINE.json configs[1]: log-space MOC, vol frac 0.3, one B200),
+plus the achieved HBM bandwidth of the PCG SpMV against the measured roofline.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one full optimiser iteration (filter -> assemble -> PCG solve ->
+element energy -> sensitivity -> filter adjoint -> LogMOC update) with export
+ticks switched off.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "scikit-topt_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "optimizer iters/sec on 1M-elem 3D cantilever; PCG SpMV HBM GB/s vs peak"
+UNIT = "iters/s"
+C2_MESH_SIZE = 0.0577          # toy_base(0.0577): 139x104x70 = 1,011,920 hex
+CPU_SAMPLE_MESH_SIZE = 0.2     # toy1_fine: 40x30x20 = 24,000 hex (largest mesh the reference defines)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------- CPU legs --
+def cpu_oracle_step_rate(steps: int, warmup: int, mesh_size: float):
+    """The oracle port of the reference path (NumPy/SciPy, scipy cg + Jacobi,
+    splu Helmholtz filter) running full LogMOC iterations on a bounded sample
+    mesh.  Returns (iters/s on the sample, n_elem_sample, seconds per step)."""
+    from oracle import mesh as omesh, optim
+    o = omesh.toy_base(mesh_size)
+    pr = optim.Problem(o["p"], o["t"], o["dirichlet_dofs"], o["force"], o["design"],
+                       o["pinned"], o["volumes"], o["E"], o["nu"], fixed=o["fixed"])
+    total = max(1, steps + warmup)
+    tm = []
+
+    # optim.run has no per-step hook: run (warmup) and (warmup+steps) iterations
+    # of the same deterministic loop and difference the wall clock
+    def timed(n):
+        t0 = time.perf_counter()
+        optim.run(pr, "logmoc", max_iters=200, iters=n, vol_frac=0.3,
+                  solver="cg_jacobi", rtol=1e-8, cg_maxiter=20000)
+        return time.perf_counter() - t0
+    t_w = timed(warmup) if warmup > 0 else 0.0
+    t_all = timed(total)
+    dt = (t_all - t_w) / max(1, steps)
+    tm.append(dt)
+    return 1.0 / dt, int(o["t"].shape[1]), dt
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on the host cores (the reference itself
+    cannot be imported here: scikit-fem / pyamg are not installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_c2 = 1011920
+    rate, n_s, dt = cpu_oracle_step_rate(args.steps, args.warmup, args.cpu_mesh_size)
+    value = rate * n_s / n_c2
+    sample = (f"oracle LogMOC iteration (scipy cg+Jacobi rtol 1e-8, splu Helmholtz filter) on "
+              f"toy_base({args.cpu_mesh_size}) = {n_s} hex ({dt:.2f} s/step), scaled linearly in "
+              f"element count to {n_c2} hex (optimistic for the CPU: CG iterations also grow "
+              f"with mesh size); scipy is single-threaded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: 3D cantilever 1,011,920 hex, LogMOC, vol_frac 0.3",
+                   "sample_mesh_size": args.cpu_mesh_size},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------- GPU arm --
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import sktopt
+    from sktopt._b200 import device as dev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tsk = sktopt.mesh.toy_problem.toy_base(args.mesh_size)
+    tmp = tempfile.mkdtemp(prefix="sktopt_bench_")
+    cfg = sktopt.core.LogMOC_Config(
+        dst_path=tmp, max_iters=200, record_times=20,
+        vol_frac=sktopt.tools.SchedulerConfig.constant(target_value=0.3),
+        solver_option="cg_pyamg",
+    )
+    opt = sktopt.core.LogMOC_Optimizer(cfg, tsk)
+    opt.parameterize()
+    opt.export_enabled = False
+    eng = opt.fem.engine
+    n_elem, n_dof, nnz = eng.n_elem, eng.n_dof, int(eng.vals.numel())
+
+    # pinned host buffers of the per-step API edge
+    rho_h = torch.empty(n_elem, dtype=torch.float64).pin_memory()
+    out_h = torch.empty(n_elem, dtype=torch.float64).pin_memory()
+
+    if args.warmup > 0:
+        opt.optimize_steps(args.warmup)
+    opt._ensure_state_initialized()
+    st = opt._state
+    rho_h.copy_(st.rho)
+    eng.pcg.set_profile(2)
+    n_solves0 = len(eng.pcg_log)
+    launches0 = dev.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_step = 0.0
+    t_e2e = 0.0
+    comp_last = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        st.rho.copy_(rho_h, non_blocking=True)          # H2D of the step's input
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        opt.optimize_steps(1)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        out_h.copy_(st.rho, non_blocking=True)          # D2H of the step's result
+        torch.cuda.synchronize()
+        comp_last = float(st.compliance)
+        rho_h.copy_(out_h)
+        t3 = time.perf_counter()
+        t_step += t2 - t1
+        t_e2e += t3 - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = dev.launch_count() - launches0
+    spmv_ms_sum, spmv_n = eng.pcg.get_profile()
+    pcg_iters = [l[0] for l in eng.pcg_log[n_solves0:]]
+
+    times = torch.tensor([t_step, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_step, t_e2e = float(times[0]), float(times[1])
+    # independent replicas for N > 1 (the sharded PCG is not built yet)
+    value = world * args.steps / t_step
+    e2e = world * args.steps / t_e2e
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        spmv_bytes = nnz * 12 + n_dof * 12 + n_dof * 8
+        spmv_ms = spmv_ms_sum / max(spmv_n, 1)
+        achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_step / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
+                "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
+                "solver": "device Jacobi-PCG rtol 1e-8, warm start",
+                "pcg_iters_per_step": pcg_iters,
+                "l2": "inputs larger than L2 (CSR 3.0 GB >> 126 MB)",
+                "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                "last_compliance": comp_last,
+            },
+            "roofline": {
+                "bound": "hbm", "kernel": "spmv_kernel<32,3,true> (PCG q=Ap + p.q)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None,
+                "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+                "peak_source": peak_src, "alg_bytes_per_launch": spmv_bytes,
+                "avg_launch_ms": spmv_ms, "samples": spmv_n, "traffic": traffic,
+            },
+            "e2e": {"value": e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": n_elem * 8, "d2h_bytes_per_step": n_elem * 8 + 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            rate, n_s, dt = cpu_oracle_step_rate(1, 0, args.cpu_mesh_size)
+            line["cpu_baseline"] = {
+                "value": rate * n_s / n_elem, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": (f"oracle LogMOC iteration on toy_base({args.cpu_mesh_size}) = {n_s} hex "
+                           f"({dt:.2f} s/step, scipy cg+Jacobi, splu filter), scaled linearly in "
+                           f"element count to {n_elem} hex (optimistic for the CPU)"),
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mesh-size", type=float, default=C2_MESH_SIZE)
+    ap.add_argument("--cpu-mesh-size", type=float, default=CPU_SAMPLE_MESH_SIZE)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

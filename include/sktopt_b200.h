@@ -38,6 +38,8 @@ extern "C" {
 
 const char *sktb_last_error(void);
 int sktb_version(void);
+/* number of kernels this library has launched in the calling process          */
+int64_t sktb_launch_count(void);
 
 /* ------------------------------------------------------------------ mesh --
  * Connectivity-derived structures shared by every operator on one mesh:
@@ -112,6 +114,13 @@ int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
                    const double *inv_diag, const double *b, double *x,
                    int use_x0, double rtol, int maxiter, int check_every,
                    int32_t *info_h, double *relres_h, void *stream);
+
+/* In-situ timing of the dominant kernel: with every_n > 0 the SpMV launch of
+ * the first iteration of every every_n-th batch is bracketed by CUDA events on
+ * the solver's stream; get_profile returns the accumulated milliseconds and
+ * the number of samples since the last set_profile.                          */
+int sktb_pcg_set_profile(sktb_pcg *s, int every_n);
+int sktb_pcg_get_profile(const sktb_pcg *s, double *ms_sum_h, int64_t *count_h);
 
 /* ------------------------------------------------------ element kernels ---*/
 /* K1: E = Emin + (E0-Emin) rho^p (fea/composer.py:19-22); ramp != 0 gives

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <cstdio>
 #include <string>
 
@@ -20,7 +21,22 @@ void set_error(const std::string &msg);
     }                                                                        \
   } while (0)
 
+// every kernel launch of the library is counted (sktb_launch_count)
+extern std::atomic<long long> g_launch_count;
+#define SKTB_COUNT(k) sktb::g_launch_count.fetch_add((k), std::memory_order_relaxed)
+
 #define SKTB_KERNEL_OK()                                                     \
+  do {                                                                       \
+    SKTB_COUNT(1);                                                           \
+    cudaError_t _e = cudaGetLastError();                                     \
+    if (_e != cudaSuccess) {                                                 \
+      sktb::set_error(std::string("kernel launch: ") +                       \
+                      cudaGetErrorString(_e));                               \
+      return 1;                                                              \
+    }                                                                        \
+  } while (0)
+
+#define SKTB_KERNEL_CHECK()                                                  \
   do {                                                                       \
     cudaError_t _e = cudaGetLastError();                                     \
     if (_e != cudaSuccess) {                                                 \

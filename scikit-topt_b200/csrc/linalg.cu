@@ -229,7 +229,38 @@ struct sktb_pcg {
   PcgScalars *S_h = nullptr;  // pinned host
   double *partials = nullptr;
   unsigned int *ticket = nullptr;
+  // optional in-situ timing of the SpMV launches (every `prof_every`-th
+  // iteration gets a CUDA-event pair on the solver's stream)
+  int prof_every = 0;
+  static constexpr int kMaxProf = 64;
+  cudaEvent_t ev0[kMaxProf], ev1[kMaxProf];
+  bool ev_init = false;
+  double prof_ms = 0.0;
+  long long prof_count = 0;
 };
+
+extern "C" int sktb_pcg_set_profile(sktb_pcg *s, int every_n) {
+  SKTB_REQUIRE(s, "null argument");
+  if (every_n > 0 && !s->ev_init) {
+    for (int i = 0; i < sktb_pcg::kMaxProf; ++i) {
+      SKTB_CUDA_OK(cudaEventCreate(&s->ev0[i]));
+      SKTB_CUDA_OK(cudaEventCreate(&s->ev1[i]));
+    }
+    s->ev_init = true;
+  }
+  s->prof_every = every_n;
+  s->prof_ms = 0.0;
+  s->prof_count = 0;
+  return 0;
+}
+
+extern "C" int sktb_pcg_get_profile(const sktb_pcg *s, double *ms_sum_h,
+                                    int64_t *count_h) {
+  SKTB_REQUIRE(s && ms_sum_h && count_h, "null argument");
+  *ms_sum_h = s->prof_ms;
+  *count_h = s->prof_count;
+  return 0;
+}
 
 extern "C" int sktb_pcg_create(sktb_pcg **out, int64_t n_rows, int device) {
   SKTB_REQUIRE(out && n_rows > 0, "bad argument");
@@ -385,24 +416,41 @@ extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
   SKTB_KERNEL_OK();
   int launched = 0;
   bool done = false;
+  int n_ev = 0;
   while (!done) {
     SKTB_CUDA_OK(cudaMemcpyAsync(s->S_h, s->S, sizeof(PcgScalars),
                                  cudaMemcpyDeviceToHost, st));
     SKTB_CUDA_OK(cudaStreamSynchronize(st));
+    // events of the previous batch are complete now; a sampled SpMV that ran
+    // as a no-op (after convergence) is recognised by iteration index
+    for (int i = 0; i < n_ev; ++i) {
+      float ms = 0.f;
+      SKTB_CUDA_OK(cudaEventElapsedTime(&ms, s->ev0[i], s->ev1[i]));
+      s->prof_ms += ms;
+      s->prof_count += 1;
+    }
+    n_ev = 0;
     if (s->S_h->rr <= s->S_h->tol2 || launched >= maxiter) break;
     int batch = maxiter - launched;
     if (batch > check_every) batch = check_every;
     for (int it = 0; it < batch; ++it) {
+      // sample only the first iteration of a batch: it is certain to do work
+      const bool sample = s->prof_every > 0 && it == 0 &&
+                          ((launched / check_every) % s->prof_every == 0) &&
+                          n_ev < sktb_pcg::kMaxProf;
+      if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev0[n_ev], st));
       if (launch_spmv(n, dpn_hint, row_ptr, col_idx, vals, s->p, s->q, s->p,
                       &rs, &s->S->pq, s->S, st))
         return 1;
+      if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev1[n_ev++], st));
       pcg_update_kernel<<<vgrid, kBlock, 0, st>>>(n, s->p, s->q, inv_diag, x,
                                                  s->r, s->z, s->partials,
                                                  s->ticket, s->S);
       pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, s->p, s->ticket,
                                                     s->S);
+      SKTB_COUNT(2);
     }
-    SKTB_KERNEL_OK();
+    SKTB_KERNEL_CHECK();
     launched += batch;
   }
   const PcgScalars &h = *s->S_h;

@@ -13,6 +13,7 @@ namespace sktb {
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
+std::atomic<long long> g_launch_count{0};
 
 static std::mutex g_scratch_mu;
 static ReduceScratch g_scratch[16];
@@ -63,6 +64,9 @@ struct sktb_mesh {
 
 extern "C" const char *sktb_last_error(void) { return sktb::g_err.c_str(); }
 extern "C" int sktb_version(void) { return 100; }
+extern "C" int64_t sktb_launch_count(void) {
+  return (int64_t)sktb::g_launch_count.load();
+}
 
 template <typename T>
 static int upload(T **dst, const std::vector<T> &src) {

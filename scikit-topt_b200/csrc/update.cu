@@ -384,6 +384,7 @@ extern "C" int sktb_reduce_stats_h(int64_t n, const double *a,
   stats2_kernel<<<grid_for(n), kBlock, 0, st>>>(n, a, idx, rs->result,
                                                 rs->partials, rs->ticket,
                                                 rs->result + 3);
+  SKTB_COUNT(1);
   SKTB_KERNEL_OK();
   double r[4];
   if (fetch_result(rs, 4, r, st)) return 1;
@@ -557,6 +558,7 @@ extern "C" int sktb_abs_percentile_h(int64_t n, const double *a, double q,
   }
   select_next_kernel<<<grid, kBlock, 0, st>>>(n, keys, state, rs->partials,
                                               rs->ticket, rs->result);
+  SKTB_COUNT(17);
   SKTB_KERNEL_OK();
   unsigned long long kth_bits = 0;
   SKTB_CUDA_OK(cudaMemcpyAsync(&kth_bits, &state->prefix, sizeof(kth_bits),

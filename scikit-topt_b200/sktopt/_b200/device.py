@@ -278,6 +278,19 @@ class PcgSolver:
                 pass
             self.handle = None
 
+    def set_profile(self, every_n: int):
+        _lib.check(self.lib.sktb_pcg_set_profile(self.handle, int(every_n)))
+
+    def get_profile(self):
+        """(sum of sampled SpMV durations in ms, number of samples)."""
+        ms = C.c_double()
+        cnt = C.c_int64()
+        _lib.check(
+            self.lib.sktb_pcg_get_profile(
+                self.handle, C.cast(C.byref(ms), C.c_void_p), C.cast(C.byref(cnt), C.c_void_p))
+        )
+        return float(ms.value), int(cnt.value)
+
     def solve(self, row_ptr, col_idx, vals, inv_diag, b, x, dpn_hint, rtol=1e-8,
               maxiter=1000, use_x0=False, check_every=32):
         info = (C.c_int32 * 2)()
@@ -455,6 +468,11 @@ def enforce_rhs(b, t, mask_u8, xD, out=None):
         _lib.load().sktb_enforce_rhs(b.numel(), _ptr(b), _ptr(t), _ptr(mask_u8), _ptr(xD), _ptr(out), _stream())
     )
     return out
+
+
+def launch_count() -> int:
+    """Kernels launched by libsktopt_b200 in this process so far."""
+    return int(_lib.load().sktb_launch_count())
 
 
 def flush_l2(scratch):

@@ -38,6 +38,9 @@ SIGNATURES = {
     "sktb_spmv": [i64, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_create": [C.POINTER(C.c_void_p), i64, i32],
     "sktb_pcg_destroy": [C.c_void_p],
+    "sktb_pcg_set_profile": [C.c_void_p, i32],
+    "sktb_pcg_get_profile": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "sktb_launch_count": [],
     "sktb_pcg_solve": [C.c_void_p, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_interpolate_modulus": [i64, c_f64p, f64, f64, f64, i32, c_f64p, c_stream],
     "sktb_element_energy": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
@@ -68,6 +71,7 @@ _RESTYPE = {
     "sktb_mesh_destroy": None,
     "sktb_pcg_destroy": None,
     "sktb_mesh_node_nnz": C.c_int64,
+    "sktb_launch_count": C.c_int64,
 }
 
 

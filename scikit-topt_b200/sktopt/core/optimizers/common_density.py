@@ -258,6 +258,9 @@ class DensityMethod(DensityMethodBase):
         self._iter_next: int | None = None
         self._iter_end: int | None = None
         self._completed = False
+        # export ticks (checkpoint npz, recorder print) can be switched off by a
+        # driver that times the loop itself (metric excludes them)
+        self.export_enabled = True
         # device index sets (fixed once the design set is final)
         self._design_idx = _idx(tsk.design_elements)
         pin = tsk.neumann_elements if cfg.design_dirichlet else tsk.dirichlet_neumann_elements
@@ -580,8 +583,9 @@ class DensityMethod(DensityMethodBase):
                 or iter_num == iter_limit - 1
             )
             if export_now:
-                with self._timed_section("export_iteration"):
-                    self._export_iteration(iter_num, st, st.energy_mean)
+                if self.export_enabled:
+                    with self._timed_section("export_iteration"):
+                        self._export_iteration(iter_num, st, st.energy_mean)
                 if conv_rho and conv_kkt:
                     converged = True
                     break
