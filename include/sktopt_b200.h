@@ -158,6 +158,42 @@ int sktb_e2n_wsum(const sktb_mesh *m, const double *w, double *out,
 int sktb_n2e_mean(const sktb_mesh *m, const double *x, int clamp_max0,
                   double *out, void *stream);
 
+/* ------------------------------------------------- heat: Robin terms -------
+ * K16/K17 (fea/solver_heat.py:552-625,723-745,928-980).
+ * Quadrature tables per geometry class (what Basis.interpolate evaluates):
+ * N[cls][q][a], physical gradients G[cls][q][a][3], dx[cls][q] = w_q |det J|. */
+int sktb_geom_tables(const sktb_mesh *m, int nqp, const double *X_h,
+                     const double *W_h, int64_t n_class,
+                     const int32_t *class_rep_h, double *N_out, double *G_out,
+                     double *dx_out, void *stream);
+/* Mq[cls][q][a][b] = dx_q N_a N_b  (unit matrices of the virtual Robin form)  */
+int sktb_unit_qp_mass(const sktb_mesh *m, int nqp, int64_t n_class,
+                      const double *N_tab, const double *dx_tab, double *out,
+                      void *stream);
+/* s[q][e] = h rho_q^p (1-rho_q)^q |grad rho_q|, rho interpolated from nodal
+ * values (get_robin_virtual, fea/solver_heat.py:552-572)                      */
+int sktb_robin_virtual_scale(const sktb_mesh *m, int nqp,
+                             const int32_t *elem_class, const double *N_tab,
+                             const double *G_tab, const double *dx_tab,
+                             const double *rho_node, double h, double p,
+                             double q, double *out, void *stream);
+/* scalar gather assembly with n_terms (scale[k][e], unit[cls][k][a][b]) terms */
+int sktb_assemble_terms(const sktb_mesh *m, int n_terms, const double *unit,
+                        const int32_t *elem_class, const double *scale,
+                        double *vals, void *stream);
+/* element-local vectors of _robin_compliance_explicit_grad_
+ * (fea/solver_heat.py:575-597): out_local[a][e]                               */
+int sktb_robin_explicit_local(const sktb_mesh *m, int nqp,
+                              const int32_t *elem_class, const double *N_tab,
+                              const double *G_tab, const double *dx_tab,
+                              const double *rho_node, const double *T, double h,
+                              double T_env, double p, double q,
+                              double *out_local, void *stream);
+/* out[n] = sum over the node's (element, local) slots of local[a][e]
+ * (optionally divided by divisor[n]): load-vector style assembly              */
+int sktb_local_to_nodes(const sktb_mesh *m, const double *local,
+                        const double *divisor, double *out, void *stream);
+
 /* ------------------------------------------------------ update kernels ----*/
 /* K12: OC candidate (core/optimizers/oc.py:50-68).  rho_e, dC over design
  * elements; writes scaling_rate, rho_cand (design) and scatters rho_cand into

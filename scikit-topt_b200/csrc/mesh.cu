@@ -636,3 +636,358 @@ extern "C" int sktb_n2e_mean(const sktb_mesh *m, const double *x,
   SKTB_KERNEL_OK();
   return 0;
 }
+
+// ===================================================================== heat --
+// Per-class quadrature tables: N[q][a], physical gradients G[q][a][3] and
+// dx[q] = w_q |det J_q|  (what skfem's Basis.interpolate / asm evaluate).
+template <int NEN>
+__global__ void geom_tables_kernel(int nqp, const double *__restrict__ Xq,
+                                   const double *__restrict__ Wq,
+                                   const int32_t *__restrict__ class_rep,
+                                   const int32_t *__restrict__ conn,
+                                   int64_t n_elem,
+                                   const double *__restrict__ coords,
+                                   int64_t n_nodes, double *__restrict__ Nout,
+                                   double *__restrict__ Gout,
+                                   double *__restrict__ dxout) {
+  __shared__ double xe[NEN][3];
+  const int64_t cls = blockIdx.x;
+  const int64_t el = class_rep[cls];
+  if (threadIdx.x < NEN * 3) {
+    int a = threadIdx.x / 3, d = threadIdx.x % 3;
+    xe[a][d] = coords[(int64_t)d * n_nodes + conn[(int64_t)a * n_elem + el]];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < nqp; q += blockDim.x) {
+    const double X = Xq[q], Y = Xq[nqp + q], Z = Xq[2 * nqp + q];
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double Nv[NEN], dNv[NEN][3];
+#pragma unroll
+    for (int v = 0; v < NEN; ++v) {
+      if (NEN == 8)
+        hex_shape(v, X, Y, Z, Nv[v], dNv[v]);
+      else
+        tet_shape(v, X, Y, Z, Nv[v], dNv[v]);
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) J[d][k] += xe[v][d] * dNv[v][k];
+    }
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double id = 1.0 / det;
+    double iJ[3][3];
+    iJ[0][0] = c00 * id;
+    iJ[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    iJ[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    iJ[1][0] = c01 * id;
+    iJ[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    iJ[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    iJ[2][0] = c02 * id;
+    iJ[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    iJ[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    double *Nq = Nout + (cls * nqp + q) * NEN;
+    double *Gq = Gout + (cls * nqp + q) * NEN * 3;
+#pragma unroll
+    for (int v = 0; v < NEN; ++v) {
+      Nq[v] = Nv[v];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        Gq[v * 3 + d] =
+            dNv[v][0] * iJ[0][d] + dNv[v][1] * iJ[1][d] + dNv[v][2] * iJ[2][d];
+    }
+    dxout[cls * nqp + q] = Wq[q] * fabs(det);
+  }
+}
+
+extern "C" int sktb_geom_tables(const sktb_mesh *m, int nqp, const double *X_h,
+                                const double *W_h, int64_t n_class,
+                                const int32_t *class_rep_h, double *N_out,
+                                double *G_out, double *dx_out, void *stream) {
+  SKTB_REQUIRE(m && X_h && W_h && class_rep_h && N_out && G_out && dx_out,
+               "null argument");
+  SKTB_REQUIRE(nqp > 0 && n_class > 0, "empty quadrature or class list");
+  cudaStream_t st = (cudaStream_t)stream;
+  double *Xd = nullptr, *Wd = nullptr;
+  int32_t *rep = nullptr;
+  SKTB_CUDA_OK(cudaMalloc(&Xd, sizeof(double) * 3 * nqp));
+  SKTB_CUDA_OK(cudaMalloc(&Wd, sizeof(double) * nqp));
+  SKTB_CUDA_OK(cudaMalloc(&rep, sizeof(int32_t) * n_class));
+  SKTB_CUDA_OK(cudaMemcpyAsync(Xd, X_h, sizeof(double) * 3 * nqp,
+                               cudaMemcpyHostToDevice, st));
+  SKTB_CUDA_OK(cudaMemcpyAsync(Wd, W_h, sizeof(double) * nqp,
+                               cudaMemcpyHostToDevice, st));
+  SKTB_CUDA_OK(cudaMemcpyAsync(rep, class_rep_h, sizeof(int32_t) * n_class,
+                               cudaMemcpyHostToDevice, st));
+  if (m->nen == 8)
+    geom_tables_kernel<8><<<(unsigned)n_class, 64, 0, st>>>(
+        nqp, Xd, Wd, rep, m->conn, m->n_elem, m->coords, m->n_nodes, N_out,
+        G_out, dx_out);
+  else
+    geom_tables_kernel<4><<<(unsigned)n_class, 32, 0, st>>>(
+        nqp, Xd, Wd, rep, m->conn, m->n_elem, m->coords, m->n_nodes, N_out,
+        G_out, dx_out);
+  SKTB_KERNEL_OK();
+  SKTB_CUDA_OK(cudaStreamSynchronize(st));
+  cudaFree(Xd);
+  cudaFree(Wd);
+  cudaFree(rep);
+  return 0;
+}
+
+// K16a: per (quadrature point, element) weight of the virtual Robin forms
+//   s = h rho^p (1-rho)^q |grad rho| dx,  rho interpolated from nodal values
+// and, if local_load != NULL, nothing else (the load is T_env * V * 1).
+template <int NEN>
+__global__ void __launch_bounds__(kBlock)
+    robin_virtual_scale_kernel(int64_t n_elem, int nqp,
+                               const int32_t *__restrict__ conn,
+                               const int32_t *__restrict__ elem_class,
+                               const double *__restrict__ Ntab,
+                               const double *__restrict__ Gtab,
+                               const double *__restrict__ dxtab,
+                               const double *__restrict__ rho_n, double h,
+                               double p, double q, double *__restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < n_elem; e += stride) {
+    double r[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) r[a] = rho_n[conn[(int64_t)a * n_elem + e]];
+    const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
+    for (int k = 0; k < nqp; ++k) {
+      const double *Nq = Ntab + (cls * nqp + k) * NEN;
+      const double *Gq = Gtab + (cls * nqp + k) * NEN * 3;
+      double rq = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        rq += __ldg(&Nq[a]) * r[a];
+        g0 += __ldg(&Gq[a * 3 + 0]) * r[a];
+        g1 += __ldg(&Gq[a * 3 + 1]) * r[a];
+        g2 += __ldg(&Gq[a * 3 + 2]) * r[a];
+      }
+      const double iface = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+      out[(int64_t)k * n_elem + e] = h * pow(rq, p) * pow(1.0 - rq, q) * iface;
+    }
+  }
+}
+
+extern "C" int sktb_robin_virtual_scale(const sktb_mesh *m, int nqp,
+                                        const int32_t *elem_class,
+                                        const double *N_tab,
+                                        const double *G_tab,
+                                        const double *dx_tab,
+                                        const double *rho_node, double h,
+                                        double p, double q, double *out,
+                                        void *stream) {
+  SKTB_REQUIRE(m && N_tab && G_tab && dx_tab && rho_node && out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(m->n_elem);
+  if (m->nen == 8)
+    robin_virtual_scale_kernel<8><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, h,
+        p, q, out);
+  else
+    robin_virtual_scale_kernel<4><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, h,
+        p, q, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// unit per-quadrature-point mass matrices  Mq[cls][q][a][b] = dx_q N_a N_b
+__global__ void unit_qp_mass_kernel(int64_t total, int nqp, int nen,
+                                    const double *__restrict__ Ntab,
+                                    const double *__restrict__ dxtab,
+                                    double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int b = i % nen;
+    const int a = (i / nen) % nen;
+    const int64_t cq = i / (nen * nen);  // cls*nqp + q
+    out[i] = dxtab[cq] * Ntab[cq * nen + a] * Ntab[cq * nen + b];
+  }
+}
+
+extern "C" int sktb_unit_qp_mass(const sktb_mesh *m, int nqp, int64_t n_class,
+                                 const double *N_tab, const double *dx_tab,
+                                 double *out, void *stream) {
+  SKTB_REQUIRE(m && N_tab && dx_tab && out, "null argument");
+  const int64_t total = n_class * nqp * m->nen * m->nen;
+  unit_qp_mass_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(
+      total, nqp, m->nen, N_tab, dx_tab, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// K16b: scalar gather assembly with several (scale, unit matrix) terms per
+// element: vals = sum_e sum_k scale[k][e] * unit[cls(e)][k][a][b]
+template <int NEN>
+__global__ void __launch_bounds__(kBlock)
+    assemble_terms_kernel(int64_t n_nodes, int64_t n_elem, int n_terms,
+                          const int32_t *__restrict__ node_ptr,
+                          const int32_t *__restrict__ pair_ptr,
+                          const int32_t *__restrict__ contrib_elem,
+                          const uint8_t *__restrict__ contrib_ab,
+                          const int32_t *__restrict__ elem_class,
+                          const double *__restrict__ unit,
+                          const double *__restrict__ scale,
+                          double *__restrict__ vals) {
+  int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_pairs = node_ptr[n_nodes];
+  for (; pair < n_pairs; pair += stride) {
+    double acc = 0.0;
+    const int32_t c1 = pair_ptr[pair + 1];
+    for (int32_t c = pair_ptr[pair]; c < c1; ++c) {
+      const int32_t el = contrib_elem[c];
+      const int ab = contrib_ab[c];
+      const int64_t cls = elem_class ? (int64_t)elem_class[el] : (int64_t)el;
+      const double *u = unit + cls * n_terms * (NEN * NEN) + ab;
+      for (int k = 0; k < n_terms; ++k)
+        acc += scale[(int64_t)k * n_elem + el] * __ldg(&u[k * (NEN * NEN)]);
+    }
+    vals[pair] = acc;
+  }
+}
+
+extern "C" int sktb_assemble_terms(const sktb_mesh *m, int n_terms,
+                                   const double *unit,
+                                   const int32_t *elem_class,
+                                   const double *scale, double *vals,
+                                   void *stream) {
+  SKTB_REQUIRE(m && unit && scale && vals && n_terms > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(m->node_nnz, kBlock, 16);
+  if (m->nen == 8)
+    assemble_terms_kernel<8><<<grid, kBlock, 0, st>>>(
+        m->n_nodes, m->n_elem, n_terms, m->node_ptr, m->pair_ptr,
+        m->contrib_elem, m->contrib_ab, elem_class, unit, scale, vals);
+  else
+    assemble_terms_kernel<4><<<grid, kBlock, 0, st>>>(
+        m->n_nodes, m->n_elem, n_terms, m->node_ptr, m->pair_ptr,
+        m->contrib_elem, m->contrib_ab, elem_class, unit, scale, vals);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// K17a: element-local contributions of the explicit Robin sensitivity form
+//   r_e[a] = sum_q dx h ( da |g| phi N_a + a phi (g / max(|g|,1e-12)) . G_a )
+//   a = rho^p (1-rho)^q, da = d a / d rho, phi = 2 T_env T - T^2
+template <int NEN>
+__global__ void __launch_bounds__(kBlock)
+    robin_explicit_local_kernel(int64_t n_elem, int nqp,
+                                const int32_t *__restrict__ conn,
+                                const int32_t *__restrict__ elem_class,
+                                const double *__restrict__ Ntab,
+                                const double *__restrict__ Gtab,
+                                const double *__restrict__ dxtab,
+                                const double *__restrict__ rho_n,
+                                const double *__restrict__ T, double h,
+                                double T_env, double p, double q,
+                                double *__restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < n_elem; e += stride) {
+    double r[NEN], t[NEN], acc[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) {
+      const int32_t nd = conn[(int64_t)a * n_elem + e];
+      r[a] = rho_n[nd];
+      t[a] = T[nd];
+      acc[a] = 0.0;
+    }
+    const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
+    for (int k = 0; k < nqp; ++k) {
+      const double *Nq = Ntab + (cls * nqp + k) * NEN;
+      const double *Gq = Gtab + (cls * nqp + k) * NEN * 3;
+      const double dx = dxtab[cls * nqp + k];
+      double rq = 0.0, tq = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        const double Na = __ldg(&Nq[a]);
+        rq += Na * r[a];
+        tq += Na * t[a];
+        g0 += __ldg(&Gq[a * 3 + 0]) * r[a];
+        g1 += __ldg(&Gq[a * 3 + 1]) * r[a];
+        g2 += __ldg(&Gq[a * 3 + 2]) * r[a];
+      }
+      const double iface = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+      const double safe = fmax(iface, 1e-12);
+      const double av = pow(rq, p) * pow(1.0 - rq, q);
+      const double da = p * pow(rq, p - 1.0) * pow(1.0 - rq, q) -
+                        q * pow(rq, p) * pow(1.0 - rq, q - 1.0);
+      const double phi = 2.0 * T_env * tq - tq * tq;
+      const double c0 = da * iface * phi;
+      const double c1 = av * phi / safe;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        const double gv = g0 * __ldg(&Gq[a * 3 + 0]) + g1 * __ldg(&Gq[a * 3 + 1]) +
+                          g2 * __ldg(&Gq[a * 3 + 2]);
+        acc[a] += h * (c0 * __ldg(&Nq[a]) + c1 * gv) * dx;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) out[(int64_t)a * n_elem + e] = acc[a];
+  }
+}
+
+extern "C" int sktb_robin_explicit_local(const sktb_mesh *m, int nqp,
+                                         const int32_t *elem_class,
+                                         const double *N_tab,
+                                         const double *G_tab,
+                                         const double *dx_tab,
+                                         const double *rho_node,
+                                         const double *T, double h,
+                                         double T_env, double p, double q,
+                                         double *out_local, void *stream) {
+  SKTB_REQUIRE(m && N_tab && G_tab && dx_tab && rho_node && T && out_local,
+               "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(m->n_elem);
+  if (m->nen == 8)
+    robin_explicit_local_kernel<8><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, T,
+        h, T_env, p, q, out_local);
+  else
+    robin_explicit_local_kernel<4><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, T,
+        h, T_env, p, q, out_local);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// K17b: nodal sum of element-local vectors local[a][e] (deterministic gather)
+__global__ void __launch_bounds__(kBlock)
+    local_to_nodes_kernel(int64_t n_nodes, int64_t n_elem,
+                          const int32_t *__restrict__ n2e_ptr,
+                          const int32_t *__restrict__ n2e_elem,
+                          const uint8_t *__restrict__ n2e_loc,
+                          const double *__restrict__ local,
+                          const double *__restrict__ divisor,
+                          double *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n_nodes; i += stride) {
+    double acc = 0.0;
+    const int32_t k1 = n2e_ptr[i + 1];
+    for (int32_t k = n2e_ptr[i]; k < k1; ++k)
+      acc += local[(int64_t)n2e_loc[k] * n_elem + n2e_elem[k]];
+    out[i] = divisor ? acc / divisor[i] : acc;
+  }
+}
+
+extern "C" int sktb_local_to_nodes(const sktb_mesh *m, const double *local,
+                                   const double *divisor, double *out,
+                                   void *stream) {
+  SKTB_REQUIRE(m && local && out, "null argument");
+  local_to_nodes_kernel<<<grid_for(m->n_nodes), kBlock, 0,
+                          (cudaStream_t)stream>>>(
+      m->n_nodes, m->n_elem, m->n2e_ptr, m->n2e_elem, m->n2e_loc, local,
+      divisor, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}

@@ -186,6 +186,79 @@ class DeviceMesh:
         )
         return out
 
+    # -- heat: quadrature tables and Robin kernels -----------------------------
+    def geom_tables(self, X: np.ndarray, W: np.ndarray):
+        """(N [cls,q,a], G [cls,q,a,3], dx [cls,q]) CUDA tensors."""
+        key = ("geom", X.shape[1], float(W.sum()), float(X.sum()))
+        if key not in self._unit_ke:
+            nq = int(X.shape[1])
+            N = torch.empty((self.n_class, nq, self.nen), dtype=F64, device="cuda")
+            G = torch.empty((self.n_class, nq, self.nen, 3), dtype=F64, device="cuda")
+            dx = torch.empty((self.n_class, nq), dtype=F64, device="cuda")
+            Xc = np.ascontiguousarray(X, dtype=np.float64)
+            Wc = np.ascontiguousarray(W, dtype=np.float64)
+            _lib.check(
+                self.lib.sktb_geom_tables(
+                    self.handle, nq, Xc.ctypes.data_as(C.c_void_p),
+                    Wc.ctypes.data_as(C.c_void_p), self.n_class,
+                    self.class_rep_h.ctypes.data_as(C.c_void_p), _ptr(N), _ptr(G),
+                    _ptr(dx), _stream(),
+                )
+            )
+            Mq = torch.empty((self.n_class, nq, self.nen, self.nen), dtype=F64, device="cuda")
+            _lib.check(
+                self.lib.sktb_unit_qp_mass(self.handle, nq, self.n_class, _ptr(N), _ptr(dx), _ptr(Mq), _stream())
+            )
+            self._unit_ke[key] = (N, G, dx, Mq)
+        return self._unit_ke[key]
+
+    def robin_virtual_scale(self, tables, rho_node, h, p, q, out=None):
+        N, G, dx, _ = tables
+        nq = N.shape[1]
+        if out is None:
+            out = torch.empty((nq, self.n_elem), dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_robin_virtual_scale(
+                self.handle, nq, _ptr(self.elem_class), _ptr(N), _ptr(G), _ptr(dx),
+                _ptr(rho_node), float(h), float(p), float(q), _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def assemble_terms(self, unit, scale, out=None):
+        n_terms = scale.shape[0]
+        if out is None:
+            out = torch.empty(self.node_nnz, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_assemble_terms(
+                self.handle, int(n_terms), _ptr(unit), _ptr(self.elem_class), _ptr(scale),
+                _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def robin_explicit_local(self, tables, rho_node, T, h, T_env, p, q, out=None):
+        N, G, dx, _ = tables
+        nq = N.shape[1]
+        if out is None:
+            out = torch.empty((self.nen, self.n_elem), dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_robin_explicit_local(
+                self.handle, nq, _ptr(self.elem_class), _ptr(N), _ptr(G), _ptr(dx),
+                _ptr(rho_node), _ptr(T), float(h), float(T_env), float(p), float(q),
+                _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def local_to_nodes(self, local, divisor=None, out=None):
+        if out is None:
+            out = torch.empty(self.n_nodes, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_local_to_nodes(self.handle, _ptr(local), _ptr(divisor), _ptr(out), _stream())
+        )
+        return out
+
     def e2n_wsum(self, w):
         out = torch.empty(self.n_nodes, dtype=F64, device="cuda")
         _lib.check(self.lib.sktb_e2n_wsum(self.handle, _ptr(w), _ptr(out), _stream()))

@@ -49,6 +49,12 @@ SIGNATURES = {
     "sktb_e2n": [C.c_void_p, c_f64p, c_f64p, c_u8p, f64, c_f64p, c_f64p, c_stream],
     "sktb_e2n_wsum": [C.c_void_p, c_f64p, c_f64p, c_stream],
     "sktb_n2e_mean": [C.c_void_p, c_f64p, i32, c_f64p, c_stream],
+    "sktb_geom_tables": [C.c_void_p, i32, C.c_void_p, C.c_void_p, i64, C.c_void_p, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_unit_qp_mass": [C.c_void_p, i32, i64, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_robin_virtual_scale": [C.c_void_p, i32, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, f64, f64, f64, c_f64p, c_stream],
+    "sktb_assemble_terms": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_robin_explicit_local": [C.c_void_p, i32, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, f64, f64, f64, f64, c_f64p, c_stream],
+    "sktb_local_to_nodes": [C.c_void_p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_oc_candidate": [i64, c_f64p, c_f64p, f64, f64, f64, f64, f64, f64, f64, f64, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_logmoc_update": [i64, c_f64p, c_f64p, f64, f64, f64, f64, f64, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_reduce_wsum_h": [i64, c_f64p, c_i32p, c_f64p, C.c_void_p, c_stream],
