@@ -115,6 +115,47 @@ int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
                    int use_x0, double rtol, int maxiter, int check_every,
                    int32_t *info_h, double *relres_h, void *stream);
 
+/* -------------------------------------------------- multi-GPU --
+ * Row-sharded operator: rank r owns the rows of the contiguous node range
+ * [node_begin, node_end) (its dofs [dpn*node_begin, dpn*node_end)); column
+ * indices stay global.  The reference has no distributed code (PETSc objects
+ * live on COMM_SELF, fea/solver_petsc.py:143,157); this is the B200 addition. */
+int sktb_mesh_dof_pattern_rows(const sktb_mesh *m, int dpn, int64_t node_begin,
+                               int64_t node_end, int32_t *row_ptr,
+                               int32_t *col_idx, void *stream);
+int sktb_assemble_rows(const sktb_mesh *m, int dpn, int64_t node_begin,
+                       int64_t node_end, const double *unit_ke,
+                       const int32_t *elem_class, const double *scale,
+                       const uint8_t *dir_mask, double *vals, void *stream);
+int sktb_csr_inv_diag_rows(int64_t n_rows, int64_t row0, const int32_t *row_ptr,
+                           const int32_t *col_idx, const double *vals,
+                           double *out, void *stream);
+/* NCCL communicator (one process per GPU); id128_h = 128-byte ncclUniqueId
+ * created on rank 0 by sktb_comm_unique_id and shipped by the host launcher.  */
+typedef struct sktb_comm sktb_comm;
+int sktb_comm_unique_id(void *id128_h);
+int sktb_comm_create(sktb_comm **out, const void *id128_h, int rank, int world,
+                     int device);
+void sktb_comm_destroy(sktb_comm *c);
+int sktb_comm_rank(const sktb_comm *c);
+int sktb_comm_world(const sktb_comm *c);
+int sktb_comm_allreduce_sum(sktb_comm *c, const double *src, double *dst,
+                            int64_t count, void *stream);
+/* in-place all-gather of contiguous slices buf[displs[r] .. +counts[r])        */
+int sktb_comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts_h,
+                         const int64_t *displs_h, void *stream);
+/* PCG workspace for the rows [row0, row0+n_local) of an n_global system.  The
+ * halo is described per peer: send_idx_h[send_off_h[i]..send_off_h[i+1]) are
+ * the global indices of owned entries peer i needs, recv_idx_h[...] the global
+ * indices received from it (ghost slots of the full-length direction vector).
+ * sktb_pcg_solve then takes local row_ptr/vals/inv_diag/b/x and global col_idx;
+ * dot products are all-reduced in the stream (2 all-reduces per iteration).    */
+int sktb_pcg_create_dist(sktb_pcg **out, sktb_comm *comm, int64_t n_global,
+                         int64_t row0, int64_t n_local, int n_peers,
+                         const int32_t *peers_h, const int64_t *send_off_h,
+                         const int32_t *send_idx_h, const int64_t *recv_off_h,
+                         const int32_t *recv_idx_h, int device);
+
 /* In-situ timing of the dominant kernel: with every_n > 0 the SpMV launch of
  * the first iteration of every every_n-th batch is bracketed by CUDA events on
  * the solver's stream; get_profile returns the accumulated milliseconds and

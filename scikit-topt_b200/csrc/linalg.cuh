@@ -1,0 +1,25 @@
+// Internal interface between the SpMV kernels (linalg.cu) and the PCG driver
+// (pcg.cu).
+#pragma once
+#include "common.cuh"
+
+// Device-resident CG scalars.  Kernels read the (global) values from `S` and
+// publish their (rank-local) sums into `Sloc`; on one GPU both are the same
+// struct, on several GPUs an all-reduce copies Sloc -> S.
+struct PcgScalars {
+  double rz;       // r.z of the current iterate
+  double pq;       // p.Ap
+  double rz_new;   // r.z after the update
+  double rr;       // ||r||^2
+  double tol2;     // (rtol*||b||)^2
+  double bb;       // ||b||^2
+  int iters;       // completed iterations
+  int pad;
+};
+
+// y = A x (+ optional dot with dotv published to *dot_out); no-op once S says
+// the solve has converged.
+int launch_spmv(int64_t n_rows, int dpn_hint, const int32_t *row_ptr,
+                const int32_t *col_idx, const double *vals, const double *x,
+                double *y, const double *dotv, sktb::ReduceScratch *rs,
+                double *dot_out, const PcgScalars *S, cudaStream_t st);

@@ -223,21 +223,26 @@ extern "C" int sktb_mesh_node_graph_h(const sktb_mesh *m, int32_t *row_ptr_h,
 }
 
 // ------------------------------------------------------------ dof pattern --
+// rows of the nodes [n_begin, n_end); row_ptr / col_idx are local to that range
 template <int D>
 __global__ void __launch_bounds__(kBlock)
-    dof_pattern_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr,
+    dof_pattern_kernel(int64_t n_begin, int64_t n_end,
+                       const int32_t *__restrict__ node_ptr,
                        const int32_t *__restrict__ node_col,
                        int32_t *__restrict__ row_ptr,
                        int32_t *__restrict__ col_idx) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t n = warp; n < n_nodes; n += nwarps) {
+  const int64_t off = (int64_t)D * D * node_ptr[n_begin];
+  for (int64_t n = n_begin + warp; n < n_end; n += nwarps) {
     const int32_t s = node_ptr[n], deg = node_ptr[n + 1] - s;
-    const int64_t base = (int64_t)D * D * s;
-    if (lane < D) row_ptr[D * n + lane] = (int32_t)(base + (int64_t)lane * D * deg);
-    if (n == n_nodes - 1 && lane == 0)
-      row_ptr[D * n_nodes] = (int32_t)((int64_t)D * D * node_ptr[n_nodes]);
+    const int64_t base = (int64_t)D * D * s - off;
+    if (lane < D)
+      row_ptr[D * (n - n_begin) + lane] = (int32_t)(base + (int64_t)lane * D * deg);
+    if (n == n_end - 1 && lane == 0)
+      row_ptr[D * (n_end - n_begin)] =
+          (int32_t)((int64_t)D * D * node_ptr[n_end] - off);
     for (int e = lane; e < D * D * deg; e += 32) {
       int q = e % (D * deg);
       col_idx[base + e] = D * node_col[s + q / D] + (q % D);
@@ -252,14 +257,30 @@ extern "C" int sktb_mesh_dof_pattern(const sktb_mesh *m, int dpn,
   SKTB_REQUIRE(dpn == 1 || dpn == 3, "dpn must be 1 or 3");
   SKTB_REQUIRE((int64_t)dpn * dpn * m->node_nnz < (int64_t)2147483647,
                "nnz exceeds int32 CSR indexing");
+  return sktb_mesh_dof_pattern_rows(m, dpn, 0, m->n_nodes, row_ptr, col_idx,
+                                    stream);
+}
+
+extern "C" int sktb_mesh_dof_pattern_rows(const sktb_mesh *m, int dpn,
+                                          int64_t node_begin, int64_t node_end,
+                                          int32_t *row_ptr, int32_t *col_idx,
+                                          void *stream) {
+  SKTB_REQUIRE(m && row_ptr && col_idx, "null argument");
+  SKTB_REQUIRE(dpn == 1 || dpn == 3, "dpn must be 1 or 3");
+  SKTB_REQUIRE(0 <= node_begin && node_begin < node_end && node_end <= m->n_nodes,
+               "bad node range");
+  const int64_t nnz_nodes =
+      (int64_t)m->node_ptr_h[node_end] - m->node_ptr_h[node_begin];
+  SKTB_REQUIRE((int64_t)dpn * dpn * nnz_nodes < (int64_t)2147483647,
+               "nnz exceeds int32 CSR indexing");
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = grid_for(m->n_nodes * 32);
+  int grid = grid_for((node_end - node_begin) * 32);
   if (dpn == 1)
-    dof_pattern_kernel<1><<<grid, kBlock, 0, st>>>(m->n_nodes, m->node_ptr,
-                                                   m->node_col, row_ptr, col_idx);
+    dof_pattern_kernel<1><<<grid, kBlock, 0, st>>>(
+        node_begin, node_end, m->node_ptr, m->node_col, row_ptr, col_idx);
   else
-    dof_pattern_kernel<3><<<grid, kBlock, 0, st>>>(m->n_nodes, m->node_ptr,
-                                                   m->node_col, row_ptr, col_idx);
+    dof_pattern_kernel<3><<<grid, kBlock, 0, st>>>(
+        node_begin, node_end, m->node_ptr, m->node_col, row_ptr, col_idx);
   SKTB_KERNEL_OK();
   return 0;
 }
@@ -428,7 +449,8 @@ extern "C" int sktb_unit_ke(const sktb_mesh *m, int kind, double nu, int nqp,
 // produced by a fixed-order gather over its contributor list (no atomics).
 template <int D, int NEN>
 __global__ void __launch_bounds__(kBlock)
-    assemble_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr,
+    assemble_kernel(int64_t n_begin, int64_t n_end,
+                    const int32_t *__restrict__ node_ptr,
                     const int32_t *__restrict__ node_col,
                     const int32_t *__restrict__ pair_ptr,
                     const int32_t *__restrict__ contrib_elem,
@@ -442,9 +464,10 @@ __global__ void __launch_bounds__(kBlock)
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t n = warp; n < n_nodes; n += nwarps) {
+  const int64_t off = (int64_t)D * D * node_ptr[n_begin];
+  for (int64_t n = n_begin + warp; n < n_end; n += nwarps) {
     const int32_t s0 = node_ptr[n], deg = node_ptr[n + 1] - s0;
-    const int64_t base = (int64_t)D * D * s0;
+    const int64_t base = (int64_t)D * D * s0 - off;
     for (int e = lane; e < D * D * deg; e += 32) {
       const int i = e / (D * deg), q = e - i * (D * deg);
       const int s = q / D, j = q - s * D;
@@ -474,14 +497,28 @@ extern "C" int sktb_assemble(const sktb_mesh *m, int dpn, const double *unit_ke,
                              const int32_t *elem_class, const double *scale,
                              const uint8_t *dir_mask, double *vals,
                              void *stream) {
+  SKTB_REQUIRE(m, "null argument");
+  return sktb_assemble_rows(m, dpn, 0, m->n_nodes, unit_ke, elem_class, scale,
+                            dir_mask, vals, stream);
+}
+
+extern "C" int sktb_assemble_rows(const sktb_mesh *m, int dpn,
+                                  int64_t node_begin, int64_t node_end,
+                                  const double *unit_ke,
+                                  const int32_t *elem_class,
+                                  const double *scale, const uint8_t *dir_mask,
+                                  double *vals, void *stream) {
   SKTB_REQUIRE(m && unit_ke && vals, "null argument");
   SKTB_REQUIRE(dpn == 1 || dpn == 3, "dpn must be 1 or 3");
+  SKTB_REQUIRE(0 <= node_begin && node_begin < node_end && node_end <= m->n_nodes,
+               "bad node range");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(m->n_nodes * 32, kBlock, 16);
+  const int grid = grid_for((node_end - node_begin) * 32, kBlock, 16);
 #define LAUNCH(D, NEN)                                                        \
   assemble_kernel<D, NEN><<<grid, kBlock, 0, st>>>(                           \
-      m->n_nodes, m->node_ptr, m->node_col, m->pair_ptr, m->contrib_elem,     \
-      m->contrib_ab, elem_class, unit_ke, scale, dir_mask, vals)
+      node_begin, node_end, m->node_ptr, m->node_col, m->pair_ptr,            \
+      m->contrib_elem, m->contrib_ab, elem_class, unit_ke, scale, dir_mask,   \
+      vals)
   if (m->nen == 8 && dpn == 3)
     LAUNCH(3, 8);
   else if (m->nen == 8 && dpn == 1)
@@ -518,6 +555,11 @@ __global__ void __launch_bounds__(kBlock)
       const int a = lane / D, c = lane - a * D;
       ue = u[(int64_t)D * conn[(int64_t)a * n_elem + e] + c];
     }
+    // the stiffness / conduction element matrices annihilate translations:
+    // subtracting local node 0 removes the cancellation a large mean value
+    // (e.g. T ~ 600 K with 0.1 K variation) would cause in u^T Ke u
+    ue -= __shfl_sync(0xffffffffu, ue, lane % D);
+    if (lane >= NDE) ue = 0.0;
     const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
     const double *ke = unit_ke + cls * (NDE * NDE);
     double acc = 0.0;

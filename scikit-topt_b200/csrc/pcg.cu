@@ -1,0 +1,380 @@
+// Device-resident Jacobi-preconditioned conjugate gradients (K4-K6), on one
+// GPU or row-sharded over several (one process per GPU, NCCL over NVLink).
+//
+// All CG scalars live in device memory.  Kernels read the global values from
+// `S` and publish rank-local sums into `Sloc`; with one GPU both are the same
+// struct, with several an in-stream all-reduce maps Sloc -> S.  Every kernel
+// tests ||r||^2 <= (rtol ||b||)^2 itself and becomes a no-op after
+// convergence (the all-reduce of the unchanged Sloc is then idempotent), so
+// the host polls only every `check_every` iterations and the result is the
+// iterate at which scipy's criterion first holds.
+//
+// Sharding: rank r owns the contiguous rows [row0, row0 + n).  The search
+// direction p is a full-length vector on every rank; before each SpMV the
+// entries other ranks need are packed, exchanged with grouped ncclSend/ncclRecv
+// and scattered into the ghost slots of p.  Matrix column indices stay global.
+#include <vector>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "linalg.cuh"
+
+using namespace sktb;
+
+struct sktb_pcg {
+  int64_t n = 0;         // owned rows
+  int64_t n_global = 0;  // length of p
+  int64_t row0 = 0;
+  int device = 0;
+  double *r = nullptr, *z = nullptr, *p = nullptr, *q = nullptr;
+  PcgScalars *S = nullptr;     // device, global values
+  PcgScalars *Sloc = nullptr;  // device, rank-local sums (== S on one GPU)
+  PcgScalars *S_h = nullptr;   // pinned host
+  double *partials = nullptr;
+  unsigned int *ticket = nullptr;
+  // distributed
+  sktb_comm *comm = nullptr;
+  std::vector<int> peers;
+  std::vector<int64_t> send_off, recv_off;
+  int32_t *send_idx = nullptr, *recv_idx = nullptr;  // device, global indices
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  // in-situ SpMV timing
+  int prof_every = 0;
+  static constexpr int kMaxProf = 64;
+  cudaEvent_t ev0[kMaxProf], ev1[kMaxProf];
+  bool ev_init = false;
+  double prof_ms = 0.0;
+  long long prof_count = 0;
+};
+
+extern "C" int sktb_pcg_set_profile(sktb_pcg *s, int every_n) {
+  SKTB_REQUIRE(s, "null argument");
+  if (every_n > 0 && !s->ev_init) {
+    for (int i = 0; i < sktb_pcg::kMaxProf; ++i) {
+      SKTB_CUDA_OK(cudaEventCreate(&s->ev0[i]));
+      SKTB_CUDA_OK(cudaEventCreate(&s->ev1[i]));
+    }
+    s->ev_init = true;
+  }
+  s->prof_every = every_n;
+  s->prof_ms = 0.0;
+  s->prof_count = 0;
+  return 0;
+}
+
+extern "C" int sktb_pcg_get_profile(const sktb_pcg *s, double *ms_sum_h,
+                                    int64_t *count_h) {
+  SKTB_REQUIRE(s && ms_sum_h && count_h, "null argument");
+  *ms_sum_h = s->prof_ms;
+  *count_h = s->prof_count;
+  return 0;
+}
+
+static int pcg_alloc(sktb_pcg *s) {
+  SKTB_CUDA_OK(cudaMalloc(&s->r, sizeof(double) * s->n));
+  SKTB_CUDA_OK(cudaMalloc(&s->z, sizeof(double) * s->n));
+  SKTB_CUDA_OK(cudaMalloc(&s->q, sizeof(double) * s->n));
+  SKTB_CUDA_OK(cudaMalloc(&s->p, sizeof(double) * s->n_global));
+  SKTB_CUDA_OK(cudaMemset(s->p, 0, sizeof(double) * s->n_global));
+  SKTB_CUDA_OK(cudaMalloc(&s->S, sizeof(PcgScalars)));
+  SKTB_CUDA_OK(cudaMemset(s->S, 0, sizeof(PcgScalars)));
+  SKTB_CUDA_OK(cudaMallocHost(&s->S_h, sizeof(PcgScalars)));
+  SKTB_CUDA_OK(cudaMalloc(&s->partials, sizeof(double) * ReduceScratch::kMaxVals *
+                                            ReduceScratch::kMaxBlocks));
+  SKTB_CUDA_OK(cudaMalloc(&s->ticket, sizeof(unsigned int)));
+  SKTB_CUDA_OK(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
+  s->Sloc = s->S;
+  return 0;
+}
+
+extern "C" int sktb_pcg_create(sktb_pcg **out, int64_t n_rows, int device) {
+  SKTB_REQUIRE(out && n_rows > 0, "bad argument");
+  SKTB_CUDA_OK(cudaSetDevice(device));
+  sktb_pcg *s = new sktb_pcg();
+  s->n = s->n_global = n_rows;
+  s->row0 = 0;
+  s->device = device;
+  if (pcg_alloc(s)) return 1;
+  *out = s;
+  return 0;
+}
+
+extern "C" int sktb_pcg_create_dist(sktb_pcg **out, sktb_comm *comm,
+                                    int64_t n_global, int64_t row0,
+                                    int64_t n_local, int n_peers,
+                                    const int32_t *peers_h,
+                                    const int64_t *send_off_h,
+                                    const int32_t *send_idx_h,
+                                    const int64_t *recv_off_h,
+                                    const int32_t *recv_idx_h, int device) {
+  SKTB_REQUIRE(out && comm && n_local > 0 && row0 >= 0 &&
+                   row0 + n_local <= n_global,
+               "bad argument");
+  SKTB_REQUIRE(n_peers == 0 || (peers_h && send_off_h && recv_off_h),
+               "null halo description");
+  SKTB_CUDA_OK(cudaSetDevice(device));
+  sktb_pcg *s = new sktb_pcg();
+  s->n = n_local;
+  s->n_global = n_global;
+  s->row0 = row0;
+  s->device = device;
+  s->comm = comm;
+  if (pcg_alloc(s)) return 1;
+  SKTB_CUDA_OK(cudaMalloc(&s->Sloc, sizeof(PcgScalars)));
+  SKTB_CUDA_OK(cudaMemset(s->Sloc, 0, sizeof(PcgScalars)));
+  s->peers.assign(peers_h, peers_h + n_peers);
+  s->send_off.assign(send_off_h, send_off_h + n_peers + 1);
+  s->recv_off.assign(recv_off_h, recv_off_h + n_peers + 1);
+  const int64_t ns = n_peers ? s->send_off[n_peers] : 0;
+  const int64_t nr = n_peers ? s->recv_off[n_peers] : 0;
+  SKTB_CUDA_OK(cudaMalloc(&s->send_idx, sizeof(int32_t) * (ns ? ns : 1)));
+  SKTB_CUDA_OK(cudaMalloc(&s->recv_idx, sizeof(int32_t) * (nr ? nr : 1)));
+  SKTB_CUDA_OK(cudaMalloc(&s->sendbuf, sizeof(double) * (ns ? ns : 1)));
+  SKTB_CUDA_OK(cudaMalloc(&s->recvbuf, sizeof(double) * (nr ? nr : 1)));
+  if (ns)
+    SKTB_CUDA_OK(cudaMemcpy(s->send_idx, send_idx_h, sizeof(int32_t) * ns,
+                            cudaMemcpyHostToDevice));
+  if (nr)
+    SKTB_CUDA_OK(cudaMemcpy(s->recv_idx, recv_idx_h, sizeof(int32_t) * nr,
+                            cudaMemcpyHostToDevice));
+  *out = s;
+  return 0;
+}
+
+extern "C" void sktb_pcg_destroy(sktb_pcg *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->r);
+  cudaFree(s->z);
+  cudaFree(s->p);
+  cudaFree(s->q);
+  if (s->Sloc != s->S) cudaFree(s->Sloc);
+  cudaFree(s->S);
+  cudaFreeHost(s->S_h);
+  cudaFree(s->partials);
+  cudaFree(s->ticket);
+  cudaFree(s->send_idx);
+  cudaFree(s->recv_idx);
+  cudaFree(s->sendbuf);
+  cudaFree(s->recvbuf);
+  delete s;
+}
+
+__device__ __forceinline__ bool done(const PcgScalars *S) {
+  return S->rr <= S->tol2;
+}
+
+// r = b - q (q = A x0; r = b when !have_q); z = Minv r; p = z; publishes
+// rz, rr, bb, tol2 (all linear in the local sums, so one all-reduce suffices)
+__global__ void __launch_bounds__(kBlock)
+    pcg_init_kernel(int64_t n, const double *__restrict__ b,
+                    const double *__restrict__ q, int have_q,
+                    const double *__restrict__ minv, double *__restrict__ r,
+                    double *__restrict__ z, double *__restrict__ p,
+                    double *__restrict__ x, double rtol, double *partials,
+                    unsigned int *ticket, PcgScalars *Sloc, PcgScalars *S) {
+  double v[3] = {0.0, 0.0, 0.0};
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double bi = b[i];
+    const double ri = have_q ? bi - q[i] : bi;
+    const double zi = minv[i] * ri;
+    if (!have_q) x[i] = 0.0;
+    r[i] = ri;
+    z[i] = zi;
+    p[i] = zi;
+    v[0] += ri * zi;
+    v[1] += ri * ri;
+    v[2] += bi * bi;
+  }
+  __shared__ double res[3];
+  if (grid_reduce<3>(v, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      Sloc->rz = res[0];
+      Sloc->rr = res[1];
+      Sloc->bb = res[2];
+      Sloc->tol2 = rtol * rtol * res[2];
+      Sloc->pq = 0.0;
+      Sloc->rz_new = res[0];
+      S->iters = 0;
+    }
+  }
+}
+
+// x += a p ; r -= a q ; z = Minv r ; publishes rz_new, rr ; iters++
+__global__ void __launch_bounds__(kBlock)
+    pcg_update_kernel(int64_t n, const double *__restrict__ p,
+                      const double *__restrict__ q,
+                      const double *__restrict__ minv, double *__restrict__ x,
+                      double *__restrict__ r, double *__restrict__ z,
+                      double *partials, unsigned int *ticket, PcgScalars *Sloc,
+                      PcgScalars *S) {
+  if (done(S)) return;
+  const double alpha = S->rz / S->pq;
+  double v[2] = {0.0, 0.0};
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * q[i];
+    const double zi = minv[i] * ri;
+    r[i] = ri;
+    z[i] = zi;
+    v[0] += ri * zi;
+    v[1] += ri * ri;
+  }
+  __shared__ double res[2];
+  if (grid_reduce<2>(v, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      Sloc->rz_new = res[0];
+      Sloc->rr = res[1];
+      S->iters += 1;
+    }
+  }
+}
+
+// p = z + beta p ; the last block rolls rz <- rz_new
+__global__ void __launch_bounds__(kBlock)
+    pcg_direction_kernel(int64_t n, const double *__restrict__ z,
+                         double *__restrict__ p, unsigned int *ticket,
+                         PcgScalars *S) {
+  if (done(S)) return;
+  const double beta = S->rz_new / S->rz;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = z[i] + beta * p[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      S->rz = S->rz_new;
+      *ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    halo_pack_kernel(int64_t n, const int32_t *__restrict__ idx,
+                     const double *__restrict__ p, double *__restrict__ buf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) buf[i] = p[idx[i]];
+}
+__global__ void __launch_bounds__(kBlock)
+    halo_unpack_kernel(int64_t n, const int32_t *__restrict__ idx,
+                       const double *__restrict__ buf, double *__restrict__ p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[idx[i]] = buf[i];
+}
+
+// ghost entries of the full-length vector v <- owners' values
+static int halo_exchange(sktb_pcg *s, double *v, cudaStream_t st) {
+  const int np = (int)s->peers.size();
+  if (!s->comm || np == 0) return 0;
+  const int64_t ns = s->send_off[np], nr = s->recv_off[np];
+  if (ns) {
+    halo_pack_kernel<<<grid_for(ns), kBlock, 0, st>>>(ns, s->send_idx, v,
+                                                     s->sendbuf);
+    SKTB_KERNEL_OK();
+  }
+  if (comm_exchange(s->comm, np, s->peers.data(), s->sendbuf,
+                    s->send_off.data(), s->recvbuf, s->recv_off.data(), st))
+    return 1;
+  if (nr) {
+    halo_unpack_kernel<<<grid_for(nr), kBlock, 0, st>>>(nr, s->recv_idx,
+                                                       s->recvbuf, v);
+    SKTB_KERNEL_OK();
+  }
+  return 0;
+}
+
+static int reduce_scalars(sktb_pcg *s, double *loc, double *glob, int count,
+                          cudaStream_t st) {
+  if (!s->comm) return 0;
+  return comm_allreduce_sum(s->comm, loc, glob, count, st);
+}
+
+extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
+                              const int32_t *col_idx, const double *vals,
+                              const double *inv_diag, const double *b,
+                              double *x, int use_x0, double rtol, int maxiter,
+                              int check_every, int32_t *info_h,
+                              double *relres_h, void *stream) {
+  SKTB_REQUIRE(s && row_ptr && col_idx && vals && inv_diag && b && x,
+               "null argument");
+  SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
+  if (check_every <= 0) check_every = 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = s->n;
+  double *p_own = s->p + s->row0;  // owned slice of the full-length direction
+  ReduceScratch rs;
+  rs.partials = s->partials;
+  rs.ticket = s->ticket;
+  const int vgrid = grid_for(n, kBlock, 8);
+  if (use_x0) {
+    // q = A x0 needs x0 on the ghost slots: stage it through p
+    SKTB_CUDA_OK(cudaMemcpyAsync(p_own, x, sizeof(double) * n,
+                                 cudaMemcpyDeviceToDevice, st));
+    if (halo_exchange(s, s->p, st)) return 1;
+    if (launch_spmv(n, dpn_hint, row_ptr, col_idx, vals, s->p, s->q, nullptr,
+                    nullptr, nullptr, nullptr, st))
+      return 1;
+  }
+  pcg_init_kernel<<<vgrid, kBlock, 0, st>>>(n, b, s->q, use_x0 ? 1 : 0, inv_diag,
+                                           s->r, s->z, p_own, x, rtol,
+                                           s->partials, s->ticket, s->Sloc,
+                                           s->S);
+  SKTB_KERNEL_OK();
+  // rz, pq, rz_new, rr, tol2, bb are the first six doubles of the struct
+  if (reduce_scalars(s, &s->Sloc->rz, &s->S->rz, 6, st)) return 1;
+  int launched = 0;
+  int n_ev = 0;
+  while (true) {
+    SKTB_CUDA_OK(cudaMemcpyAsync(s->S_h, s->S, sizeof(PcgScalars),
+                                 cudaMemcpyDeviceToHost, st));
+    SKTB_CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_ev; ++i) {
+      float ms = 0.f;
+      SKTB_CUDA_OK(cudaEventElapsedTime(&ms, s->ev0[i], s->ev1[i]));
+      s->prof_ms += ms;
+      s->prof_count += 1;
+    }
+    n_ev = 0;
+    if (s->S_h->rr <= s->S_h->tol2 || launched >= maxiter) break;
+    int batch = maxiter - launched;
+    if (batch > check_every) batch = check_every;
+    for (int it = 0; it < batch; ++it) {
+      if (halo_exchange(s, s->p, st)) return 1;
+      // sample only the first iteration of a batch: it is certain to do work
+      const bool sample = s->prof_every > 0 && it == 0 &&
+                          ((launched / check_every) % s->prof_every == 0) &&
+                          n_ev < sktb_pcg::kMaxProf;
+      if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev0[n_ev], st));
+      if (launch_spmv(n, dpn_hint, row_ptr, col_idx, vals, s->p, s->q, p_own,
+                      &rs, &s->Sloc->pq, s->S, st))
+        return 1;
+      if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev1[n_ev++], st));
+      if (reduce_scalars(s, &s->Sloc->pq, &s->S->pq, 1, st)) return 1;
+      pcg_update_kernel<<<vgrid, kBlock, 0, st>>>(n, p_own, s->q, inv_diag, x,
+                                                 s->r, s->z, s->partials,
+                                                 s->ticket, s->Sloc, s->S);
+      if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
+      pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, p_own, s->ticket,
+                                                    s->S);
+      SKTB_COUNT(2);
+    }
+    SKTB_KERNEL_CHECK();
+    launched += batch;
+  }
+  const PcgScalars &h = *s->S_h;
+  if (info_h) {
+    info_h[0] = h.iters;
+    info_h[1] = (h.rr <= h.tol2) ? 1 : 0;
+  }
+  if (relres_h) *relres_h = (h.bb > 0.0) ? sqrt(h.rr / h.bb) : 0.0;
+  return 0;
+}

@@ -143,6 +143,31 @@ class DeviceMesh:
             self._patterns[dpn] = (rp, ci)
         return self._patterns[dpn]
 
+    def dof_pattern_rows(self, dpn: int, n0: int, n1: int):
+        """Local CSR pattern of the rows of nodes [n0, n1) (global columns)."""
+        rp_h, _ = self.node_graph_cached()
+        nnz = dpn * dpn * int(rp_h[n1] - rp_h[n0])
+        rp = torch.empty(dpn * (n1 - n0) + 1, dtype=I32, device="cuda")
+        ci = torch.empty(nnz, dtype=I32, device="cuda")
+        _lib.check(
+            self.lib.sktb_mesh_dof_pattern_rows(self.handle, dpn, int(n0), int(n1), _ptr(rp), _ptr(ci), _stream())
+        )
+        return rp, ci
+
+    def node_graph_cached(self):
+        if getattr(self, "_graph_h", None) is None:
+            self._graph_h = self.node_graph()
+        return self._graph_h
+
+    def assemble_rows(self, dpn, n0, n1, unit_ke, scale=None, dir_mask=None, out=None):
+        _lib.check(
+            self.lib.sktb_assemble_rows(
+                self.handle, dpn, int(n0), int(n1), _ptr(unit_ke), _ptr(self.elem_class),
+                _ptr(scale), _ptr(dir_mask), _ptr(out), _stream(),
+            )
+        )
+        return out
+
     # -- unit element matrices ----------------------------------------------
     def unit_ke(self, kind: int, X: np.ndarray, W: np.ndarray, nu: float = 0.0):
         key = (kind, float(nu), X.shape[1], float(W.sum()), float(X.sum()))
@@ -316,12 +341,12 @@ def csr_enforce(row_ptr, col_idx, vals, mask_u8):
     return vals
 
 
-def csr_inv_diag(row_ptr, col_idx, vals, out=None):
+def csr_inv_diag(row_ptr, col_idx, vals, out=None, row0: int = 0):
     n = row_ptr.numel() - 1
     if out is None:
         out = torch.empty(n, dtype=F64, device="cuda")
     _lib.check(
-        _lib.load().sktb_csr_inv_diag(n, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(out), _stream())
+        _lib.load().sktb_csr_inv_diag_rows(n, int(row0), _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(out), _stream())
     )
     return out
 
@@ -329,13 +354,31 @@ def csr_inv_diag(row_ptr, col_idx, vals, out=None):
 class PcgSolver:
     """Device-resident Jacobi-PCG workspace (``sktb_pcg``)."""
 
-    def __init__(self, n_rows: int, device: int | None = None):
+    def __init__(self, n_rows: int, device: int | None = None, comm=None,
+                 n_global: int | None = None, row0: int = 0, halo=None):
+        """``comm`` / ``n_global`` / ``row0`` / ``halo`` select the row-sharded
+        variant (``sktb_pcg_create_dist``); ``halo`` comes from
+        ``dist.build_halo``."""
         require_cuda()
         self.lib = _lib.load()
         self.n = int(n_rows)
         dev = torch.cuda.current_device() if device is None else device
         h = C.c_void_p()
-        _lib.check(self.lib.sktb_pcg_create(C.byref(h), self.n, dev))
+        if comm is None:
+            _lib.check(self.lib.sktb_pcg_create(C.byref(h), self.n, dev))
+        else:
+            peers, send_off, send_idx, recv_off, recv_idx = halo
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            self._halo_keep = (np.ascontiguousarray(peers, dtype=np.int32),
+                               np.ascontiguousarray(send_off, dtype=np.int64),
+                               np.ascontiguousarray(send_idx, dtype=np.int32),
+                               np.ascontiguousarray(recv_off, dtype=np.int64),
+                               np.ascontiguousarray(recv_idx, dtype=np.int32))
+            pe, so, si, ro, ri = self._halo_keep
+            _lib.check(self.lib.sktb_pcg_create_dist(
+                C.byref(h), comm.handle, int(n_global), int(row0), self.n,
+                int(pe.size), vp(pe), vp(so), vp(si), vp(ro), vp(ri), dev))
+        self.comm = comm
         self.handle = h
         self.last_iters = 0
         self.last_converged = True

@@ -38,6 +38,17 @@ SIGNATURES = {
     "sktb_spmv": [i64, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_create": [C.POINTER(C.c_void_p), i64, i32],
     "sktb_pcg_destroy": [C.c_void_p],
+    "sktb_mesh_dof_pattern_rows": [C.c_void_p, i32, i64, i64, c_i32p, c_i32p, c_stream],
+    "sktb_assemble_rows": [C.c_void_p, i32, i64, i64, c_f64p, c_i32p, c_f64p, c_u8p, c_f64p, c_stream],
+    "sktb_csr_inv_diag_rows": [i64, i64, c_i32p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_comm_unique_id": [C.c_void_p],
+    "sktb_comm_create": [C.POINTER(C.c_void_p), C.c_void_p, i32, i32, i32],
+    "sktb_comm_destroy": [C.c_void_p],
+    "sktb_comm_rank": [C.c_void_p],
+    "sktb_comm_world": [C.c_void_p],
+    "sktb_comm_allreduce_sum": [C.c_void_p, c_f64p, c_f64p, i64, c_stream],
+    "sktb_comm_allgatherv": [C.c_void_p, c_f64p, C.c_void_p, C.c_void_p, c_stream],
+    "sktb_pcg_create_dist": [C.POINTER(C.c_void_p), C.c_void_p, i64, i64, i64, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32],
     "sktb_pcg_set_profile": [C.c_void_p, i32],
     "sktb_pcg_get_profile": [C.c_void_p, C.c_void_p, C.c_void_p],
     "sktb_launch_count": [],
@@ -76,6 +87,7 @@ _RESTYPE = {
     "sktb_last_error": C.c_char_p,
     "sktb_mesh_destroy": None,
     "sktb_pcg_destroy": None,
+    "sktb_comm_destroy": None,
     "sktb_mesh_node_nnz": C.c_int64,
     "sktb_launch_count": C.c_int64,
 }

@@ -4,6 +4,12 @@ This is the glue between the reference-shaped Python API in ``solver_elastic``
 / ``solver_heat`` and the kernels: it owns the CSR pattern, the value buffer,
 the Jacobi diagonal, the PCG workspace and the per-load solution vectors that
 are reused as warm starts.
+
+With a communicator (``torch.distributed`` initialised with more than one
+rank) the operator is row-sharded: this rank assembles and stores only the rows
+of its contiguous node range, the PCG runs distributed (halo exchange + dot
+all-reduces over NCCL) and the solution is all-gathered so that the replicated
+element-wise stages see the full vector.
 """
 from __future__ import annotations
 
@@ -11,6 +17,7 @@ import numpy as np
 import torch
 
 from sktopt._b200 import device as dev
+from sktopt._b200 import dist as bdist
 from sktopt.tools.logconf import mylogger
 
 logger = mylogger(__name__)
@@ -26,30 +33,49 @@ def default_maxiter(n_dof: int) -> int:
 
 
 class FeaEngine:
-    def __init__(self, basis, dirichlet_dofs, kind: int, nu: float = 0.0):
+    def __init__(self, basis, dirichlet_dofs, kind: int, nu: float = 0.0, comm=None):
         dev.require_cuda()
         self.basis = basis
         self.kind = kind
         self.dpn = 3 if kind == KE_ELASTIC else 1
         self.dm = dev.device_mesh(basis.mesh)
-        self.n_dof = self.dpn * self.dm.n_nodes
-        self.n_elem = self.dm.n_elem
-        self.row_ptr, self.col_idx = self.dm.dof_pattern(self.dpn)
-        self.unit_ke = self.dm.unit_ke(kind, basis.X, basis.W, nu=nu)
+        dm, dpn = self.dm, self.dpn
+        self.n_dof = dpn * dm.n_nodes
+        self.n_elem = dm.n_elem
+        self.unit_ke = dm.unit_ke(kind, basis.X, basis.W, nu=nu)
         mask = np.zeros(self.n_dof, dtype=np.uint8)
         if dirichlet_dofs is not None and len(dirichlet_dofs):
             mask[np.asarray(dirichlet_dofs, dtype=np.int64)] = 1
         self.dir_mask = dev.to_dev(mask, dev.U8)
         self.has_dirichlet = bool(mask.any())
-        nnz = self.dpn * self.dpn * self.dm.node_nnz
-        self.vals = torch.empty(nnz, dtype=dev.F64, device="cuda")
-        self.inv_diag = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
+        self.comm = comm
+        if comm is None:
+            self.node0, self.node1 = 0, dm.n_nodes
+            self.row_ptr, self.col_idx = dm.dof_pattern(dpn)
+            self.pcg = dev.PcgSolver(self.n_dof)
+            self.cuts = None
+        else:
+            rp_h, ci_h = dm.node_graph_cached()
+            self.cuts = bdist.partition_nodes(rp_h, comm.world)
+            self.node0, self.node1 = int(self.cuts[comm.rank]), int(self.cuts[comm.rank + 1])
+            self.row_ptr, self.col_idx = dm.dof_pattern_rows(dpn, self.node0, self.node1)
+            halo = bdist.build_halo(rp_h, ci_h, self.cuts, comm.rank, dpn)
+            self.pcg = dev.PcgSolver(dpn * (self.node1 - self.node0), comm=comm,
+                                     n_global=self.n_dof, row0=dpn * self.node0, halo=halo)
+            self.halo_dofs = int(halo[4].size)
+        self.row0 = dpn * self.node0
+        self.n_local = dpn * (self.node1 - self.node0)
+        self.vals = torch.empty(self.col_idx.numel(), dtype=dev.F64, device="cuda")
+        self.inv_diag = torch.empty(self.n_local, dtype=dev.F64, device="cuda")
         self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
         self.rhs = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
-        self.pcg = dev.PcgSolver(self.n_dof)
-        self.u = {}  # load index -> device solution (warm start)
+        self.u = {}  # load index -> device solution (warm start), full length
         self.warm_start = True
         self.pcg_log = []  # (iters, converged, relres) of every solve
+
+    @property
+    def sharded(self) -> bool:
+        return self.comm is not None
 
     # ------------------------------------------------------------------
     def set_modulus(self, rho, c_max, c_min, p, ramp=False):
@@ -57,14 +83,17 @@ class FeaEngine:
         return self.scale
 
     def assemble(self, enforce: bool = True, out=None):
-        """K = sum_e scale_e Ke0_e (Dirichlet rows/cols as identity if enforce)."""
+        """K = sum_e scale_e Ke0_e for the owned rows (Dirichlet rows/cols as
+        identity if enforce)."""
         mask = self.dir_mask if (enforce and self.has_dirichlet) else None
-        return self.dm.assemble(self.dpn, self.unit_ke, scale=self.scale,
-                                dir_mask=mask, out=self.vals if out is None else out)
+        return self.dm.assemble_rows(self.dpn, self.node0, self.node1, self.unit_ke,
+                                     scale=self.scale, dir_mask=mask,
+                                     out=self.vals if out is None else out)
 
     def update_preconditioner(self, vals=None):
         dev.csr_inv_diag(self.row_ptr, self.col_idx,
-                         self.vals if vals is None else vals, out=self.inv_diag)
+                         self.vals if vals is None else vals, out=self.inv_diag,
+                         row0=self.row0)
 
     def solution(self, load: int):
         if load not in self.u:
@@ -72,13 +101,20 @@ class FeaEngine:
         return self.u[load]
 
     def solve(self, rhs, load: int, rtol: float, maxiter: int | None, vals=None):
-        """PCG on the enforced system; returns the device solution vector."""
+        """PCG on the enforced system; ``rhs`` and the returned solution are
+        full-length device vectors (identical on every rank)."""
         x = self.solution(load)
         mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
+        lo, hi = self.row0, self.row0 + self.n_local
         self.pcg.solve(self.row_ptr, self.col_idx,
-                       self.vals if vals is None else vals, self.inv_diag, rhs, x,
+                       self.vals if vals is None else vals, self.inv_diag,
+                       rhs[lo:hi], x[lo:hi],
                        dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
                        use_x0=self.warm_start, check_every=32)
+        if self.sharded:
+            counts = self.dpn * np.diff(self.cuts)
+            displs = self.dpn * self.cuts[:-1]
+            self.comm.allgatherv(x, counts, displs)
         self.pcg_log.append((self.pcg.last_iters, self.pcg.last_converged,
                              self.pcg.last_relres))
         if not self.pcg.last_converged:
@@ -88,6 +124,8 @@ class FeaEngine:
         return x
 
     def spmv(self, x, vals=None, out=None):
+        if self.sharded:
+            raise RuntimeError("full-vector SpMV is not available on a sharded operator")
         return dev.spmv(self.row_ptr, self.col_idx,
                         self.vals if vals is None else vals, x, self.dpn, out=out)
 
@@ -98,12 +136,13 @@ class FeaEngine:
 _ENGINES: dict = {}
 
 
-def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0) -> FeaEngine:
+def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0, shard: bool = True) -> FeaEngine:
     d = None if dirichlet_dofs is None else np.asarray(dirichlet_dofs, dtype=np.int64)
-    key = (id(basis), kind, float(nu),
+    comm = bdist.default_comm() if shard else None
+    key = (id(basis), kind, float(nu), comm is not None,
            None if d is None else (d.size, int(d.sum()) if d.size else 0))
     ent = _ENGINES.get(key)
     if ent is None or ent[0] is not basis:
-        ent = (basis, FeaEngine(basis, d, kind, nu))
+        ent = (basis, FeaEngine(basis, d, kind, nu, comm=comm))
         _ENGINES[key] = ent
     return ent[1]

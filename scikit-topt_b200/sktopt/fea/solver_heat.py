@@ -52,7 +52,9 @@ class _HeatDevice:
         self.task = task
         basis = task.basis
         d_nodes = _as_list(task.dirichlet_nodes)
-        self.eng = get_engine(basis, np.asarray(d_nodes[0], dtype=np.int64), KE_LAPLACE)
+        # the heat operator is replicated on every rank (scalar system, small)
+        self.eng = get_engine(basis, np.asarray(d_nodes[0], dtype=np.int64), KE_LAPLACE,
+                              shard=False)
         eng = self.eng
         dm = eng.dm
         n = eng.n_dof
@@ -173,6 +175,10 @@ class FEM_SimpLinearHeatConduction():
         for i in range(n_loads):
             dev.spmv(eng.row_ptr, eng.col_idx, st.K, st.xD[i], 1, out=st.tmp)
             dev.enforce_rhs(st.emit, st.tmp, eng.dir_mask, st.xD[i], out=eng.rhs)
+            # start from the exact Dirichlet values: their identity rows then
+            # have zero residual for the whole solve (as exact as the LU)
+            x0 = eng.solution(i)
+            dev.enforce_rhs(x0, None, eng.dir_mask, st.xD[i], out=x0)
             T = eng.solve(eng.rhs, i, self.solver_config.rtol,
                           self.solver_config.maxiter, vals=st.K_e)
             dev.spmv(eng.row_ptr, eng.col_idx, st.K, T, 1, out=st.tmp)
