@@ -115,6 +115,19 @@ int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
                    int use_x0, double rtol, int maxiter, int check_every,
                    int32_t *info_h, double *relres_h, void *stream);
 
+/* Node-block variant for 3 dofs per node: the values keep the CSR layout
+ * (row 3n+i = 3*deg(n) contiguous entries, the node's three rows back to back)
+ * but columns are read once per 3x3 block from the node graph
+ * (node_ptr[n_nodes+1], node_col[]): 8 + 4/9 bytes per non-zero instead of 12. */
+int sktb_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
+                   const int32_t *node_col, const double *vals, const double *x,
+                   double *y, void *stream);
+int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
+                        const int32_t *node_col, const double *vals,
+                        const double *inv_diag, const double *b, double *x,
+                        int use_x0, double rtol, int maxiter, int check_every,
+                        int32_t *info_h, double *relres_h, void *stream);
+
 /* -------------------------------------------------- multi-GPU --
  * Row-sharded operator: rank r owns the rows of the contiguous node range
  * [node_begin, node_end) (its dofs [dpn*node_begin, dpn*node_end)); column

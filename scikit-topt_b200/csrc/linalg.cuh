@@ -23,3 +23,10 @@ int launch_spmv(int64_t n_rows, int dpn_hint, const int32_t *row_ptr,
                 const int32_t *col_idx, const double *vals, const double *x,
                 double *y, const double *dotv, sktb::ReduceScratch *rs,
                 double *dot_out, const PcgScalars *S, cudaStream_t st);
+
+// same for the node-block layout of the 3-dof elasticity operator (spmv_bsr.cu)
+int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
+                     const int32_t *node_col, const double *vals,
+                     const double *x, double *y, const double *dotv,
+                     sktb::ReduceScratch *rs, double *dot_out,
+                     const PcgScalars *S, cudaStream_t st);

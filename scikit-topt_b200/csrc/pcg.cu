@@ -298,13 +298,31 @@ static int reduce_scalars(sktb_pcg *s, double *loc, double *glob, int count,
   return comm_allreduce_sum(s->comm, loc, glob, count, st);
 }
 
-extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
-                              const int32_t *col_idx, const double *vals,
-                              const double *inv_diag, const double *b,
-                              double *x, int use_x0, double rtol, int maxiter,
-                              int check_every, int32_t *info_h,
-                              double *relres_h, void *stream) {
-  SKTB_REQUIRE(s && row_ptr && col_idx && vals && inv_diag && b && x,
+// matrix handed to the solver: CSR (kind 0) or node-block CSR for 3 dofs per
+// node (kind 1: rp/ci index node blocks, vals keep the CSR layout)
+struct PcgMat {
+  int kind;
+  int dpn_hint;
+  const int32_t *rp;
+  const int32_t *ci;
+  const double *vals;
+};
+
+static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
+                     const double *dotv, ReduceScratch *rs, double *dot_out,
+                     const PcgScalars *S, cudaStream_t st) {
+  if (A.kind == 1)
+    return launch_spmv_bsr3(n / 3, A.rp, A.ci, A.vals, x, y, dotv, rs, dot_out,
+                            S, st);
+  return launch_spmv(n, A.dpn_hint, A.rp, A.ci, A.vals, x, y, dotv, rs, dot_out,
+                     S, st);
+}
+
+static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
+                   const double *b, double *x, int use_x0, double rtol,
+                   int maxiter, int check_every, int32_t *info_h,
+                   double *relres_h, void *stream) {
+  SKTB_REQUIRE(s && A.rp && A.ci && A.vals && inv_diag && b && x,
                "null argument");
   SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
   if (check_every <= 0) check_every = 32;
@@ -320,8 +338,7 @@ extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
     SKTB_CUDA_OK(cudaMemcpyAsync(p_own, x, sizeof(double) * n,
                                  cudaMemcpyDeviceToDevice, st));
     if (halo_exchange(s, s->p, st)) return 1;
-    if (launch_spmv(n, dpn_hint, row_ptr, col_idx, vals, s->p, s->q, nullptr,
-                    nullptr, nullptr, nullptr, st))
+    if (apply_mat(A, n, s->p, s->q, nullptr, nullptr, nullptr, nullptr, st))
       return 1;
   }
   pcg_init_kernel<<<vgrid, kBlock, 0, st>>>(n, b, s->q, use_x0 ? 1 : 0, inv_diag,
@@ -354,8 +371,7 @@ extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
                           ((launched / check_every) % s->prof_every == 0) &&
                           n_ev < sktb_pcg::kMaxProf;
       if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev0[n_ev], st));
-      if (launch_spmv(n, dpn_hint, row_ptr, col_idx, vals, s->p, s->q, p_own,
-                      &rs, &s->Sloc->pq, s->S, st))
+      if (apply_mat(A, n, s->p, s->q, p_own, &rs, &s->Sloc->pq, s->S, st))
         return 1;
       if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev1[n_ev++], st));
       if (reduce_scalars(s, &s->Sloc->pq, &s->S->pq, 1, st)) return 1;
@@ -377,4 +393,28 @@ extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
   }
   if (relres_h) *relres_h = (h.bb > 0.0) ? sqrt(h.rr / h.bb) : 0.0;
   return 0;
+}
+
+extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
+                              const int32_t *col_idx, const double *vals,
+                              const double *inv_diag, const double *b,
+                              double *x, int use_x0, double rtol, int maxiter,
+                              int check_every, int32_t *info_h,
+                              double *relres_h, void *stream) {
+  PcgMat A{0, dpn_hint, row_ptr, col_idx, vals};
+  return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
+                 info_h, relres_h, stream);
+}
+
+extern "C" int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
+                                   const int32_t *node_col, const double *vals,
+                                   const double *inv_diag, const double *b,
+                                   double *x, int use_x0, double rtol,
+                                   int maxiter, int check_every,
+                                   int32_t *info_h, double *relres_h,
+                                   void *stream) {
+  SKTB_REQUIRE(s && s->n % 3 == 0, "block solve needs 3 dofs per node");
+  PcgMat A{1, 3, node_ptr, node_col, vals};
+  return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
+                 info_h, relres_h, stream);
 }

@@ -1,0 +1,101 @@
+// SpMV for the 3-dof-per-node elasticity operator with block (node-level)
+// column indices.
+//
+// The values keep the CSR layout (row 3n+i holds its 3*deg(n) entries
+// contiguously, the three rows of a node back to back), but the kernel reads
+// ONE int32 column per 3x3 block (the node graph) instead of one per entry:
+// 8 + 4/9 bytes per non-zero instead of 12.  One warp owns a node: its
+// 9*deg <= 243 values are one contiguous run, loaded with up to 8 coalesced
+// loads per lane that are all in flight before the first gather of x.
+#include "common.cuh"
+#include "linalg.cuh"
+
+using namespace sktb;
+
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock)
+    spmv_bsr3_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr,
+                     const int32_t *__restrict__ node_col,
+                     const double *__restrict__ vals,
+                     const double *__restrict__ x, double *__restrict__ y,
+                     const double *__restrict__ dotv, double *partials,
+                     unsigned int *ticket, double *dot_out,
+                     const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  constexpr int U = 8;  // 8 * 32 = 256 >= 243 values of a 27-neighbour node
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int64_t n = warp; n < n_nodes; n += nwarps) {
+    const int32_t s0 = __ldg(&node_ptr[n]);
+    const int32_t deg = __ldg(&node_ptr[n + 1]) - s0;
+    const int32_t w = 3 * deg;          // entries per row
+    const int32_t total = 3 * w;        // entries of the node's three rows
+    const int64_t base = (int64_t)9 * s0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int32_t e0 = 0; e0 < total; e0 += U * 32) {
+      double v[U];
+      int32_t c[U];
+      int rowi[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t e = e0 + lane + 32 * u;
+        const bool ok = e < total;
+        v[u] = ok ? __ldcs(&vals[base + e]) : 0.0;
+        const int32_t i = ok ? (int32_t)(e >= w) + (int32_t)(e >= 2 * w) : 0;
+        const int32_t q = e - i * w;
+        const int32_t s = q / 3;
+        rowi[u] = i;
+        c[u] = ok ? 3 * __ldg(&node_col[s0 + s]) + (q - 3 * s) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double t = v[u] * __ldg(&x[c[u]]);
+        a0 += (rowi[u] == 0) ? t : 0.0;
+        a1 += (rowi[u] == 1) ? t : 0.0;
+        a2 += (rowi[u] == 2) ? t : 0.0;
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      const int64_t r = 3 * n;
+      y[r] = a0;
+      y[r + 1] = a1;
+      y[r + 2] = a2;
+      if (DOT) dot += a0 * dotv[r] + a1 * dotv[r + 1] + a2 * dotv[r + 2];
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
+                     const int32_t *node_col, const double *vals,
+                     const double *x, double *y, const double *dotv,
+                     ReduceScratch *rs, double *dot_out, const PcgScalars *S,
+                     cudaStream_t st) {
+  const int grid = grid_for(n_nodes * 32, kBlock, 8);
+  if (dotv)
+    spmv_bsr3_kernel<true><<<grid, kBlock, 0, st>>>(
+        n_nodes, node_ptr, node_col, vals, x, y, dotv, rs->partials, rs->ticket,
+        dot_out, S);
+  else
+    spmv_bsr3_kernel<false><<<grid, kBlock, 0, st>>>(
+        n_nodes, node_ptr, node_col, vals, x, y, nullptr, nullptr, nullptr,
+        nullptr, S);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+extern "C" int sktb_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
+                              const int32_t *node_col, const double *vals,
+                              const double *x, double *y, void *stream) {
+  SKTB_REQUIRE(node_ptr && node_col && vals && x && y, "null argument");
+  return launch_spmv_bsr3(n_nodes, node_ptr, node_col, vals, x, y, nullptr,
+                          nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}

@@ -333,6 +333,17 @@ def spmv(row_ptr, col_idx, vals, x, dpn_hint, out=None):
     return out
 
 
+def spmv_bsr3(node_ptr, node_col, vals, x, out=None):
+    """y = A x with block column indices (3 dofs per node, CSR value layout)."""
+    n_nodes = node_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_spmv_bsr3(n_nodes, _ptr(node_ptr), _ptr(node_col), _ptr(vals), _ptr(x), _ptr(out), _stream())
+    )
+    return out
+
+
 def csr_enforce(row_ptr, col_idx, vals, mask_u8):
     n = row_ptr.numel() - 1
     _lib.check(
@@ -408,17 +419,20 @@ class PcgSolver:
         return float(ms.value), int(cnt.value)
 
     def solve(self, row_ptr, col_idx, vals, inv_diag, b, x, dpn_hint, rtol=1e-8,
-              maxiter=1000, use_x0=False, check_every=32):
+              maxiter=1000, use_x0=False, check_every=32, block3=False):
+        """``block3=True``: ``row_ptr`` / ``col_idx`` are the node-level graph
+        (one column per 3x3 block), ``vals`` keeps the CSR layout."""
         info = (C.c_int32 * 2)()
         relres = C.c_double()
-        _lib.check(
-            self.lib.sktb_pcg_solve(
-                self.handle, dpn_hint, _ptr(row_ptr), _ptr(col_idx), _ptr(vals),
-                _ptr(inv_diag), _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
+        tail = (_ptr(inv_diag), _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
                 int(maxiter), int(check_every), C.cast(info, C.c_void_p),
-                C.cast(C.byref(relres), C.c_void_p), _stream(),
-            )
-        )
+                C.cast(C.byref(relres), C.c_void_p), _stream())
+        if block3:
+            _lib.check(self.lib.sktb_pcg_solve_bsr3(
+                self.handle, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), *tail))
+        else:
+            _lib.check(self.lib.sktb_pcg_solve(
+                self.handle, dpn_hint, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), *tail))
         self.last_iters = int(info[0])
         self.last_converged = bool(info[1])
         self.last_relres = float(relres.value)

@@ -65,6 +65,14 @@ class FeaEngine:
             self.halo_dofs = int(halo[4].size)
         self.row0 = dpn * self.node0
         self.n_local = dpn * (self.node1 - self.node0)
+        # node-block view of the owned rows (3 dofs per node): one column index
+        # per 3x3 block for the PCG SpMV; "csr" keeps the per-entry indices
+        self.spmv_format = "bsr3" if dpn == 3 else "csr"
+        if dpn == 3:
+            rp_h, ci_h = dm.node_graph_cached()
+            s, e = int(rp_h[self.node0]), int(rp_h[self.node1])
+            self.node_ptr_loc = dev.to_dev(rp_h[self.node0:self.node1 + 1] - s, dev.I32)
+            self.node_col_loc = dev.to_dev(ci_h[s:e], dev.I32)
         self.vals = torch.empty(self.col_idx.numel(), dtype=dev.F64, device="cuda")
         self.inv_diag = torch.empty(self.n_local, dtype=dev.F64, device="cuda")
         self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
@@ -106,11 +114,13 @@ class FeaEngine:
         x = self.solution(load)
         mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
         lo, hi = self.row0, self.row0 + self.n_local
-        self.pcg.solve(self.row_ptr, self.col_idx,
+        block3 = self.spmv_format == "bsr3"
+        self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
+                       self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,
                        rhs[lo:hi], x[lo:hi],
                        dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
-                       use_x0=self.warm_start, check_every=32)
+                       use_x0=self.warm_start, check_every=32, block3=block3)
         if self.sharded:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]

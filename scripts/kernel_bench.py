@@ -64,6 +64,12 @@ def main():
     out["spmv"] = {"ms": ms, "best_ms": best, "alg_bytes": spmv_bytes,
                    "alg_GBps": spmv_bytes / ms / 1e6, "best_GBps": spmv_bytes / best / 1e6}
 
+    ms, best = timeit(lambda: dev.spmv_bsr3(eng.node_ptr_loc, eng.node_col_loc, eng.vals, x, out=y),
+                      reps, flush)
+    bsr_bytes = nnz * 8 + (nnz // 9) * 4 + (n // 3) * 4 + n * 16
+    out["spmv_bsr3"] = {"ms": ms, "best_ms": best, "alg_GBps_csr_accounting": spmv_bytes / ms / 1e6,
+                        "format_bytes": bsr_bytes, "format_GBps": bsr_bytes / ms / 1e6}
+
     u = torch.randn(n, dtype=dev.F64, device="cuda")
     e = torch.empty(ne, dtype=dev.F64, device="cuda")
     ms, best = timeit(lambda: eng.energy(u, out=e), reps, flush)
@@ -78,8 +84,8 @@ def main():
     eng.warm_start = False
     torch.cuda.synchronize()
     t0 = time.time()
-    eng.pcg.solve(eng.row_ptr, eng.col_idx, eng.vals, eng.inv_diag, eng.rhs, xs,
-                  dpn_hint=3, rtol=0.0, maxiter=iters, use_x0=False, check_every=50)
+    eng.pcg.solve(eng.node_ptr_loc, eng.node_col_loc, eng.vals, eng.inv_diag, eng.rhs, xs,
+                  dpn_hint=3, rtol=0.0, maxiter=iters, use_x0=False, check_every=50, block3=True)
     torch.cuda.synchronize()
     dt = time.time() - t0
     pcg_bytes = spmv_bytes + 16 * n * 8
@@ -87,8 +93,8 @@ def main():
                        "alg_GBps": pcg_bytes / (dt / iters) / 1e9}
     # real solve to rtol 1e-8
     t0 = time.time()
-    eng.pcg.solve(eng.row_ptr, eng.col_idx, eng.vals, eng.inv_diag, eng.rhs, xs,
-                  dpn_hint=3, rtol=1e-8, maxiter=60000, use_x0=False, check_every=50)
+    eng.pcg.solve(eng.node_ptr_loc, eng.node_col_loc, eng.vals, eng.inv_diag, eng.rhs, xs,
+                  dpn_hint=3, rtol=1e-8, maxiter=60000, use_x0=False, check_every=50, block3=True)
     torch.cuda.synchronize()
     out["pcg_solve"] = {"s": time.time() - t0, "iters": eng.pcg.last_iters,
                         "converged": eng.pcg.last_converged, "relres": eng.pcg.last_relres}

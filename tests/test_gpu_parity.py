@@ -104,6 +104,12 @@ def test_spmv_matches_scipy(gpu):
     y = dev.spmv(dev.to_dev(K.indptr, dev.I32), dev.to_dev(K.indices, dev.I32),
                  dev.to_dev(K.data), dev.to_dev(x), 3).cpu().numpy()
     assert rel_err(y, K @ x) <= 1e-13
+    # node-block column indices (the PCG's format for 3 dofs per node)
+    dm = dev.device_mesh(tsk.mesh)
+    rp, ci = dm.node_graph()
+    yb = dev.spmv_bsr3(dev.to_dev(rp, dev.I32), dev.to_dev(ci, dev.I32), dev.to_dev(K.data),
+                       dev.to_dev(x)).cpu().numpy()
+    assert rel_err(yb, K @ x) <= 1e-13
     # scalar rows (8 lanes per row pair)
     A = sp.random(3001, 3001, density=0.01, random_state=0, format="csr") + sp.eye(3001)
     A = A.tocsr()
