@@ -122,8 +122,17 @@ int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
 int sktb_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
                    const int32_t *node_col, const double *vals, const double *x,
                    double *y, void *stream);
+/* bulk-async (cp.async.bulk + mbarrier) pipelined variant: tiles of 16 nodes
+ * are streamed into a 3-stage shared-memory ring by one thread per CTA while
+ * the warps consume the previous tile; needs max_deg <= 27 (hex8 graphs).
+ * n_blocks = node_ptr[n_nodes].  The PCG uses it automatically when eligible. */
+int sktb_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                       const int32_t *node_ptr, const int32_t *node_col,
+                       const double *vals, const double *x, double *y,
+                       void *stream);
 int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
-                        const int32_t *node_col, const double *vals,
+                        const int32_t *node_col, int64_t n_blocks, int max_deg,
+                        const double *vals,
                         const double *inv_diag, const double *b, double *x,
                         int use_x0, double rtol, int maxiter, int check_every,
                         int32_t *info_h, double *relres_h, void *stream);

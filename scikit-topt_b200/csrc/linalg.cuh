@@ -30,3 +30,12 @@ int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
                      const double *x, double *y, const double *dotv,
                      sktb::ReduceScratch *rs, double *dot_out,
                      const PcgScalars *S, cudaStream_t st);
+
+// bulk-async (TMA) pipelined variant (spmv_bsr_tma.cu); returns -1 when the
+// layout is not eligible (max_deg > 27 or too few nodes) so the caller can
+// fall back to launch_spmv_bsr3
+int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                         const int32_t *node_ptr, const int32_t *node_col,
+                         const double *vals, const double *x, double *y,
+                         const double *dotv, sktb::ReduceScratch *rs,
+                         double *dot_out, const PcgScalars *S, cudaStream_t st);

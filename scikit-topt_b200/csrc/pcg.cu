@@ -306,14 +306,20 @@ struct PcgMat {
   const int32_t *rp;
   const int32_t *ci;
   const double *vals;
+  int64_t n_blocks = 0;  // kind 1: number of 3x3 blocks
+  int max_deg = 0;       // kind 1: largest number of blocks in a node row
 };
 
 static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
                      const double *dotv, ReduceScratch *rs, double *dot_out,
                      const PcgScalars *S, cudaStream_t st) {
-  if (A.kind == 1)
+  if (A.kind == 1) {
+    int rc = launch_spmv_bsr3_tma(n / 3, A.n_blocks, A.max_deg, A.rp, A.ci,
+                                  A.vals, x, y, dotv, rs, dot_out, S, st);
+    if (rc != -1) return rc;
     return launch_spmv_bsr3(n / 3, A.rp, A.ci, A.vals, x, y, dotv, rs, dot_out,
                             S, st);
+  }
   return launch_spmv(n, A.dpn_hint, A.rp, A.ci, A.vals, x, y, dotv, rs, dot_out,
                      S, st);
 }
@@ -407,14 +413,15 @@ extern "C" int sktb_pcg_solve(sktb_pcg *s, int dpn_hint, const int32_t *row_ptr,
 }
 
 extern "C" int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
-                                   const int32_t *node_col, const double *vals,
+                                   const int32_t *node_col, int64_t n_blocks,
+                                   int max_deg, const double *vals,
                                    const double *inv_diag, const double *b,
                                    double *x, int use_x0, double rtol,
                                    int maxiter, int check_every,
                                    int32_t *info_h, double *relres_h,
                                    void *stream) {
   SKTB_REQUIRE(s && s->n % 3 == 0, "block solve needs 3 dofs per node");
-  PcgMat A{1, 3, node_ptr, node_col, vals};
+  PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
   return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
                  info_h, relres_h, stream);
 }

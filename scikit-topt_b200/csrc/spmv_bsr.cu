@@ -13,7 +13,7 @@
 using namespace sktb;
 
 template <bool DOT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 6)
     spmv_bsr3_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr,
                      const int32_t *__restrict__ node_col,
                      const double *__restrict__ vals,
@@ -24,37 +24,44 @@ __global__ void __launch_bounds__(kBlock)
   if (S && S->rr <= S->tol2) return;
   constexpr int U = 8;  // 8 * 32 = 256 >= 243 values of a 27-neighbour node
   const int lane = threadIdx.x & 31;
-  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // each CTA walks a CONTIGUOUS chunk of nodes: the x entries gathered for one
+  // mesh line are reused from L1 by the neighbouring lines of the same chunk
+  const int64_t chunk = (n_nodes + gridDim.x - 1) / gridDim.x;
+  const int64_t n_lo = (int64_t)blockIdx.x * chunk;
+  const int64_t n_hi = (n_lo + chunk < n_nodes) ? n_lo + chunk : n_nodes;
   double dot = 0.0;
-  for (int64_t n = warp; n < n_nodes; n += nwarps) {
+  for (int64_t n = n_lo + (threadIdx.x >> 5); n < n_hi; n += kBlock / 32) {
     const int32_t s0 = __ldg(&node_ptr[n]);
     const int32_t deg = __ldg(&node_ptr[n + 1]) - s0;
     const int32_t w = 3 * deg;          // entries per row
     const int32_t total = 3 * w;        // entries of the node's three rows
-    const int64_t base = (int64_t)9 * s0;
+    const double *vp = vals + (int64_t)9 * s0;
+    const int32_t *cp = node_col + s0;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int32_t e0 = 0; e0 < total; e0 += U * 32) {
+    for (int32_t e0 = lane; e0 < total; e0 += U * 32) {
       double v[U];
-      int32_t c[U];
-      int rowi[U];
+      int32_t nc[U];
+      // phase 1: matrix stream (values + one block column per entry's block)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int32_t e = e0 + lane + 32 * u;
+        const int32_t e = e0 + 32 * u;
         const bool ok = e < total;
-        v[u] = ok ? __ldcs(&vals[base + e]) : 0.0;
-        const int32_t i = ok ? (int32_t)(e >= w) + (int32_t)(e >= 2 * w) : 0;
-        const int32_t q = e - i * w;
-        const int32_t s = q / 3;
-        rowi[u] = i;
-        c[u] = ok ? 3 * __ldg(&node_col[s0 + s]) + (q - 3 * s) : 0;
+        const int32_t q = e - ((e >= w) ? w : 0) - ((e >= 2 * w) ? w : 0);
+        v[u] = ok ? __ldcs(&vp[e]) : 0.0;
+        nc[u] = ok ? __ldg(&cp[q / 3]) : 0;
       }
+      // phase 2: gather x and accumulate into the row the entry belongs to
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const double t = v[u] * __ldg(&x[c[u]]);
-        a0 += (rowi[u] == 0) ? t : 0.0;
-        a1 += (rowi[u] == 1) ? t : 0.0;
-        a2 += (rowi[u] == 2) ? t : 0.0;
+        const int32_t e = e0 + 32 * u;
+        const int32_t q = e - ((e >= w) ? w : 0) - ((e >= 2 * w) ? w : 0);
+        const double t = v[u] * __ldg(&x[3 * nc[u] + (q - 3 * (q / 3))]);
+        if (e < w)
+          a0 += t;
+        else if (e < 2 * w)
+          a1 += t;
+        else
+          a2 += t;
       }
     }
     a0 = warp_sum(a0);
@@ -79,7 +86,7 @@ int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
                      const double *x, double *y, const double *dotv,
                      ReduceScratch *rs, double *dot_out, const PcgScalars *S,
                      cudaStream_t st) {
-  const int grid = grid_for(n_nodes * 32, kBlock, 8);
+  const int grid = grid_for(n_nodes * 32, kBlock, 6);
   if (dotv)
     spmv_bsr3_kernel<true><<<grid, kBlock, 0, st>>>(
         n_nodes, node_ptr, node_col, vals, x, y, dotv, rs->partials, rs->ticket,

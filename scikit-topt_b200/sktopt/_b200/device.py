@@ -344,6 +344,17 @@ def spmv_bsr3(node_ptr, node_col, vals, x, out=None):
     return out
 
 
+def spmv_bsr3_tma(node_ptr, node_col, vals, x, max_deg, out=None):
+    """Bulk-async pipelined variant of ``spmv_bsr3`` (max_deg <= 27)."""
+    n_nodes = node_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_spmv_bsr3_tma(n_nodes, int(node_col.numel()), int(max_deg), _ptr(node_ptr), _ptr(node_col), _ptr(vals), _ptr(x), _ptr(out), _stream())
+    )
+    return out
+
+
 def csr_enforce(row_ptr, col_idx, vals, mask_u8):
     n = row_ptr.numel() - 1
     _lib.check(
@@ -419,7 +430,8 @@ class PcgSolver:
         return float(ms.value), int(cnt.value)
 
     def solve(self, row_ptr, col_idx, vals, inv_diag, b, x, dpn_hint, rtol=1e-8,
-              maxiter=1000, use_x0=False, check_every=32, block3=False):
+              maxiter=1000, use_x0=False, check_every=32, block3=False,
+              max_deg=0):
         """``block3=True``: ``row_ptr`` / ``col_idx`` are the node-level graph
         (one column per 3x3 block), ``vals`` keeps the CSR layout."""
         info = (C.c_int32 * 2)()
@@ -429,7 +441,8 @@ class PcgSolver:
                 C.cast(C.byref(relres), C.c_void_p), _stream())
         if block3:
             _lib.check(self.lib.sktb_pcg_solve_bsr3(
-                self.handle, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), *tail))
+                self.handle, _ptr(row_ptr), _ptr(col_idx), int(col_idx.numel()),
+                int(max_deg), _ptr(vals), *tail))
         else:
             _lib.check(self.lib.sktb_pcg_solve(
                 self.handle, dpn_hint, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), *tail))

@@ -73,6 +73,7 @@ class FeaEngine:
             s, e = int(rp_h[self.node0]), int(rp_h[self.node1])
             self.node_ptr_loc = dev.to_dev(rp_h[self.node0:self.node1 + 1] - s, dev.I32)
             self.node_col_loc = dev.to_dev(ci_h[s:e], dev.I32)
+            self.max_deg = int(np.diff(rp_h[self.node0:self.node1 + 1]).max())
         self.vals = torch.empty(self.col_idx.numel(), dtype=dev.F64, device="cuda")
         self.inv_diag = torch.empty(self.n_local, dtype=dev.F64, device="cuda")
         self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
@@ -120,7 +121,8 @@ class FeaEngine:
                        self.vals if vals is None else vals, self.inv_diag,
                        rhs[lo:hi], x[lo:hi],
                        dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
-                       use_x0=self.warm_start, check_every=32, block3=block3)
+                       use_x0=self.warm_start, check_every=32, block3=block3,
+                       max_deg=getattr(self, "max_deg", 0))
         if self.sharded:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]

@@ -70,6 +70,11 @@ def main():
     out["spmv_bsr3"] = {"ms": ms, "best_ms": best, "alg_GBps_csr_accounting": spmv_bytes / ms / 1e6,
                         "format_bytes": bsr_bytes, "format_GBps": bsr_bytes / ms / 1e6}
 
+    ms, best = timeit(lambda: dev.spmv_bsr3_tma(eng.node_ptr_loc, eng.node_col_loc, eng.vals, x,
+                                                eng.max_deg, out=y), reps, flush)
+    out["spmv_bsr3_tma"] = {"ms": ms, "best_ms": best, "alg_GBps_csr_accounting": spmv_bytes / ms / 1e6,
+                            "format_GBps": bsr_bytes / ms / 1e6}
+
     u = torch.randn(n, dtype=dev.F64, device="cuda")
     e = torch.empty(ne, dtype=dev.F64, device="cuda")
     ms, best = timeit(lambda: eng.energy(u, out=e), reps, flush)
@@ -85,7 +90,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.time()
     eng.pcg.solve(eng.node_ptr_loc, eng.node_col_loc, eng.vals, eng.inv_diag, eng.rhs, xs,
-                  dpn_hint=3, rtol=0.0, maxiter=iters, use_x0=False, check_every=50, block3=True)
+                  dpn_hint=3, rtol=0.0, maxiter=iters, use_x0=False, check_every=50, block3=True, max_deg=eng.max_deg)
     torch.cuda.synchronize()
     dt = time.time() - t0
     pcg_bytes = spmv_bytes + 16 * n * 8
@@ -94,7 +99,7 @@ def main():
     # real solve to rtol 1e-8
     t0 = time.time()
     eng.pcg.solve(eng.node_ptr_loc, eng.node_col_loc, eng.vals, eng.inv_diag, eng.rhs, xs,
-                  dpn_hint=3, rtol=1e-8, maxiter=60000, use_x0=False, check_every=50, block3=True)
+                  dpn_hint=3, rtol=1e-8, maxiter=60000, use_x0=False, check_every=50, block3=True, max_deg=eng.max_deg)
     torch.cuda.synchronize()
     out["pcg_solve"] = {"s": time.time() - t0, "iters": eng.pcg.last_iters,
                         "converged": eng.pcg.last_converged, "relres": eng.pcg.last_relres}

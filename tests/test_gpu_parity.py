@@ -110,6 +110,9 @@ def test_spmv_matches_scipy(gpu):
     yb = dev.spmv_bsr3(dev.to_dev(rp, dev.I32), dev.to_dev(ci, dev.I32), dev.to_dev(K.data),
                        dev.to_dev(x)).cpu().numpy()
     assert rel_err(yb, K @ x) <= 1e-13
+    yt = dev.spmv_bsr3_tma(dev.to_dev(rp, dev.I32), dev.to_dev(ci, dev.I32), dev.to_dev(K.data),
+                           dev.to_dev(x), int(np.diff(rp).max())).cpu().numpy()
+    assert rel_err(yt, K @ x) <= 1e-13
     # scalar rows (8 lanes per row pair)
     A = sp.random(3001, 3001, density=0.01, random_state=0, format="csr") + sp.eye(3001)
     A = A.tocsr()
