@@ -6,12 +6,13 @@
 // index arithmetic, per-entry column loads and three 5-step fp64 warp
 // reductions.  This kernel removes both limits:
 //   * the matrix stream is decoupled from the warps: a persistent CTA (one per
-//     SM) walks tiles of 32 consecutive nodes; a producer warp issues two 1-D
-//     bulk copies per tile (the tile's contiguous values, <= 62 KB, and its
-//     block columns) into a 3-stage shared-memory ring and signals an
-//     mbarrier, so ~125 KB per SM are in flight regardless of occupancy;
-//   * two threads own one matrix row and walk it from shared memory (no
-//     cross-lane reduction besides one shuffle, one column load per 3x3 block,
+//     SM pair of slots) walks tiles of 16 consecutive nodes; a producer warp
+//     issues two 1-D bulk copies per tile (the tile's contiguous values,
+//     <= 31 KB, and its block columns) into a 3-stage shared-memory ring and
+//     signals an mbarrier; two CTAs per SM keep ~130 KB per SM in flight
+//     regardless of occupancy;
+//   * four threads own one matrix row and walk it from shared memory (no
+//     cross-lane reduction besides two shuffles, one column load per 3x3 block,
 //     x gathered through the read-only path: the three rows of a node
 //     broadcast and neighbouring nodes coalesce) -> ~30 warp instructions per
 //     node row.
@@ -24,14 +25,14 @@ using namespace sktb;
 
 namespace {
 
-constexpr int kTile = 32;     // nodes per tile -> 96 rows -> 6 consumer warps
+constexpr int kTile = 16;     // nodes per tile -> 48 rows x 4 threads -> 6 consumer warps
 constexpr int kStages = 3;
 constexpr int kMaxDeg = 27;   // hex8 node graph
 constexpr int kConsumerWarps = 6;
 constexpr int kProducerWarp = 6;
 constexpr int kValCap = kTile * 9 * kMaxDeg + 2;  // doubles (+ alignment slack)
 constexpr int kColCap = kTile * kMaxDeg + 8;      // int32   (+ alignment slack)
-constexpr int kPtrCap = 36;                       // kTile + 1, padded to 16 B
+constexpr int kPtrCap = 36;                       // >= 33 slots (one per producer lane + end)
 constexpr int kStageBytes = kValCap * 8 + kColCap * 4 + kPtrCap * 4;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 16;
 static_assert(kStageBytes % 16 == 0, "stages must stay 16-byte aligned");
@@ -104,8 +105,7 @@ __device__ __forceinline__ void issue_tile(
   int32_t my = (lane < nn) ? __ldg(&node_ptr[n_a + lane]) : 0;
   const int32_t s_b = __ldg(&node_ptr[n_b]);
   if (lane >= nn) my = s_b;
-  sp.nptr[lane] = my;
-  if (lane == 0) sp.nptr[kTile] = s_b;
+  sp.nptr[lane] = my;  // slots nn..31 hold the end pointer
   const int32_t s_a = __shfl_sync(0xffffffffu, my, 0);
   __syncwarp();
   if (lane == 0) {
@@ -132,7 +132,7 @@ __device__ __forceinline__ void issue_tile(
 }
 
 template <bool DOT>
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, 2)
     spmv_bsr3_tma_kernel(int64_t n_nodes, int64_t n_blocks,
                          const int32_t *__restrict__ node_ptr,
                          const int32_t *__restrict__ node_col,
@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(kBlock, 1)
       }
     }
   } else if (wid < kConsumerWarps) {
-    // two threads per row: 16 rows per warp, 96 rows (32 nodes) per tile
-    const int half = lane & 1;
-    const int row_in_tile = wid * 16 + (lane >> 1);
+    // four threads per row: 8 rows per warp, 48 rows (16 nodes) per tile
+    const int quarter = lane & 3;
+    const int row_in_tile = wid * 8 + (lane >> 2);
     const int ln = row_in_tile / 3;       // node within the tile
     const int ri = row_in_tile - 3 * ln;  // row within the node
     int stage = 0;
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kBlock, 1)
       if (ln < nn) {
         const int32_t s0 = sp.nptr[ln];
         const int32_t deg = sp.nptr[ln + 1] - s0;
-        const int32_t b0 = half ? (deg + 1) / 2 : 0;
-        const int32_t b1 = half ? deg : (deg + 1) / 2;
+        const int32_t b0 = (deg * quarter) >> 2;
+        const int32_t b1 = (deg * (quarter + 1)) >> 2;
         const double *vp = sp.vals + ((int64_t)9 * s0 - v_lo) + (int64_t)ri * 3 * deg;
         const int32_t *cp = sp.cols + ((int64_t)s0 - c_lo);
         double acc1 = 0.0, acc2 = 0.0;
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kBlock, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (half == 0 && ln < nn) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (quarter == 0 && ln < nn) {
         const int64_t r = 3 * (n_a + ln) + ri;
         y[r] = acc;
         if (DOT) dot += acc * dotv[r];
@@ -239,7 +240,7 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const PcgScalars *S, cudaStream_t st) {
   if (max_deg > kMaxDeg || n_nodes < 8 * kTile) return -1;
   const int64_t n_tiles = (n_nodes + kTile - 1) / kTile;
-  int64_t g = (int64_t)kNumSM;
+  int64_t g = (int64_t)kNumSM * 2;
   if (g > n_tiles) g = n_tiles;
   const int grid = (int)g;
   const int which = dotv ? 1 : 0;
