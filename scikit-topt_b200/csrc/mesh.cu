@@ -563,11 +563,14 @@ __global__ void __launch_bounds__(kBlock)
     const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
     const double *ke = unit_ke + cls * (NDE * NDE);
     double acc = 0.0;
-    for (int ent = lane; ent < NDE * NDE; ent += 32) {
-      const int r = ent / NDE, c = ent - r * NDE;
+    // warp-uniform trip count (NDE*NDE need not be a multiple of 32: tets)
+    for (int base = 0; base < NDE * NDE; base += 32) {
+      const int ent = base + lane;
+      const bool ok = ent < NDE * NDE;
+      const int r = ok ? ent / NDE : 0, c = ok ? ent - r * NDE : 0;
       const double ur = __shfl_sync(0xffffffffu, ue, r);
       const double uc = __shfl_sync(0xffffffffu, ue, c);
-      acc += ur * __ldg(&ke[ent]) * uc;
+      if (ok) acc += ur * __ldg(&ke[ent]) * uc;
     }
     acc = warp_sum(acc);
     if (lane == 0) out[e] = 0.5 * (scale ? scale[e] : 1.0) * acc;
