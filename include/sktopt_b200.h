@@ -130,12 +130,63 @@ int sktb_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                        const int32_t *node_ptr, const int32_t *node_col,
                        const double *vals, const double *x, double *y,
                        void *stream);
+/* out[3n+i] = 1 / A[3n+i,3n+i] from the node-block layout                      */
+int sktb_bsr3_inv_diag(int64_t n_nodes, const int32_t *node_ptr,
+                       const int32_t *node_col, const double *vals, double *out,
+                       void *stream);
 int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
                         const int32_t *node_col, int64_t n_blocks, int max_deg,
                         const double *vals,
                         const double *inv_diag, const double *b, double *x,
                         int use_x0, double rtol, int maxiter, int check_every,
                         int32_t *info_h, double *relres_h, void *stream);
+
+/* ----------------------------------------------- multigrid preconditioner --
+ * Replaces pyamg.smoothed_aggregation_solver(K).aspreconditioner()
+ * (fea/solver_elastic.py:94-104, rebuilt every optimiser iteration there) for
+ * tensor-product hexahedral grids: geometric hierarchy (cell counts halved per
+ * level, trilinear prolongation), exact Galerkin coarse operators formed
+ * element-wise, V(1,1) damped-Jacobi cycle, Dirichlet dofs masked per level.
+ * All level arrays are caller-owned device buffers.                           */
+typedef struct sktb_mg sktb_mg;
+int sktb_mg_create(sktb_mg **out, int n_levels, int device);
+void sktb_mg_destroy(sktb_mg *m);
+int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse);
+/* operator of one level: node-block CSR (values in CSR layout, enforced),
+ * inverse diagonal, optional per-dof Dirichlet mask                           */
+int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes, int64_t n_blocks,
+                      int max_deg, const int32_t *node_ptr,
+                      const int32_t *node_col, const double *vals,
+                      const double *inv_diag, const uint8_t *mask);
+/* transfer between level (fine) and level+1 (coarse).  Nodes per axis (x,y,z)
+ * of both grids (node = iy + npy*ix + npy*npx*iz); per-axis interpolation
+ * tables on the device, concatenated [x|y|z]: fine index i takes coarse
+ * c0[i], c1[i] with weights w0[i], w1[i]; transposed tables [3 slots][x|y|z]:
+ * coarse index I gathers fine axT_f (or -1) with weight axT_w.                */
+int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_np_h,
+                         const int32_t *coarse_np_h, const int32_t *ax_c0,
+                         const int32_t *ax_c1, const double *ax_w0,
+                         const double *ax_w1, const int32_t *axT_f,
+                         const double *axT_w);
+/* z = M^-1 r (one V-cycle)                                                    */
+int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stream);
+/* Galerkin coarse element matrices: out[E] = sum_c Q^T K_child Q over the
+ * children child[c][E] (-1 = none) of coarse element E, Q = Qtab[ptype[E]][c]
+ * (8x8 trilinear weights child vertex <- parent vertex).  Children are either
+ * per-element matrices fine_ke[e][24][24] or scale[e]*unit[cls[e]] (level 0). */
+int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
+                       const uint8_t *ptype, const double *Qtab,
+                       const double *fine_ke, const double *unit,
+                       const int32_t *cls, const double *scale, double *out,
+                       void *stream);
+/* PCG preconditioned by the V-cycle (single GPU)                              */
+int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg, const int32_t *node_ptr,
+                           const int32_t *node_col, int64_t n_blocks,
+                           int max_deg, const double *vals,
+                           const double *inv_diag, const double *b, double *x,
+                           int use_x0, double rtol, int maxiter,
+                           int check_every, int32_t *info_h, double *relres_h,
+                           void *stream);
 
 /* -------------------------------------------------- multi-GPU --
  * Row-sharded operator: rank r owns the rows of the contiguous node range

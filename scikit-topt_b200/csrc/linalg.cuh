@@ -39,3 +39,7 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const double *vals, const double *x, double *y,
                          const double *dotv, sktb::ReduceScratch *rs,
                          double *dot_out, const PcgScalars *S, cudaStream_t st);
+
+// multigrid preconditioner z = M^-1 r (mg.cu)
+struct sktb_mg;
+int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st);

@@ -1,0 +1,352 @@
+// Geometric multigrid preconditioner for the 3-dof elasticity operator on
+// tensor-product hexahedral grids ("AMG-smoothed PCG" of the north star, built
+// on the grid hierarchy because the benchmark meshes are box grids).
+//
+//  * Hierarchy: every level halves the cell counts (ceil), coarse nodes are a
+//    subset of the fine nodes, prolongation is trilinear interpolation.
+//  * Coarse operators are exact Galerkin products A_{l+1} = P^T A_l P, formed
+//    element-wise: a coarse element matrix is sum_c Q_c^T Ke_child Q_c over its
+//    (up to 8) children (elem_restrict_kernel), then gathered into the level's
+//    CSR by the ordinary assembly kernel (mesh.cu).  Level-0 children are
+//    E_e * Ke0[class].
+//  * V(1,1) cycle with damped Jacobi; residual and restriction are fused.
+//  * Dirichlet dofs are masked on every level (coarse dof fixed iff the
+//    coincident fine dof is fixed), so M^-1 stays symmetric positive definite.
+#include <vector>
+
+#include "common.cuh"
+#include "linalg.cuh"
+
+using namespace sktb;
+
+struct MgLevel {
+  int64_t n_nodes = 0, n_blocks = 0;
+  int max_deg = 0;
+  const int32_t *node_ptr = nullptr, *node_col = nullptr;
+  const double *vals = nullptr, *inv_diag = nullptr;
+  const uint8_t *mask = nullptr;  // per dof, may be null
+  double *x = nullptr, *b = nullptr, *tmp = nullptr;  // owned work vectors
+  // transfer to the next coarser level (tensor grid tables, device)
+  int32_t fnp[3] = {0, 0, 0}, cnp[3] = {0, 0, 0};  // nodes per axis (x, y, z)
+  const int32_t *ax_c0 = nullptr, *ax_c1 = nullptr;  // [fnx | fny | fnz]
+  const double *ax_w0 = nullptr, *ax_w1 = nullptr;
+  const int32_t *axT_f = nullptr;  // [3 slots][cnx | cny | cnz], -1 = none
+  const double *axT_w = nullptr;
+};
+
+struct sktb_mg {
+  int device = 0;
+  std::vector<MgLevel> lv;
+  double omega = 0.5;
+  int nu_coarse = 20;
+};
+
+extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
+  SKTB_REQUIRE(out && n_levels >= 1 && n_levels <= 16, "bad argument");
+  sktb_mg *m = new sktb_mg();
+  m->device = device;
+  m->lv.resize(n_levels);
+  *out = m;
+  return 0;
+}
+
+extern "C" void sktb_mg_destroy(sktb_mg *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (auto &l : m->lv) {
+    cudaFree(l.x);
+    cudaFree(l.b);
+    cudaFree(l.tmp);
+  }
+  delete m;
+}
+
+extern "C" int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse) {
+  SKTB_REQUIRE(m && omega > 0.0 && omega < 2.0 && nu_coarse >= 0, "bad argument");
+  m->omega = omega;
+  m->nu_coarse = nu_coarse;
+  return 0;
+}
+
+extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
+                                 int64_t n_blocks, int max_deg,
+                                 const int32_t *node_ptr,
+                                 const int32_t *node_col, const double *vals,
+                                 const double *inv_diag, const uint8_t *mask) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size(), "bad level");
+  SKTB_REQUIRE(node_ptr && node_col && vals && inv_diag && n_nodes > 0, "null argument");
+  SKTB_CUDA_OK(cudaSetDevice(m->device));
+  MgLevel &l = m->lv[level];
+  if (l.n_nodes != n_nodes) {
+    cudaFree(l.x);
+    cudaFree(l.b);
+    cudaFree(l.tmp);
+    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * n_nodes));
+    SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
+    SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
+  }
+  l.n_nodes = n_nodes;
+  l.n_blocks = n_blocks;
+  l.max_deg = max_deg;
+  l.node_ptr = node_ptr;
+  l.node_col = node_col;
+  l.vals = vals;
+  l.inv_diag = inv_diag;
+  l.mask = mask;
+  return 0;
+}
+
+extern "C" int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_np_h,
+                                    const int32_t *coarse_np_h,
+                                    const int32_t *ax_c0, const int32_t *ax_c1,
+                                    const double *ax_w0, const double *ax_w1,
+                                    const int32_t *axT_f, const double *axT_w) {
+  SKTB_REQUIRE(m && level >= 0 && level + 1 < (int)m->lv.size(), "bad level");
+  SKTB_REQUIRE(fine_np_h && coarse_np_h && ax_c0 && ax_c1 && ax_w0 && ax_w1 &&
+                   axT_f && axT_w,
+               "null argument");
+  MgLevel &l = m->lv[level];
+  for (int a = 0; a < 3; ++a) {
+    l.fnp[a] = fine_np_h[a];
+    l.cnp[a] = coarse_np_h[a];
+  }
+  l.ax_c0 = ax_c0;
+  l.ax_c1 = ax_c1;
+  l.ax_w0 = ax_w0;
+  l.ax_w1 = ax_w1;
+  l.axT_f = axT_f;
+  l.axT_w = axT_w;
+  return 0;
+}
+
+// ------------------------------------------------ Galerkin element matrices --
+// out[E] = sum_c Q_c^T K_child Q_c ; block per coarse element, thread per entry
+__global__ void __launch_bounds__(192)
+    elem_restrict_kernel(int64_t n_coarse, const int32_t *__restrict__ child,
+                         const uint8_t *__restrict__ ptype,
+                         const double *__restrict__ Qtab,
+                         const double *__restrict__ fine_ke,
+                         const double *__restrict__ unit,
+                         const int32_t *__restrict__ cls,
+                         const double *__restrict__ scale,
+                         double *__restrict__ out) {
+  const int64_t E = blockIdx.x;
+  const int type = ptype[E];
+  __shared__ int32_t ch[8];
+  __shared__ double Q[8][64];
+  if (threadIdx.x < 8) ch[threadIdx.x] = child[(int64_t)threadIdx.x * n_coarse + E];
+  for (int k = threadIdx.x; k < 512; k += blockDim.x)
+    Q[k >> 6][k & 63] = Qtab[(type * 8 + (k >> 6)) * 64 + (k & 63)];
+  __syncthreads();
+  for (int ent = threadIdx.x; ent < 576; ent += blockDim.x) {
+    const int r = ent / 24, c = ent - 24 * r;
+    const int A = r / 3, i = r - 3 * A, B = c / 3, j = c - 3 * B;
+    double acc = 0.0;
+    for (int cc = 0; cc < 8; ++cc) {
+      const int32_t ce = ch[cc];
+      if (ce < 0) continue;
+      const double *Kc;
+      double sc = 1.0;
+      if (fine_ke) {
+        Kc = fine_ke + (int64_t)ce * 576;
+      } else {
+        Kc = unit + (int64_t)(cls ? cls[ce] : 0) * 576;
+        sc = scale[ce];
+      }
+      double part = 0.0;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const double wa = Q[cc][a * 8 + A];
+        if (wa == 0.0) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const double wb = Q[cc][b * 8 + B];
+          if (wb == 0.0) continue;
+          part += wa * wb * __ldg(&Kc[(3 * a + i) * 24 + 3 * b + j]);
+        }
+      }
+      acc += sc * part;
+    }
+    out[E * 576 + ent] = acc;
+  }
+}
+
+extern "C" int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
+                                  const uint8_t *ptype, const double *Qtab,
+                                  const double *fine_ke, const double *unit,
+                                  const int32_t *cls, const double *scale,
+                                  double *out, void *stream) {
+  SKTB_REQUIRE(child && ptype && Qtab && out && n_coarse > 0, "null argument");
+  SKTB_REQUIRE(fine_ke || (unit && scale), "need fine element matrices or (unit, scale)");
+  elem_restrict_kernel<<<(unsigned)n_coarse, 192, 0, (cudaStream_t)stream>>>(
+      n_coarse, child, ptype, Qtab, fine_ke, unit, cls, scale, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------ level kernels --
+#define GS(i, n)                                                       \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x,     \
+               _st = (int64_t)gridDim.x * blockDim.x;                  \
+       i < (n); i += _st)
+
+__global__ void __launch_bounds__(kBlock)
+    mg_jacobi0_kernel(int64_t n, double omega, const double *__restrict__ dinv,
+                      const double *__restrict__ b, double *__restrict__ x) {
+  GS(i, n) x[i] = omega * dinv[i] * b[i];
+}
+__global__ void __launch_bounds__(kBlock)
+    mg_jacobi_kernel(int64_t n, double omega, const double *__restrict__ dinv,
+                     const double *__restrict__ b, const double *__restrict__ Ax,
+                     double *__restrict__ x) {
+  GS(i, n) x[i] += omega * dinv[i] * (b[i] - Ax[i]);
+}
+
+// b_c = mask_c * P^T (b_f - Ax_f) ; one thread per coarse node
+__global__ void __launch_bounds__(kBlock)
+    mg_restrict_kernel(int cnx, int cny, int cnz, int fnx, int fny, int fnz,
+                       const int32_t *__restrict__ axT_f,
+                       const double *__restrict__ axT_w,
+                       const double *__restrict__ bf,
+                       const double *__restrict__ Axf,
+                       const uint8_t *__restrict__ mask_c,
+                       double *__restrict__ bc) {
+  const int64_t nc = (int64_t)cnx * cny * cnz;
+  const int tot = cnx + cny + cnz;
+  GS(I, nc) {
+    const int iy = (int)(I % cny);
+    const int ix = (int)((I / cny) % cnx);
+    const int iz = (int)(I / ((int64_t)cny * cnx));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int sz = 0; sz < 3; ++sz) {
+      const int fz = axT_f[sz * tot + cnx + cny + iz];
+      if (fz < 0) continue;
+      const double wz = axT_w[sz * tot + cnx + cny + iz];
+      for (int sx = 0; sx < 3; ++sx) {
+        const int fx = axT_f[sx * tot + ix];
+        if (fx < 0) continue;
+        const double wx = axT_w[sx * tot + ix] * wz;
+        for (int sy = 0; sy < 3; ++sy) {
+          const int fy = axT_f[sy * tot + cnx + iy];
+          if (fy < 0) continue;
+          const double w = axT_w[sy * tot + cnx + iy] * wx;
+          const int64_t f = 3 * ((int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz);
+          a0 += w * (bf[f] - Axf[f]);
+          a1 += w * (bf[f + 1] - Axf[f + 1]);
+          a2 += w * (bf[f + 2] - Axf[f + 2]);
+        }
+      }
+    }
+    const int64_t o = 3 * I;
+    bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
+    bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+    bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+  }
+}
+
+// x_f += mask_f * P x_c ; one thread per fine node
+__global__ void __launch_bounds__(kBlock)
+    mg_prolong_kernel(int cnx, int cny, int cnz, int fnx, int fny, int fnz,
+                      const int32_t *__restrict__ c0, const int32_t *__restrict__ c1,
+                      const double *__restrict__ w0, const double *__restrict__ w1,
+                      const double *__restrict__ xc,
+                      const uint8_t *__restrict__ mask_f,
+                      double *__restrict__ xf) {
+  const int64_t nf = (int64_t)fnx * fny * fnz;
+  GS(F, nf) {
+    const int iy = (int)(F % fny);
+    const int ix = (int)((F / fny) % fnx);
+    const int iz = (int)(F / ((int64_t)fny * fnx));
+    const int cx[2] = {c0[ix], c1[ix]};
+    const double wx[2] = {w0[ix], w1[ix]};
+    const int cy[2] = {c0[fnx + iy], c1[fnx + iy]};
+    const double wy[2] = {w0[fnx + iy], w1[fnx + iy]};
+    const int cz[2] = {c0[fnx + fny + iz], c1[fnx + fny + iz]};
+    const double wz[2] = {w0[fnx + fny + iz], w1[fnx + fny + iz]};
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int kz = 0; kz < 2; ++kz) {
+      if (wz[kz] == 0.0) continue;
+#pragma unroll
+      for (int kx = 0; kx < 2; ++kx) {
+        if (wx[kx] == 0.0) continue;
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+          if (wy[ky] == 0.0) continue;
+          const double w = wz[kz] * wx[kx] * wy[ky];
+          const int64_t c = 3 * ((int64_t)cy[ky] + (int64_t)cny * cx[kx] +
+                                 (int64_t)cny * cnx * cz[kz]);
+          a0 += w * xc[c];
+          a1 += w * xc[c + 1];
+          a2 += w * xc[c + 2];
+        }
+      }
+    }
+    const int64_t o = 3 * F;
+    if (!(mask_f && mask_f[o])) xf[o] += a0;
+    if (!(mask_f && mask_f[o + 1])) xf[o + 1] += a1;
+    if (!(mask_f && mask_f[o + 2])) xf[o + 2] += a2;
+  }
+}
+
+static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st) {
+  int rc = launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
+                                l.node_col, l.vals, x, y, nullptr, nullptr,
+                                nullptr, nullptr, st);
+  if (rc != -1) return rc;
+  return launch_spmv_bsr3(l.n_nodes, l.node_ptr, l.node_col, l.vals, x, y,
+                          nullptr, nullptr, nullptr, nullptr, st);
+}
+
+// z = M^-1 r : V(1,1) cycle, level 0 reads r and writes z directly
+int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st) {
+  const int L = (int)m->lv.size();
+  const double om = m->omega;
+  // downward sweep
+  for (int k = 0; k < L; ++k) {
+    MgLevel &l = m->lv[k];
+    const int64_t n = 3 * l.n_nodes;
+    const double *b = (k == 0) ? r : l.b;
+    double *x = (k == 0) ? z : l.x;
+    const int g = grid_for(n);
+    mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
+    SKTB_COUNT(1);
+    if (k == L - 1) {
+      for (int s = 0; s < m->nu_coarse; ++s) {
+        if (level_spmv(l, x, l.tmp, st)) return 1;
+        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+        SKTB_COUNT(1);
+      }
+    } else {
+      if (level_spmv(l, x, l.tmp, st)) return 1;
+      MgLevel &c = m->lv[k + 1];
+      mg_restrict_kernel<<<grid_for(c.n_nodes), kBlock, 0, st>>>(
+          l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
+          l.axT_w, b, l.tmp, c.mask, c.b);
+      SKTB_COUNT(1);
+    }
+  }
+  // upward sweep
+  for (int k = L - 2; k >= 0; --k) {
+    MgLevel &l = m->lv[k];
+    MgLevel &c = m->lv[k + 1];
+    const int64_t n = 3 * l.n_nodes;
+    const double *b = (k == 0) ? r : l.b;
+    double *x = (k == 0) ? z : l.x;
+    mg_prolong_kernel<<<grid_for(l.n_nodes), kBlock, 0, st>>>(
+        l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.ax_c0,
+        l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, x);
+    SKTB_COUNT(1);
+    if (level_spmv(l, x, l.tmp, st)) return 1;
+    mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+    SKTB_COUNT(1);
+  }
+  SKTB_KERNEL_CHECK();
+  return 0;
+}
+
+extern "C" int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stream) {
+  SKTB_REQUIRE(m && r && z, "null argument");
+  for (auto &l : m->lv) SKTB_REQUIRE(l.node_ptr, "multigrid level not set");
+  return mg_vcycle(m, r, z, (cudaStream_t)stream);
+}

@@ -324,10 +324,30 @@ static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
                      S, st);
 }
 
+// rz (and optionally the rolled copy) <- r.z, for a general preconditioner
+__global__ void __launch_bounds__(kBlock)
+    pcg_rz_kernel(int64_t n, const double *__restrict__ r,
+                  const double *__restrict__ z, int set_both, double *partials,
+                  unsigned int *ticket, PcgScalars *Sloc, const PcgScalars *S) {
+  if (done(S)) return;
+  double v[1] = {0.0};
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) v[0] += r[i] * z[i];
+  __shared__ double res[1];
+  if (grid_reduce<1>(v, partials, ticket, res)) {
+    if (threadIdx.x == 0) {
+      Sloc->rz_new = res[0];
+      if (set_both) Sloc->rz = res[0];
+    }
+  }
+}
+
 static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                    const double *b, double *x, int use_x0, double rtol,
                    int maxiter, int check_every, int32_t *info_h,
-                   double *relres_h, void *stream) {
+                   double *relres_h, void *stream, sktb_mg *mg = nullptr) {
+  SKTB_REQUIRE(!(mg && s->comm), "the multigrid preconditioner is single-GPU");
   SKTB_REQUIRE(s && A.rp && A.ci && A.vals && inv_diag && b && x,
                "null argument");
   SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
@@ -354,6 +374,15 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
   SKTB_KERNEL_OK();
   // rz, pq, rz_new, rr, tol2, bb are the first six doubles of the struct
   if (reduce_scalars(s, &s->Sloc->rz, &s->S->rz, 6, st)) return 1;
+  if (mg) {
+    // z = M^-1 r by one V-cycle; p = z; rz = r.z
+    if (mg_vcycle(mg, s->r, s->z, st)) return 1;
+    SKTB_CUDA_OK(cudaMemcpyAsync(p_own, s->z, sizeof(double) * n,
+                                 cudaMemcpyDeviceToDevice, st));
+    pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 1, s->partials,
+                                           s->ticket, s->Sloc, s->S);
+    SKTB_KERNEL_OK();
+  }
   int launched = 0;
   int n_ev = 0;
   while (true) {
@@ -385,6 +414,12 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                                                  s->r, s->z, s->partials,
                                                  s->ticket, s->Sloc, s->S);
       if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
+      if (mg) {
+        if (mg_vcycle(mg, s->r, s->z, st)) return 1;
+        pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 0, s->partials,
+                                               s->ticket, s->Sloc, s->S);
+        SKTB_COUNT(1);
+      }
       pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, p_own, s->ticket,
                                                     s->S);
       SKTB_COUNT(2);
@@ -424,4 +459,19 @@ extern "C" int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
   PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
   return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
                  info_h, relres_h, stream);
+}
+
+extern "C" int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg,
+                                      const int32_t *node_ptr,
+                                      const int32_t *node_col, int64_t n_blocks,
+                                      int max_deg, const double *vals,
+                                      const double *inv_diag, const double *b,
+                                      double *x, int use_x0, double rtol,
+                                      int maxiter, int check_every,
+                                      int32_t *info_h, double *relres_h,
+                                      void *stream) {
+  SKTB_REQUIRE(s && mg && s->n % 3 == 0, "block solve needs 3 dofs per node");
+  PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
+  return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
+                 info_h, relres_h, stream, mg);
 }

@@ -189,12 +189,16 @@ class DeviceMesh:
         return self._unit_ke[key]
 
     # -- kernels ---------------------------------------------------------------
-    def assemble(self, dpn, unit_ke, scale=None, dir_mask=None, out=None):
+    def assemble(self, dpn, unit_ke, scale=None, dir_mask=None, out=None,
+                 per_element=False):
+        """``per_element=True``: ``unit_ke`` holds one matrix per element (the
+        class table is bypassed), e.g. Galerkin coarse element matrices."""
         if out is None:
             out = torch.empty(dpn * dpn * self.node_nnz, dtype=F64, device="cuda")
+        cls = None if per_element else self.elem_class
         _lib.check(
             self.lib.sktb_assemble(
-                self.handle, dpn, _ptr(unit_ke), _ptr(self.elem_class), _ptr(scale),
+                self.handle, dpn, _ptr(unit_ke), _ptr(cls), _ptr(scale),
                 _ptr(dir_mask), _ptr(out), _stream(),
             )
         )
@@ -344,6 +348,16 @@ def spmv_bsr3(node_ptr, node_col, vals, x, out=None):
     return out
 
 
+def bsr3_inv_diag(node_ptr, node_col, vals, out=None):
+    n_nodes = node_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_bsr3_inv_diag(n_nodes, _ptr(node_ptr), _ptr(node_col), _ptr(vals), _ptr(out), _stream())
+    )
+    return out
+
+
 def spmv_bsr3_tma(node_ptr, node_col, vals, x, max_deg, out=None):
     """Bulk-async pipelined variant of ``spmv_bsr3`` (max_deg <= 27)."""
     n_nodes = node_ptr.numel() - 1
@@ -431,7 +445,7 @@ class PcgSolver:
 
     def solve(self, row_ptr, col_idx, vals, inv_diag, b, x, dpn_hint, rtol=1e-8,
               maxiter=1000, use_x0=False, check_every=32, block3=False,
-              max_deg=0):
+              max_deg=0, mg=None):
         """``block3=True``: ``row_ptr`` / ``col_idx`` are the node-level graph
         (one column per 3x3 block), ``vals`` keeps the CSR layout."""
         info = (C.c_int32 * 2)()
@@ -439,7 +453,11 @@ class PcgSolver:
         tail = (_ptr(inv_diag), _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
                 int(maxiter), int(check_every), C.cast(info, C.c_void_p),
                 C.cast(C.byref(relres), C.c_void_p), _stream())
-        if block3:
+        if mg is not None:
+            _lib.check(self.lib.sktb_pcg_solve_bsr3_mg(
+                self.handle, mg.handle, _ptr(row_ptr), _ptr(col_idx), int(col_idx.numel()),
+                int(max_deg), _ptr(vals), *tail))
+        elif block3:
             _lib.check(self.lib.sktb_pcg_solve_bsr3(
                 self.handle, _ptr(row_ptr), _ptr(col_idx), int(col_idx.numel()),
                 int(max_deg), _ptr(vals), *tail))

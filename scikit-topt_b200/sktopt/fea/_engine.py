@@ -13,6 +13,8 @@ element-wise stages see the full vector.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -78,6 +80,27 @@ class FeaEngine:
         self.inv_diag = torch.empty(self.n_local, dtype=dev.F64, device="cuda")
         self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
         self.rhs = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
+        # preconditioner: "mg" (geometric multigrid, tensor hex grids, one GPU)
+        # or "jacobi"; SKTOPT_B200_PRECOND = jacobi | mg | auto overrides
+        self.precond = "jacobi"
+        self.mg = None
+        self.mg_enabled = True      # solver selector 'cg_jacobi' switches it off
+        want = os.environ.get("SKTOPT_B200_PRECOND", "auto").lower()
+        if want not in ("jacobi", "mg", "auto"):
+            raise ValueError("SKTOPT_B200_PRECOND must be jacobi, mg or auto")
+        if dpn == 3 and comm is None and want != "jacobi" and dm.elem_class is not None:
+            from sktopt.fea._multigrid import Multigrid, detect_tensor_grid
+            axes = detect_tensor_grid(basis.mesh)
+            big = dm.n_nodes >= Multigrid.MIN_FINE_NODES or want == "mg"
+            if axes is not None and big:
+                try:
+                    self.mg = Multigrid(self, axes)
+                    self.precond = "mg"
+                except ValueError:
+                    self.mg = None
+        if want == "mg" and self.mg is None:
+            raise RuntimeError("multigrid preconditioner requested but the mesh is not an "
+                               "eligible tensor hexahedral grid (or the run is sharded)")
         self.u = {}  # load index -> device solution (warm start), full length
         self.warm_start = True
         self.pcg_log = []  # (iters, converged, relres) of every solve
@@ -103,6 +126,8 @@ class FeaEngine:
         dev.csr_inv_diag(self.row_ptr, self.col_idx,
                          self.vals if vals is None else vals, out=self.inv_diag,
                          row0=self.row0)
+        if self.mg is not None and self.mg_enabled and vals is None:
+            self.mg.setup()
 
     def solution(self, load: int):
         if load not in self.u:
@@ -116,13 +141,16 @@ class FeaEngine:
         mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
         lo, hi = self.row0, self.row0 + self.n_local
         block3 = self.spmv_format == "bsr3"
+        use_mg = self.mg is not None and self.mg_enabled and vals is None
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,
                        rhs[lo:hi], x[lo:hi],
                        dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
-                       use_x0=self.warm_start, check_every=32, block3=block3,
-                       max_deg=getattr(self, "max_deg", 0))
+                       use_x0=self.warm_start,
+                       check_every=2 if use_mg else 32, block3=block3,
+                       max_deg=getattr(self, "max_deg", 0),
+                       mg=self.mg if use_mg else None)
         if self.sharded:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]

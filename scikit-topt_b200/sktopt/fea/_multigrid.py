@@ -1,0 +1,248 @@
+"""Host-side set-up of the geometric multigrid preconditioner (``csrc/mg.cu``).
+
+Stands in for ``pyamg.smoothed_aggregation_solver(K).aspreconditioner()`` of the
+reference's ``cg_pyamg`` path (``fea/solver_elastic.py:94-104``) on
+tensor-product hexahedral meshes (``create_box_hex``): the grid hierarchy halves
+the cell counts per level, prolongation is trilinear, and the coarse operators
+are exact Galerkin products formed element-wise on the device every time K(rho)
+changes.  A preconditioner only changes the iteration count, not the converged
+solution, so parity tests are unaffected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from sktopt._b200 import device as dev
+from sktopt._b200 import lib as _lib
+from sktopt._fem import MeshHex
+
+
+def detect_tensor_grid(mesh):
+    """(xs, ys, zs) if ``mesh`` is exactly ``MeshHex.init_tensor(xs, ys, zs)``
+    (same node numbering and connectivity), else None."""
+    if not isinstance(mesh, MeshHex):
+        return None
+    p = mesh.p
+    xs, ys, zs = (np.unique(p[d]) for d in range(3))
+    if xs.size * ys.size * zs.size != p.shape[1] or min(xs.size, ys.size, zs.size) < 2:
+        return None
+    ref = MeshHex.init_tensor(xs, ys, zs)
+    if ref.t.shape != mesh.t.shape or not np.array_equal(ref.t, mesh.t):
+        return None
+    if not np.array_equal(ref.p, p):
+        return None
+    return xs, ys, zs
+
+
+def coarse_index_map(n_cells: int) -> np.ndarray:
+    """Fine node index of every coarse node along one axis."""
+    nc = (n_cells + 1) // 2
+    return np.minimum(2 * np.arange(nc + 1), n_cells)
+
+
+def axis_tables(n_cells: int):
+    """1-D linear interpolation between the nested node sets of one axis.
+
+    Returns (c0, c1, w0, w1) indexed by fine node and (fT (3, nc+1), wT (3, nc+1))
+    indexed by coarse node (-1 = empty slot)."""
+    fmap = coarse_index_map(n_cells)
+    nc = fmap.size - 1
+    c0 = np.zeros(n_cells + 1, dtype=np.int32)
+    c1 = np.zeros(n_cells + 1, dtype=np.int32)
+    w0 = np.zeros(n_cells + 1)
+    w1 = np.zeros(n_cells + 1)
+    coarse_of = {int(f): i for i, f in enumerate(fmap)}
+    for i in range(n_cells + 1):
+        if i in coarse_of:
+            c0[i] = c1[i] = coarse_of[i]
+            w0[i] = 1.0
+        else:                       # midpoint of a full coarse cell
+            c0[i] = coarse_of[i - 1]
+            c1[i] = coarse_of[i + 1]
+            w0[i] = w1[i] = 0.5
+    fT = np.full((3, nc + 1), -1, dtype=np.int32)
+    wT = np.zeros((3, nc + 1))
+    fill = np.zeros(nc + 1, dtype=int)
+    for i in range(n_cells + 1):
+        for c, w in ((c0[i], w0[i]), (c1[i], w1[i])):
+            if w != 0.0:
+                fT[fill[c], c] = i
+                wT[fill[c], c] = w
+                fill[c] += 1
+    return c0, c1, w0, w1, fT, wT
+
+
+_W1D = {
+    (0, 0): np.array([[1.0, 0.0], [0.5, 0.5]]),   # full parent, first child
+    (0, 1): np.array([[0.5, 0.5], [0.0, 1.0]]),   # full parent, second child
+    (1, 0): np.array([[1.0, 0.0], [0.0, 1.0]]),   # half parent (single child)
+    (1, 1): np.zeros((2, 2)),
+}
+
+
+def vertex_bits(mesh) -> np.ndarray:
+    """(8, 3) 0/1 offsets (x, y, z) of the local vertices, read off element 0."""
+    xe = mesh.p[:, mesh.t[:, 0]]
+    lo = xe.min(axis=1, keepdims=True)
+    hi = xe.max(axis=1, keepdims=True)
+    return (xe > 0.5 * (lo + hi)).T.astype(int)
+
+
+def q_tables(bits: np.ndarray) -> np.ndarray:
+    """Qtab[type][child][a][A]: weight of parent vertex A in child vertex a.
+    type = tx + 2 ty + 4 tz (t = 1: the parent has a single child along that
+    axis), child = cx + 2 cy + 4 cz."""
+    Q = np.zeros((8, 8, 8, 8))
+    for ty_ in range(8):
+        t = (ty_ & 1, (ty_ >> 1) & 1, (ty_ >> 2) & 1)
+        for ch in range(8):
+            c = (ch & 1, (ch >> 1) & 1, (ch >> 2) & 1)
+            W = [_W1D[(t[d], c[d])] for d in range(3)]
+            for a in range(8):
+                for A in range(8):
+                    Q[ty_, ch, a, A] = np.prod([W[d][bits[a, d], bits[A, d]] for d in range(3)])
+    return Q
+
+
+def child_tables(fine_cells, coarse_cells):
+    """child[c][E] (fine element id or -1) and ptype[E] for every coarse
+    element; element id = ey + ny*ex + ny*nx*ez on both levels."""
+    nx, ny, nz = fine_cells
+    cx_, cy_, cz_ = coarse_cells
+    Ez, Ex, Ey = np.meshgrid(np.arange(cz_), np.arange(cx_), np.arange(cy_), indexing="ij")
+    Ex, Ey, Ez = Ex.ravel(), Ey.ravel(), Ez.ravel()      # ordered by element id
+    child = np.full((8, Ex.size), -1, dtype=np.int32)
+    for ch in range(8):
+        c = (ch & 1, (ch >> 1) & 1, (ch >> 2) & 1)
+        fx, fy, fz = 2 * Ex + c[0], 2 * Ey + c[1], 2 * Ez + c[2]
+        ok = (fx < nx) & (fy < ny) & (fz < nz)
+        child[ch, ok] = (fy + ny * fx + ny * nx * fz)[ok]
+    half = lambda E, n: (2 * E + 1 >= n).astype(np.uint8)
+    ptype = (half(Ex, nx) + 2 * half(Ey, ny) + 4 * half(Ez, nz)).astype(np.uint8)
+    return child, ptype
+
+
+class Multigrid:
+    """Grid hierarchy + Galerkin set-up for one elasticity engine."""
+
+    MIN_FINE_NODES = 1500
+
+    def __init__(self, engine, axes, omega: float = 0.5, nu_coarse: int = 30,
+                 coarsest_max_cells: int = 6):
+        self.lib = _lib.load()
+        self.eng = engine
+        xs, ys, zs = axes
+        coords = [(xs, ys, zs)]
+        while True:
+            cx, cy, cz = (c.size - 1 for c in coords[-1])
+            if max(cx, cy, cz) <= coarsest_max_cells or min(cx, cy, cz) <= 2:
+                break
+            coords.append(tuple(a[coarse_index_map(a.size - 1)] for a in coords[-1]))
+        self.coords = coords
+        self.n_levels = len(coords)
+        if self.n_levels < 2:
+            raise ValueError("grid too small for a multigrid hierarchy")
+        fine_mesh = engine.basis.mesh
+        bits = vertex_bits(fine_mesh)
+        self.Qtab = dev.to_dev(q_tables(bits).ravel())
+        h = C.c_void_p()
+        _lib.check(self.lib.sktb_mg_create(C.byref(h), self.n_levels, torch.cuda.current_device()))
+        self.handle = h
+        _lib.check(self.lib.sktb_mg_set_params(h, float(omega), int(nu_coarse)))
+        self.levels = [None]          # level 0 lives in the engine
+        self.transfers = []
+        mask_f = engine.dir_mask.cpu().numpy()
+        for l in range(1, self.n_levels):
+            cxs, cys, czs = coords[l]
+            mesh_c = MeshHex.init_tensor(cxs, cys, czs)
+            if not np.array_equal(vertex_bits(mesh_c), bits):
+                raise RuntimeError("coarse and fine meshes disagree on local vertex order")
+            dm = dev.DeviceMesh(mesh_c)
+            rp_h, ci_h = dm.node_graph()
+            fine_cells = tuple(c.size - 1 for c in coords[l - 1])
+            coarse_cells = tuple(c.size - 1 for c in coords[l])
+            child, ptype = child_tables(fine_cells, coarse_cells)
+            # Dirichlet mask: a coarse dof is fixed iff the coincident fine dof is
+            fm = [coarse_index_map(n) for n in fine_cells]
+            npx_f, npy_f = fine_cells[0] + 1, fine_cells[1] + 1
+            Iz, Ix, Iy = np.meshgrid(np.arange(coarse_cells[2] + 1), np.arange(coarse_cells[0] + 1),
+                                     np.arange(coarse_cells[1] + 1), indexing="ij")
+            fnode = (fm[1][Iy] + npy_f * fm[0][Ix] + npy_f * npx_f * fm[2][Iz]).ravel()
+            mask_c = mask_f.reshape(-1, 3)[fnode].ravel().copy()
+            lvl = dict(
+                dm=dm, n_nodes=dm.n_nodes, n_elem=dm.n_elem,
+                node_ptr=dev.to_dev(rp_h, dev.I32), node_col=dev.to_dev(ci_h, dev.I32),
+                max_deg=int(np.diff(rp_h).max()),
+                vals=torch.empty(9 * ci_h.size, dtype=dev.F64, device="cuda"),
+                inv_diag=torch.empty(3 * dm.n_nodes, dtype=dev.F64, device="cuda"),
+                mask=dev.to_dev(mask_c, dev.U8),
+                ke=torch.empty((dm.n_elem, 576), dtype=dev.F64, device="cuda"),
+                child=dev.to_dev(child, dev.I32), ptype=dev.to_dev(ptype, dev.U8),
+            )
+            self.levels.append(lvl)
+            # transfer tables fine (l-1) -> coarse (l), concatenated [x | y | z]
+            tabs = [axis_tables(n) for n in fine_cells]
+            cat = lambda k, dt: np.ascontiguousarray(np.concatenate([t[k] for t in tabs]).astype(dt))
+            catT = lambda k, dt: np.ascontiguousarray(np.concatenate([t[k] for t in tabs], axis=1).astype(dt))
+            tr = dict(
+                c0=dev.to_dev(cat(0, np.int32), dev.I32), c1=dev.to_dev(cat(1, np.int32), dev.I32),
+                w0=dev.to_dev(cat(2, np.float64)), w1=dev.to_dev(cat(3, np.float64)),
+                fT=dev.to_dev(catT(4, np.int32).ravel(), dev.I32), wT=dev.to_dev(catT(5, np.float64).ravel()),
+                fnp=np.array([n + 1 for n in fine_cells], dtype=np.int32),
+                cnp=np.array([n + 1 for n in coarse_cells], dtype=np.int32),
+            )
+            self.transfers.append(tr)
+            _lib.check(self.lib.sktb_mg_set_transfer(
+                h, l - 1, tr["fnp"].ctypes.data_as(C.c_void_p), tr["cnp"].ctypes.data_as(C.c_void_p),
+                dev._ptr(tr["c0"]), dev._ptr(tr["c1"]), dev._ptr(tr["w0"]), dev._ptr(tr["w1"]),
+                dev._ptr(tr["fT"]), dev._ptr(tr["wT"])))
+            mask_f = mask_c
+        self.setup_count = 0
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_mg_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def setup(self):
+        """Galerkin coarse operators for the engine's current modulus field;
+        call after the engine assembled level 0 and its inverse diagonal."""
+        eng = self.eng
+        st = dev._stream()
+        lib = self.lib
+        _lib.check(lib.sktb_mg_set_level(
+            self.handle, 0, eng.dm.n_nodes, int(eng.node_col_loc.numel()), int(eng.max_deg),
+            dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc), dev._ptr(eng.vals),
+            dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        for l in range(1, self.n_levels):
+            lv = self.levels[l]
+            if l == 1:
+                _lib.check(lib.sktb_elem_restrict(
+                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
+                    None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
+                    dev._ptr(lv["ke"]), st))
+            else:
+                _lib.check(lib.sktb_elem_restrict(
+                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
+                    dev._ptr(self.levels[l - 1]["ke"]), None, None, None, dev._ptr(lv["ke"]), st))
+            lv["dm"].assemble(3, lv["ke"], scale=None, dir_mask=lv["mask"], out=lv["vals"],
+                              per_element=True)
+            dev.bsr3_inv_diag(lv["node_ptr"], lv["node_col"], lv["vals"], out=lv["inv_diag"])
+            _lib.check(lib.sktb_mg_set_level(
+                self.handle, l, lv["n_nodes"], int(lv["node_col"].numel()), lv["max_deg"],
+                dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
+                dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+        self.setup_count += 1
+
+    def vcycle(self, r, z=None):
+        if z is None:
+            z = torch.empty_like(r)
+        _lib.check(self.lib.sktb_mg_vcycle(self.handle, dev._ptr(r), dev._ptr(z), dev._stream()))
+        return z

@@ -103,6 +103,9 @@ def _run_loads(basis, dirichlet_dofs, force_list, E0, Emin, p, nu0, rho, u_all,
     returns (compliances, engine)."""
     _check_solver(solver_cfg.solver)
     eng = get_engine(basis, dirichlet_dofs, KE_ELASTIC, nu0)
+    # 'cg_jacobi' asks for the diagonal preconditioner; every other selector
+    # gets the multigrid V-cycle when the mesh is an eligible tensor grid
+    eng.mg_enabled = solver_cfg.solver != "cg_jacobi"
     rho_d = dev.to_dev(rho)
     with _section(timer, "assemble"):
         eng.set_modulus(rho_d, E0, Emin, p, ramp=composer.is_ramp(elem_func))

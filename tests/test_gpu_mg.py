@@ -1,0 +1,142 @@
+"""Geometric multigrid preconditioner: Galerkin coarse operators equal
+P^T A P, the V-cycle is a symmetric operator, and MG-PCG converges to the same
+solution as Jacobi-PCG / the direct solver in far fewer iterations."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sktopt
+    from sktopt._b200 import device as dev
+    return sktopt, dev
+
+
+def _engine(sktopt, dims=(2.8, 2.0, 1.6), h=0.4, monkey=None):
+    from sktopt._fem import Basis, ElementHex1, ElementVector
+    from sktopt.fea._engine import FeaEngine, KE_ELASTIC
+    mesh = sktopt.mesh.toy_problem.create_box_hex(*dims, h)       # 7 x 5 x 4 cells (odd sizes)
+    basis = Basis(mesh, ElementVector(ElementHex1()), intorder=2)
+    clamp = np.nonzero(mesh.p[0] == 0.0)[0]
+    D = np.unique((3 * clamp[:, None] + np.arange(3)[None, :]).ravel())
+    return mesh, basis, D, FeaEngine(basis, D, KE_ELASTIC, 0.3)
+
+
+def _prolongation(mg, level):
+    """scipy P (fine nodes x coarse nodes) from the axis tables, per component."""
+    from sktopt.fea._multigrid import axis_tables
+    fine_cells = tuple(c.size - 1 for c in mg.coords[level])
+    mats = []
+    for n in fine_cells:
+        c0, c1, w0, w1, _, _ = axis_tables(n)
+        nc = (n + 1) // 2
+        P = sp.lil_matrix((n + 1, nc + 1))
+        for i in range(n + 1):
+            P[i, c0[i]] += w0[i]
+            P[i, c1[i]] += w1[i]
+        mats.append(P.tocsr())
+    Px, Py, Pz = mats
+    # node = iy + npy*ix + npy*npx*iz  ->  kron(Pz, kron(Px, Py))
+    Pn = sp.kron(Pz, sp.kron(Px, Py)).tocsr()
+    return sp.kron(Pn, sp.eye(3)).tocsr()
+
+
+def test_galerkin_coarse_operator_equals_PtAP(gpu, monkeypatch):
+    sktopt, dev = gpu
+    monkeypatch.setenv("SKTOPT_B200_PRECOND", "mg")
+    mesh, basis, D, eng = _engine(sktopt)
+    assert eng.precond == "mg" and eng.mg.n_levels >= 2
+    rho = np.random.default_rng(0).uniform(0.05, 1.0, mesh.nelements)
+    eng.set_modulus(dev.to_dev(rho), 210e3, 210.0, 3.0)
+    eng.assemble(enforce=False)
+    rp, ci = eng.dm.dof_pattern(3)
+    K = sktopt.fea.composer._csr_to_scipy(eng.n_dof, rp, ci, eng.vals)
+    mg = eng.mg
+    lv = mg.levels[1]
+    from sktopt._b200 import lib as _lib
+    _lib.check(mg.lib.sktb_elem_restrict(
+        lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(mg.Qtab),
+        None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
+        dev._ptr(lv["ke"]), dev._stream()))
+    vals = lv["dm"].assemble(3, lv["ke"], scale=None, dir_mask=None, per_element=True)
+    rpc, cic = lv["dm"].dof_pattern(3)
+    Kc = sktopt.fea.composer._csr_to_scipy(3 * lv["n_nodes"], rpc, cic, vals)
+    P = _prolongation(mg, 0)
+    ref = (P.T @ K @ P).tocsr()
+    assert abs(Kc - ref).max() <= 1e-10 * abs(ref).max()
+    # uniform modulus: the Galerkin element matrix of a full 2x2x2 parent is the
+    # geometric element matrix of the coarse element
+    eng.set_modulus(dev.to_dev(np.ones(mesh.nelements)), 1.0, 0.0, 1.0)
+    _lib.check(mg.lib.sktb_elem_restrict(
+        lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(mg.Qtab),
+        None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
+        dev._ptr(lv["ke"]), dev._stream()))
+    geo = lv["dm"].unit_ke(0, basis.X, basis.W, nu=0.3)
+    cls = lv["dm"].elem_class.cpu().numpy()
+    full = np.nonzero(lv["ptype"].cpu().numpy() == 0)[0]
+    got = lv["ke"].cpu().numpy()[full].reshape(-1, 24, 24)
+    want = geo.cpu().numpy()[cls[full]]
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.abs(want).max()
+
+
+def test_vcycle_is_symmetric_and_mg_pcg_converges(gpu, monkeypatch):
+    sktopt, dev = gpu
+    from oracle import fem
+    monkeypatch.setenv("SKTOPT_B200_PRECOND", "mg")
+    mesh, basis, D, eng = _engine(sktopt, dims=(4.0, 3.0, 2.0), h=0.25)   # 16 x 12 x 8
+    rho = np.random.default_rng(1).uniform(0.01, 1.0, mesh.nelements)
+    eng.set_modulus(dev.to_dev(rho), 210e3, 210.0, 3.0)
+    eng.assemble(enforce=True)
+    eng.update_preconditioner()
+    rng = np.random.default_rng(2)
+    a, b = rng.standard_normal(eng.n_dof), rng.standard_normal(eng.n_dof)
+    a[D] = 0.0
+    b[D] = 0.0
+    Ma = eng.mg.vcycle(dev.to_dev(a)).cpu().numpy()
+    Mb = eng.mg.vcycle(dev.to_dev(b)).cpu().numpy()
+    assert abs(Ma @ b - a @ Mb) <= 1e-10 * abs(Ma @ b)
+    assert a @ Ma > 0 and b @ Mb > 0
+    assert np.all(Ma[D] == 0.0)
+    # solve with MG-PCG and with Jacobi-PCG
+    f = np.zeros(eng.n_dof)
+    tip = np.nonzero(mesh.p[0] == mesh.p[0].max())[0]
+    f[3 * tip + 2] = -1.0
+    f[D] = 0.0
+    fd = dev.to_dev(f)
+    eng.warm_start = False
+    u_mg = eng.solve(fd, 0, 1e-9, None).cpu().numpy().copy()
+    it_mg = eng.pcg_log[-1][0]
+    eng.mg_enabled = False
+    u_j = eng.solve(fd, 1, 1e-9, None).cpu().numpy().copy()
+    it_j = eng.pcg_log[-1][0]
+    K = fem.assemble_stiffness(mesh.p, mesh.t, rho, 210e3, 210.0, 3.0, 0.3)
+    K_e, f_e = fem.enforce(K, f, D)
+    u_ref, _, _ = fem.solve(K_e, f_e, "spsolve")
+    assert eng.pcg_log[-2][1] and eng.pcg_log[-1][1]
+    assert np.max(np.abs(u_mg - u_ref)) <= 1e-6 * np.abs(u_ref).max()
+    assert np.max(np.abs(u_j - u_ref)) <= 1e-6 * np.abs(u_ref).max()
+    print("iterations: multigrid", it_mg, "jacobi", it_j)
+    assert it_mg * 5 < it_j
+
+
+def test_selector_cg_jacobi_disables_multigrid(gpu):
+    sktopt, dev = gpu
+    tsk = sktopt.mesh.toy_problem.toy_base(0.45)
+    rho = np.full(tsk.mesh.nelements, 0.5)
+    u = np.zeros((tsk.basis.N, 1))
+    f_mg = sktopt.fea.FEM_SimpLinearElasticity(tsk, 1e-3, solver_option="cg_pyamg")
+    c_mg = f_mg.objectives_multi_load(rho, 3.0, u)
+    assert f_mg.engine.precond == "mg"
+    it_mg = f_mg.engine.pcg_log[-1][0]
+    f_j = sktopt.fea.FEM_SimpLinearElasticity(tsk, 1e-3, solver_option="cg_jacobi")
+    f_j.engine.warm_start = False
+    c_j = f_j.objectives_multi_load(rho, 3.0, u)
+    it_j = f_j.engine.pcg_log[-1][0]
+    assert abs(c_mg[0] - c_j[0]) <= 1e-7 * abs(c_j[0])
+    assert it_mg < it_j
