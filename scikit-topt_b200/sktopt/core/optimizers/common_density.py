@@ -459,7 +459,10 @@ class DensityMethod(DensityMethodBase):
     # ----------------------------------------------------------------- loop
     def _optimize_impl(self, max_steps: int | None = None):
         tsk, cfg = self.tsk, self.cfg
-        tsk.export_analysis_condition_on_mesh(cfg.dst_path)
+        if not getattr(self, "_condition_exported", False):
+            # the reference rewrites this file on every call; once is enough
+            tsk.export_analysis_condition_on_mesh(cfg.dst_path)
+            self._condition_exported = True
         if not self._ensure_state_initialized():
             return
         _, dC_drho_func = interpolation_funcs(cfg)

@@ -94,7 +94,8 @@ class FeaEngine:
             big = dm.n_nodes >= Multigrid.MIN_FINE_NODES or want == "mg"
             if axes is not None and big:
                 try:
-                    self.mg = Multigrid(self, axes)
+                    om = os.environ.get("SKTOPT_B200_MG_OMEGA")
+                    self.mg = Multigrid(self, axes, omega=None if om is None else float(om))
                     self.precond = "mg"
                 except ValueError:
                     self.mg = None
@@ -142,15 +143,23 @@ class FeaEngine:
         lo, hi = self.row0, self.row0 + self.n_local
         block3 = self.spmv_format == "bsr3"
         use_mg = self.mg is not None and self.mg_enabled and vals is None
+        mi_first = min(mi, 400) if use_mg else mi
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,
                        rhs[lo:hi], x[lo:hi],
-                       dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
+                       dpn_hint=self.dpn, rtol=rtol, maxiter=mi_first,
                        use_x0=self.warm_start,
                        check_every=2 if use_mg else 32, block3=block3,
                        max_deg=getattr(self, "max_deg", 0),
                        mg=self.mg if use_mg else None)
+        if use_mg and not self.pcg.last_converged:
+            # safety net: a V-cycle that stopped contracting (smoother out of its
+            # stability range) must not cost the solve -- finish with Jacobi
+            logger.warning("multigrid PCG did not converge; continuing with Jacobi PCG")
+            self.pcg.solve(self.node_ptr_loc, self.node_col_loc, self.vals, self.inv_diag,
+                           rhs[lo:hi], x[lo:hi], dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
+                           use_x0=True, check_every=32, block3=True, max_deg=self.max_deg)
         if self.sharded:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]

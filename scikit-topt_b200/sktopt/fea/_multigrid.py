@@ -130,10 +130,15 @@ class Multigrid:
 
     MIN_FINE_NODES = 1500
 
-    def __init__(self, engine, axes, omega: float = 0.5, nu_coarse: int = 30,
+    def __init__(self, engine, axes, omega: float | None = None, nu_coarse: int = 30,
                  coarsest_max_cells: int = 6):
         self.lib = _lib.load()
         self.eng = engine
+        self.omega_auto = omega is None
+        self.omega = 0.5 if omega is None else float(omega)
+        self.nu_coarse = int(nu_coarse)
+        self.lambda_max = None
+        omega = self.omega
         xs, ys, zs = axes
         coords = [(xs, ys, zs)]
         while True:
@@ -211,10 +216,35 @@ class Multigrid:
                 pass
             self.handle = None
 
+    def estimate_lambda_max(self, iters: int = 12) -> float:
+        """Largest eigenvalue of D^-1 A on level 0 by power iteration (the
+        damped-Jacobi smoother needs omega < 2 / lambda_max)."""
+        eng = self.eng
+        n = eng.n_dof
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1234)
+        v = torch.rand(n, dtype=dev.F64, device="cuda", generator=g) - 0.5
+        w = torch.empty_like(v)
+        lam = 1.0
+        for _ in range(iters):
+            v /= float(np.sqrt(dev.dot(v, v)))
+            dev.spmv_bsr3(eng.node_ptr_loc, eng.node_col_loc, eng.vals, v, out=w)
+            dev.hadamard(1.0, w, eng.inv_diag, w)
+            lam = dev.dot(v, w)
+            v, w = w, v
+        return float(lam)
+
     def setup(self):
         """Galerkin coarse operators for the engine's current modulus field;
         call after the engine assembled level 0 and its inverse diagonal."""
         eng = self.eng
+        if self.omega_auto and self.setup_count == 0:
+            lam = self.estimate_lambda_max()
+            self.lambda_max = lam
+            # omega * lambda_max = 1.6: inside the stability bound 2 with margin
+            self.omega = 1.6 / (1.05 * lam)
+            _lib.check(self.lib.sktb_mg_set_params(self.handle, float(self.omega),
+                                                   int(self.nu_coarse)))
         st = dev._stream()
         lib = self.lib
         _lib.check(lib.sktb_mg_set_level(

@@ -1,0 +1,38 @@
+"""Per-section wall-clock breakdown of optimiser iterations at C2 (device
+synchronised at section exits).  Usage: python scripts/step_breakdown.py [h] [iters]"""
+import json, os, sys, tempfile, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scikit-topt_b200"))
+import sktopt
+from sktopt._b200 import device as dev
+
+h = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0577
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+kind = sys.argv[3] if len(sys.argv) > 3 else "logmoc"
+tsk = sktopt.mesh.toy_problem.toy_base(h)
+tmp = tempfile.mkdtemp()
+if kind == "logmoc":
+    cfg = sktopt.core.LogMOC_Config(dst_path=tmp, max_iters=200, record_times=20,
+                                    vol_frac=sktopt.tools.SchedulerConfig.constant(target_value=0.3),
+                                    solver_option="cg_pyamg")
+    opt = sktopt.core.LogMOC_Optimizer(cfg, tsk)
+else:
+    cfg = sktopt.core.OC_Config(dst_path=tmp, max_iters=200, record_times=20, solver_option="cg_pyamg",
+                                vol_frac=sktopt.tools.SchedulerConfig.constant(target_value=0.3))
+    opt = sktopt.core.OC_Optimizer(cfg, tsk)
+opt.parameterize()
+opt.export_enabled = False
+opt.optimize_steps(3)
+opt.timer.reset()
+opt.timer.cuda_sync = True
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+opt.optimize_steps(n)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+st = opt.timer.stats()
+print("ms/step", dt * 1e3)
+for k, v in sorted(st.items(), key=lambda kv: -kv[1]["total"]):
+    print(f"{k:60s} {v['total']/n*1e3:9.2f} ms/step  n={v['count']//n}")
+print("pcg", opt.fem.engine.pcg_log[-n:], "filter iters", opt.filter._dev_state.solve_iters[-8:])
