@@ -158,6 +158,11 @@ int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes, int64_t n_blocks,
                       int max_deg, const int32_t *node_ptr,
                       const int32_t *node_col, const double *vals,
                       const double *inv_diag, const uint8_t *mask);
+/* level 0 of a row-sharded operator: this rank owns the nodes starting at
+ * node0 out of n_global (call before sktb_mg_set_level(m, 0, n_owned, ...)).
+ * Coarser levels stay replicated; the restricted residual is all-reduced and
+ * the level-0 smoother exchanges halos through the PCG workspace it runs in.  */
+int sktb_mg_set_level0_range(sktb_mg *m, int64_t node0, int64_t n_global);
 /* transfer between level (fine) and level+1 (coarse).  Nodes per axis (x,y,z)
  * of both grids (node = iy + npy*ix + npy*npx*iz); per-axis interpolation
  * tables on the device, concatenated [x|y|z]: fine index i takes coarse

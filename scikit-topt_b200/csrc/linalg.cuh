@@ -42,4 +42,12 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
 
 // multigrid preconditioner z = M^-1 r (mg.cu)
 struct sktb_mg;
-int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st);
+struct sktb_pcg;
+// `dist` (may be null) supplies the halo exchange / all-reduce of a row-sharded
+// level 0; coarser levels are replicated
+int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
+              sktb_pcg *dist = nullptr);
+// row-sharded helpers implemented by the PCG workspace (pcg.cu)
+bool pcg_is_dist(const sktb_pcg *s);
+int pcg_halo_exchange(sktb_pcg *s, double *full_vec, cudaStream_t st);
+int pcg_allreduce_vec(sktb_pcg *s, double *buf, int64_t n, cudaStream_t st);

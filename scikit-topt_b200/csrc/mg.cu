@@ -26,6 +26,9 @@ struct MgLevel {
   const double *vals = nullptr, *inv_diag = nullptr;
   const uint8_t *mask = nullptr;  // per dof, may be null
   double *x = nullptr, *b = nullptr, *tmp = nullptr;  // owned work vectors
+  // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
+  // the operator is not sharded); x is always full length (n_global nodes)
+  int64_t node0 = 0, n_global = 0;
   // transfer to the next coarser level (tensor grid tables, device)
   int32_t fnp[3] = {0, 0, 0}, cnp[3] = {0, 0, 0};  // nodes per axis (x, y, z)
   const int32_t *ax_c0 = nullptr, *ax_c1 = nullptr;  // [fnx | fny | fnz]
@@ -77,11 +80,13 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   SKTB_REQUIRE(node_ptr && node_col && vals && inv_diag && n_nodes > 0, "null argument");
   SKTB_CUDA_OK(cudaSetDevice(m->device));
   MgLevel &l = m->lv[level];
-  if (l.n_nodes != n_nodes) {
+  if (l.n_global < n_nodes) l.n_global = n_nodes;
+  if (l.n_nodes != n_nodes || !l.x) {
     cudaFree(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
-    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * n_nodes));
+    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
+    SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
     SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
   }
@@ -93,6 +98,21 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   l.vals = vals;
   l.inv_diag = inv_diag;
   l.mask = mask;
+  return 0;
+}
+
+// level 0 of a row-sharded operator: this rank owns the nodes
+// [node0, node0 + n_owned) of n_global; call before sktb_mg_set_level(0, ...)
+extern "C" int sktb_mg_set_level0_range(sktb_mg *m, int64_t node0,
+                                        int64_t n_global) {
+  SKTB_REQUIRE(m && node0 >= 0 && n_global > 0, "bad argument");
+  MgLevel &l = m->lv[0];
+  if (l.n_global != n_global) {
+    cudaFree(l.x);
+    l.x = nullptr;
+  }
+  l.node0 = node0;
+  l.n_global = n_global;
   return 0;
 }
 
@@ -210,7 +230,7 @@ __global__ void __launch_bounds__(kBlock)
                        const double *__restrict__ bf,
                        const double *__restrict__ Axf,
                        const uint8_t *__restrict__ mask_c,
-                       double *__restrict__ bc) {
+                       double *__restrict__ bc, int64_t f_lo, int64_t f_hi) {
   const int64_t nc = (int64_t)cnx * cny * cnz;
   const int tot = cnx + cny + cnz;
   GS(I, nc) {
@@ -230,7 +250,9 @@ __global__ void __launch_bounds__(kBlock)
           const int fy = axT_f[sy * tot + cnx + iy];
           if (fy < 0) continue;
           const double w = axT_w[sy * tot + cnx + iy] * wx;
-          const int64_t f = 3 * ((int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz);
+          const int64_t fn = (int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz;
+          if (fn < f_lo || fn >= f_hi) continue;  // another rank's fine node
+          const int64_t f = 3 * (fn - f_lo);      // bf / Axf hold the owned rows
           a0 += w * (bf[f] - Axf[f]);
           a1 += w * (bf[f + 1] - Axf[f + 1]);
           a2 += w * (bf[f + 2] - Axf[f + 2]);
@@ -251,9 +273,9 @@ __global__ void __launch_bounds__(kBlock)
                       const double *__restrict__ w0, const double *__restrict__ w1,
                       const double *__restrict__ xc,
                       const uint8_t *__restrict__ mask_f,
-                      double *__restrict__ xf) {
-  const int64_t nf = (int64_t)fnx * fny * fnz;
-  GS(F, nf) {
+                      double *__restrict__ xf, int64_t f_lo, int64_t f_hi) {
+  GS(Fi, f_hi - f_lo) {
+    const int64_t F = f_lo + Fi;
     const int iy = (int)(F % fny);
     const int ix = (int)((F / fny) % fnx);
     const int iz = (int)(F / ((int64_t)fny * fnx));
@@ -298,32 +320,44 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
                           nullptr, nullptr, nullptr, nullptr, st);
 }
 
-// z = M^-1 r : V(1,1) cycle, level 0 reads r and writes z directly
-int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st) {
+// z = M^-1 r : V(1,1) cycle.  Level 0 may be row-sharded (its x is a
+// full-length vector whose ghost slots are refreshed before every SpMV, the
+// restricted residual is all-reduced); levels >= 1 are replicated.
+int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
+              sktb_pcg *dist) {
   const int L = (int)m->lv.size();
   const double om = m->omega;
+  const bool sharded = dist && pcg_is_dist(dist);
+  MgLevel &l0 = m->lv[0];
+  const int64_t f_lo = l0.node0, f_hi = l0.node0 + l0.n_nodes;
   // downward sweep
   for (int k = 0; k < L; ++k) {
     MgLevel &l = m->lv[k];
     const int64_t n = 3 * l.n_nodes;
     const double *b = (k == 0) ? r : l.b;
-    double *x = (k == 0) ? z : l.x;
+    double *xfull = l.x;                                  // gather source of the SpMV
+    double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;       // owned rows
     const int g = grid_for(n);
     mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
     SKTB_COUNT(1);
     if (k == L - 1) {
       for (int s = 0; s < m->nu_coarse; ++s) {
-        if (level_spmv(l, x, l.tmp, st)) return 1;
+        if (level_spmv(l, xfull, l.tmp, st)) return 1;
         mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
         SKTB_COUNT(1);
       }
     } else {
-      if (level_spmv(l, x, l.tmp, st)) return 1;
+      if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
+      if (level_spmv(l, xfull, l.tmp, st)) return 1;
       MgLevel &c = m->lv[k + 1];
+      const int64_t lo = (k == 0) ? f_lo : 0;
+      const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
       mg_restrict_kernel<<<grid_for(c.n_nodes), kBlock, 0, st>>>(
           l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
-          l.axT_w, b, l.tmp, c.mask, c.b);
+          l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
       SKTB_COUNT(1);
+      if (k == 0 && sharded && pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st))
+        return 1;
     }
   }
   // upward sweep
@@ -332,15 +366,21 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st) {
     MgLevel &c = m->lv[k + 1];
     const int64_t n = 3 * l.n_nodes;
     const double *b = (k == 0) ? r : l.b;
-    double *x = (k == 0) ? z : l.x;
-    mg_prolong_kernel<<<grid_for(l.n_nodes), kBlock, 0, st>>>(
+    double *xfull = l.x;
+    double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;
+    const int64_t lo = (k == 0) ? f_lo : 0;
+    const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
+    mg_prolong_kernel<<<grid_for(hi - lo), kBlock, 0, st>>>(
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.ax_c0,
-        l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, x);
+        l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, xfull, lo, hi);
     SKTB_COUNT(1);
-    if (level_spmv(l, x, l.tmp, st)) return 1;
+    if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
+    if (level_spmv(l, xfull, l.tmp, st)) return 1;
     mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
     SKTB_COUNT(1);
   }
+  SKTB_CUDA_OK(cudaMemcpyAsync(z, l0.x + 3 * l0.node0, sizeof(double) * 3 * l0.n_nodes,
+                               cudaMemcpyDeviceToDevice, st));
   SKTB_KERNEL_CHECK();
   return 0;
 }
@@ -348,5 +388,5 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st) {
 extern "C" int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stream) {
   SKTB_REQUIRE(m && r && z, "null argument");
   for (auto &l : m->lv) SKTB_REQUIRE(l.node_ptr, "multigrid level not set");
-  return mg_vcycle(m, r, z, (cudaStream_t)stream);
+  return mg_vcycle(m, r, z, (cudaStream_t)stream, nullptr);
 }

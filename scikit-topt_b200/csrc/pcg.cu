@@ -292,6 +292,15 @@ static int halo_exchange(sktb_pcg *s, double *v, cudaStream_t st) {
   return 0;
 }
 
+bool pcg_is_dist(const sktb_pcg *s) { return s && s->comm != nullptr; }
+int pcg_halo_exchange(sktb_pcg *s, double *full_vec, cudaStream_t st) {
+  return halo_exchange(s, full_vec, st);
+}
+int pcg_allreduce_vec(sktb_pcg *s, double *buf, int64_t n, cudaStream_t st) {
+  if (!s || !s->comm) return 0;
+  return comm_allreduce_sum(s->comm, buf, buf, n, st);
+}
+
 static int reduce_scalars(sktb_pcg *s, double *loc, double *glob, int count,
                           cudaStream_t st) {
   if (!s->comm) return 0;
@@ -347,7 +356,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                    const double *b, double *x, int use_x0, double rtol,
                    int maxiter, int check_every, int32_t *info_h,
                    double *relres_h, void *stream, sktb_mg *mg = nullptr) {
-  SKTB_REQUIRE(!(mg && s->comm), "the multigrid preconditioner is single-GPU");
+
   SKTB_REQUIRE(s && A.rp && A.ci && A.vals && inv_diag && b && x,
                "null argument");
   SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
@@ -376,12 +385,14 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
   if (reduce_scalars(s, &s->Sloc->rz, &s->S->rz, 6, st)) return 1;
   if (mg) {
     // z = M^-1 r by one V-cycle; p = z; rz = r.z
-    if (mg_vcycle(mg, s->r, s->z, st)) return 1;
+    if (mg_vcycle(mg, s->r, s->z, st, s)) return 1;
     SKTB_CUDA_OK(cudaMemcpyAsync(p_own, s->z, sizeof(double) * n,
                                  cudaMemcpyDeviceToDevice, st));
     pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 1, s->partials,
                                            s->ticket, s->Sloc, s->S);
     SKTB_KERNEL_OK();
+    // rz, pq (= 0), rz_new
+    if (reduce_scalars(s, &s->Sloc->rz, &s->S->rz, 3, st)) return 1;
   }
   int launched = 0;
   int n_ev = 0;
@@ -415,10 +426,11 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                                                  s->ticket, s->Sloc, s->S);
       if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
       if (mg) {
-        if (mg_vcycle(mg, s->r, s->z, st)) return 1;
+        if (mg_vcycle(mg, s->r, s->z, st, s)) return 1;
         pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 0, s->partials,
                                                s->ticket, s->Sloc, s->S);
         SKTB_COUNT(1);
+        if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 1, st)) return 1;
       }
       pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, p_own, s->ticket,
                                                     s->S);

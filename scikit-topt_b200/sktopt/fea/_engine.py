@@ -88,7 +88,7 @@ class FeaEngine:
         want = os.environ.get("SKTOPT_B200_PRECOND", "auto").lower()
         if want not in ("jacobi", "mg", "auto"):
             raise ValueError("SKTOPT_B200_PRECOND must be jacobi, mg or auto")
-        if dpn == 3 and comm is None and want != "jacobi" and dm.elem_class is not None:
+        if dpn == 3 and want != "jacobi" and dm.elem_class is not None:
             from sktopt.fea._multigrid import Multigrid, detect_tensor_grid
             axes = detect_tensor_grid(basis.mesh)
             big = dm.n_nodes >= Multigrid.MIN_FINE_NODES or want == "mg"

@@ -217,10 +217,11 @@ class Multigrid:
             self.handle = None
 
     def estimate_lambda_max(self, iters: int = 12) -> float:
-        """Largest eigenvalue of D^-1 A on level 0 by power iteration (the
-        damped-Jacobi smoother needs omega < 2 / lambda_max)."""
-        eng = self.eng
-        n = eng.n_dof
+        """Largest eigenvalue of D^-1 A by power iteration on level 1 (replicated
+        on every rank, so all ranks get the same value; the Galerkin hierarchy of
+        one PDE shares it closely).  Damped Jacobi needs omega < 2 / lambda_max."""
+        lv = self.levels[1]
+        n = 3 * lv["n_nodes"]
         g = torch.Generator(device="cuda")
         g.manual_seed(1234)
         v = torch.rand(n, dtype=dev.F64, device="cuda", generator=g) - 0.5
@@ -228,8 +229,8 @@ class Multigrid:
         lam = 1.0
         for _ in range(iters):
             v /= float(np.sqrt(dev.dot(v, v)))
-            dev.spmv_bsr3(eng.node_ptr_loc, eng.node_col_loc, eng.vals, v, out=w)
-            dev.hadamard(1.0, w, eng.inv_diag, w)
+            dev.spmv_bsr3(lv["node_ptr"], lv["node_col"], lv["vals"], v, out=w)
+            dev.hadamard(1.0, w, lv["inv_diag"], w)
             lam = dev.dot(v, w)
             v, w = w, v
         return float(lam)
@@ -238,17 +239,12 @@ class Multigrid:
         """Galerkin coarse operators for the engine's current modulus field;
         call after the engine assembled level 0 and its inverse diagonal."""
         eng = self.eng
-        if self.omega_auto and self.setup_count == 0:
-            lam = self.estimate_lambda_max()
-            self.lambda_max = lam
-            # omega * lambda_max = 1.6: inside the stability bound 2 with margin
-            self.omega = 1.6 / (1.05 * lam)
-            _lib.check(self.lib.sktb_mg_set_params(self.handle, float(self.omega),
-                                                   int(self.nu_coarse)))
+
         st = dev._stream()
         lib = self.lib
+        _lib.check(lib.sktb_mg_set_level0_range(self.handle, int(eng.node0), int(eng.dm.n_nodes)))
         _lib.check(lib.sktb_mg_set_level(
-            self.handle, 0, eng.dm.n_nodes, int(eng.node_col_loc.numel()), int(eng.max_deg),
+            self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()), int(eng.max_deg),
             dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc), dev._ptr(eng.vals),
             dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
         for l in range(1, self.n_levels):
@@ -269,6 +265,14 @@ class Multigrid:
                 self.handle, l, lv["n_nodes"], int(lv["node_col"].numel()), lv["max_deg"],
                 dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
                 dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+        if self.omega_auto and self.setup_count == 0:
+            lam = self.estimate_lambda_max()
+            self.lambda_max = lam
+            # omega * lambda_max ~ 1.75: inside the stability bound 2 (the power
+            # iteration approaches lambda_max from below, hence the 1.03)
+            self.omega = 1.75 / (1.03 * lam)
+            _lib.check(self.lib.sktb_mg_set_params(self.handle, float(self.omega),
+                                                   int(self.nu_coarse)))
         self.setup_count += 1
 
     def vcycle(self, r, z=None):
