@@ -152,6 +152,7 @@ typedef struct sktb_mg sktb_mg;
 int sktb_mg_create(sktb_mg **out, int n_levels, int device);
 void sktb_mg_destroy(sktb_mg *m);
 int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse);
+int sktb_mg_set_level_omega(sktb_mg *m, int level, double omega);
 /* operator of one level: node-block CSR (values in CSR layout, enforced),
  * inverse diagonal, optional per-dof Dirichlet mask                           */
 int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes, int64_t n_blocks,
@@ -192,6 +193,14 @@ int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg, const int32_t *node_ptr,
                            int use_x0, double rtol, int maxiter,
                            int check_every, int32_t *info_h, double *relres_h,
                            void *stream);
+
+/* lambda_max(D^-1 A) by `iters` power iterations on the (possibly row-sharded)
+ * node-block operator; used to place the multigrid smoother's damping.        */
+int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
+                             const int32_t *node_col, int64_t n_blocks,
+                             int max_deg, const double *vals,
+                             const double *inv_diag, int iters, double *out_h,
+                             void *stream);
 
 /* -------------------------------------------------- multi-GPU --
  * Row-sharded operator: rank r owns the rows of the contiguous node range

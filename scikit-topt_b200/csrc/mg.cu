@@ -29,6 +29,7 @@ struct MgLevel {
   // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
   // the operator is not sharded); x is always full length (n_global nodes)
   int64_t node0 = 0, n_global = 0;
+  double omega = 0.0;  // damping of this level's Jacobi smoother (0: use the global one)
   // transfer to the next coarser level (tensor grid tables, device)
   int32_t fnp[3] = {0, 0, 0}, cnp[3] = {0, 0, 0};  // nodes per axis (x, y, z)
   const int32_t *ax_c0 = nullptr, *ax_c1 = nullptr;  // [fnx | fny | fnz]
@@ -68,6 +69,13 @@ extern "C" int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse) {
   SKTB_REQUIRE(m && omega > 0.0 && omega < 2.0 && nu_coarse >= 0, "bad argument");
   m->omega = omega;
   m->nu_coarse = nu_coarse;
+  return 0;
+}
+
+extern "C" int sktb_mg_set_level_omega(sktb_mg *m, int level, double omega) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size() && omega > 0.0 && omega < 2.0,
+               "bad argument");
+  m->lv[level].omega = omega;
   return 0;
 }
 
@@ -326,7 +334,6 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
 int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
               sktb_pcg *dist) {
   const int L = (int)m->lv.size();
-  const double om = m->omega;
   const bool sharded = dist && pcg_is_dist(dist);
   MgLevel &l0 = m->lv[0];
   const int64_t f_lo = l0.node0, f_hi = l0.node0 + l0.n_nodes;
@@ -338,6 +345,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     double *xfull = l.x;                                  // gather source of the SpMV
     double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;       // owned rows
     const int g = grid_for(n);
+    const double om = l.omega > 0.0 ? l.omega : m->omega;
     mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
     SKTB_COUNT(1);
     if (k == L - 1) {
@@ -370,6 +378,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;
     const int64_t lo = (k == 0) ? f_lo : 0;
     const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
+    const double om = l.omega > 0.0 ? l.omega : m->omega;
     mg_prolong_kernel<<<grid_for(hi - lo), kBlock, 0, st>>>(
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.ax_c0,
         l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, xfull, lo, hi);

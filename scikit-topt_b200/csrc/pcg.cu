@@ -487,3 +487,81 @@ extern "C" int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg,
   return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
                  info_h, relres_h, stream, mg);
 }
+
+// ------------------------------------------------ spectral radius estimate --
+__global__ void __launch_bounds__(kBlock)
+    pw_init_kernel(int64_t n, int64_t row0, double *__restrict__ v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    // deterministic pseudo-random start vector from the GLOBAL index
+    unsigned long long h = (unsigned long long)(row0 + i) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    v[i] = (double)(h & 0xFFFFFull) / 1048576.0 - 0.5;
+  }
+}
+__global__ void __launch_bounds__(kBlock)
+    pw_dot_kernel(int64_t n, const double *__restrict__ a,
+                  const double *__restrict__ b, double *partials,
+                  unsigned int *ticket, double *out) {
+  double v[1] = {0.0};
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) v[0] += a[i] * b[i];
+  grid_reduce<1>(v, partials, ticket, out);
+}
+__global__ void __launch_bounds__(kBlock)
+    pw_scale_kernel(int64_t n, double a, const double *__restrict__ x,
+                    const double *__restrict__ d, double *__restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = a * x[i] * (d ? d[i] : 1.0);
+}
+
+// lambda_max(D^-1 A) by power iteration on the (possibly row-sharded) operator
+extern "C" int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
+                                        const int32_t *node_col,
+                                        int64_t n_blocks, int max_deg,
+                                        const double *vals,
+                                        const double *inv_diag, int iters,
+                                        double *out_h, void *stream) {
+  SKTB_REQUIRE(s && node_ptr && node_col && vals && inv_diag && out_h && iters > 0,
+               "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = s->n;
+  double *p_own = s->p + s->row0;
+  const int vgrid = grid_for(n, kBlock, 8);
+  PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
+  auto gdot = [&](const double *a, const double *b, double *res) -> int {
+    pw_dot_kernel<<<vgrid, kBlock, 0, st>>>(n, a, b, s->partials, s->ticket,
+                                           &s->Sloc->pq);
+    SKTB_KERNEL_OK();
+    if (reduce_scalars(s, &s->Sloc->pq, &s->Sloc->pq, 1, st)) return 1;
+    SKTB_CUDA_OK(cudaMemcpyAsync(&s->S_h->pq, &s->Sloc->pq, sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    SKTB_CUDA_OK(cudaStreamSynchronize(st));
+    *res = s->S_h->pq;
+    return 0;
+  };
+  pw_init_kernel<<<vgrid, kBlock, 0, st>>>(n, s->row0, p_own);
+  SKTB_KERNEL_OK();
+  double lam = 1.0;
+  for (int it = 0; it < iters; ++it) {
+    double nrm2 = 0.0;
+    if (gdot(p_own, p_own, &nrm2)) return 1;
+    SKTB_REQUIRE(nrm2 > 0.0, "power iteration broke down");
+    pw_scale_kernel<<<vgrid, kBlock, 0, st>>>(n, 1.0 / sqrt(nrm2), p_own, nullptr, p_own);
+    SKTB_KERNEL_OK();
+    if (halo_exchange(s, s->p, st)) return 1;
+    if (apply_mat(A, n, s->p, s->q, nullptr, nullptr, nullptr, nullptr, st)) return 1;
+    pw_scale_kernel<<<vgrid, kBlock, 0, st>>>(n, 1.0, s->q, inv_diag, s->z);
+    SKTB_KERNEL_OK();
+    if (gdot(p_own, s->z, &lam)) return 1;
+    SKTB_CUDA_OK(cudaMemcpyAsync(p_own, s->z, sizeof(double) * n,
+                                 cudaMemcpyDeviceToDevice, st));
+  }
+  *out_h = lam;
+  return 0;
+}

@@ -216,11 +216,20 @@ class Multigrid:
                 pass
             self.handle = None
 
-    def estimate_lambda_max(self, iters: int = 12) -> float:
-        """Largest eigenvalue of D^-1 A by power iteration on level 1 (replicated
-        on every rank, so all ranks get the same value; the Galerkin hierarchy of
-        one PDE shares it closely).  Damped Jacobi needs omega < 2 / lambda_max."""
-        lv = self.levels[1]
+    def _lambda_max_level(self, l: int, iters: int = 12) -> float:
+        """Largest eigenvalue of D^-1 A of level ``l`` by power iteration.  Level
+        0 runs inside the PCG workspace (it may be row-sharded); the replicated
+        coarse levels use plain device kernels.  Every rank gets the same value."""
+        if l == 0:
+            eng = self.eng
+            out = C.c_double()
+            _lib.check(self.lib.sktb_pcg_lambda_max_bsr3(
+                eng.pcg.handle, dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc),
+                int(eng.node_col_loc.numel()), int(eng.max_deg), dev._ptr(eng.vals),
+                dev._ptr(eng.inv_diag), int(iters), C.cast(C.byref(out), C.c_void_p),
+                dev._stream()))
+            return float(out.value)
+        lv = self.levels[l]
         n = 3 * lv["n_nodes"]
         g = torch.Generator(device="cuda")
         g.manual_seed(1234)
@@ -266,13 +275,16 @@ class Multigrid:
                 dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
                 dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
         if self.omega_auto and self.setup_count == 0:
-            lam = self.estimate_lambda_max()
-            self.lambda_max = lam
-            # omega * lambda_max ~ 1.75: inside the stability bound 2 (the power
-            # iteration approaches lambda_max from below, hence the 1.03)
-            self.omega = 1.75 / (1.03 * lam)
-            _lib.check(self.lib.sktb_mg_set_params(self.handle, float(self.omega),
-                                                   int(self.nu_coarse)))
+            # per-level damping: omega_l * lambda_max_l ~ 1.75, inside the
+            # stability bound 2 (the power iteration approaches lambda_max from
+            # below, hence the 1.03).  Done once: lambda_max(D^-1 A) depends on
+            # the discretisation far more than on the density field.
+            self.lambda_max = []
+            for l in range(self.n_levels):
+                lam = self._lambda_max_level(l)
+                self.lambda_max.append(lam)
+                _lib.check(self.lib.sktb_mg_set_level_omega(
+                    self.handle, l, float(1.75 / (1.03 * lam))))
         self.setup_count += 1
 
     def vcycle(self, r, z=None):
