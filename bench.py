@@ -253,7 +253,9 @@ def run_b200(args):
             "config": {
                 "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
                 "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
-                "solver": "device Jacobi-PCG rtol 1e-8, warm start",
+                "solver": ("device PCG rtol 1e-8, warm start, preconditioner: "
+                           + ("geometric multigrid V(1,1) (Galerkin coarse operators, damped Jacobi)"
+                              if eng.precond == "mg" else "Jacobi")),
                 "pcg_iters_per_step": pcg_iters,
                 "l2": "inputs larger than L2 (CSR 3.0 GB >> 126 MB)",
                 "parallelism": "single GPU" if world == 1 else (
