@@ -130,8 +130,9 @@ int sktb_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                        const int32_t *node_ptr, const int32_t *node_col,
                        const double *vals, const double *x, double *y,
                        void *stream);
-/* out[3n+i] = 1 / A[3n+i,3n+i] from the node-block layout                      */
-int sktb_bsr3_inv_diag(int64_t n_nodes, const int32_t *node_ptr,
+/* out[3n+i] = 1 / A[3n+i,3n+i] from the node-block layout; node0 = global id
+ * of the first (local) row node when the rows are a shard                      */
+int sktb_bsr3_inv_diag(int64_t n_nodes, int64_t node0, const int32_t *node_ptr,
                        const int32_t *node_col, const double *vals, double *out,
                        void *stream);
 int sktb_pcg_solve_bsr3(sktb_pcg *s, const int32_t *node_ptr,
@@ -185,7 +186,13 @@ int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
                        const double *fine_ke, const double *unit,
                        const int32_t *cls, const double *scale, double *out,
                        void *stream);
-/* PCG preconditioned by the V-cycle (single GPU)                              */
+/* level 0 -> 1 fast path: children are scale[e]*Ke0[cls[e]], so out[E] =
+ * sum_c scale[child] * T[(cls*8 + ptype[E])*8 + c] with the precomputed tables
+ * T = Q_c^T Ke0[cls] Q_c (576 doubles each)                                    */
+int sktb_elem_combine(int64_t n_coarse, const int32_t *child,
+                      const uint8_t *ptype, const double *T, const int32_t *cls,
+                      const double *scale, double *out, void *stream);
+/* PCG preconditioned by the V-cycle (level 0 may be row-sharded)               */
 int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg, const int32_t *node_ptr,
                            const int32_t *node_col, int64_t n_blocks,
                            int max_deg, const double *vals,

@@ -101,7 +101,8 @@ int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
 
 // out[3n+i] = 1 / A[3n+i, 3n+i] from the node-block layout
 __global__ void __launch_bounds__(kBlock)
-    bsr3_inv_diag_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr,
+    bsr3_inv_diag_kernel(int64_t n_nodes, int64_t node0,
+                         const int32_t *__restrict__ node_ptr,
                          const int32_t *__restrict__ node_col,
                          const double *__restrict__ vals,
                          double *__restrict__ out) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kBlock)
   for (; n < n_nodes; n += stride) {
     const int32_t s0 = node_ptr[n], deg = node_ptr[n + 1] - s0;
     for (int32_t s = 0; s < deg; ++s) {
-      if (node_col[s0 + s] == n) {
+      if (node_col[s0 + s] == n + node0) {
         const double *vp = vals + (int64_t)9 * s0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -121,12 +122,13 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
-extern "C" int sktb_bsr3_inv_diag(int64_t n_nodes, const int32_t *node_ptr,
+extern "C" int sktb_bsr3_inv_diag(int64_t n_nodes, int64_t node0,
+                                  const int32_t *node_ptr,
                                   const int32_t *node_col, const double *vals,
                                   double *out, void *stream) {
   SKTB_REQUIRE(node_ptr && node_col && vals && out, "null argument");
   bsr3_inv_diag_kernel<<<grid_for(n_nodes), kBlock, 0, (cudaStream_t)stream>>>(
-      n_nodes, node_ptr, node_col, vals, out);
+      n_nodes, node0, node_ptr, node_col, vals, out);
   SKTB_KERNEL_OK();
   return 0;
 }

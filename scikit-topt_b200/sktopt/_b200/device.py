@@ -348,12 +348,12 @@ def spmv_bsr3(node_ptr, node_col, vals, x, out=None):
     return out
 
 
-def bsr3_inv_diag(node_ptr, node_col, vals, out=None):
+def bsr3_inv_diag(node_ptr, node_col, vals, out=None, node0: int = 0):
     n_nodes = node_ptr.numel() - 1
     if out is None:
         out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
     _lib.check(
-        _lib.load().sktb_bsr3_inv_diag(n_nodes, _ptr(node_ptr), _ptr(node_col), _ptr(vals), _ptr(out), _stream())
+        _lib.load().sktb_bsr3_inv_diag(n_nodes, int(node0), _ptr(node_ptr), _ptr(node_col), _ptr(vals), _ptr(out), _stream())
     )
     return out
 

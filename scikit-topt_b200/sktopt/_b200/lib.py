@@ -39,7 +39,7 @@ SIGNATURES = {
     "sktb_pcg_create": [C.POINTER(C.c_void_p), i64, i32],
     "sktb_pcg_destroy": [C.c_void_p],
     "sktb_spmv_bsr3": [i64, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
-    "sktb_bsr3_inv_diag": [i64, c_i32p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_bsr3_inv_diag": [i64, i64, c_i32p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_spmv_bsr3_tma": [i64, i64, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_solve_bsr3": [C.c_void_p, c_i32p, c_i32p, i64, i32, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_mg_create": [C.POINTER(C.c_void_p), i32, i32],
@@ -51,6 +51,7 @@ SIGNATURES = {
     "sktb_mg_set_level0_range": [C.c_void_p, i64, i64],
     "sktb_mg_set_transfer": [C.c_void_p, i32, C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
     "sktb_mg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
+    "sktb_elem_combine": [i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_restrict": [i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_solve_bsr3_mg": [C.c_void_p, C.c_void_p, c_i32p, c_i32p, i64, i32, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_mesh_dof_pattern_rows": [C.c_void_p, i32, i64, i64, c_i32p, c_i32p, c_stream],

@@ -124,9 +124,12 @@ class FeaEngine:
                                      out=self.vals if out is None else out)
 
     def update_preconditioner(self, vals=None):
-        dev.csr_inv_diag(self.row_ptr, self.col_idx,
-                         self.vals if vals is None else vals, out=self.inv_diag,
-                         row0=self.row0)
+        v = self.vals if vals is None else vals
+        if self.dpn == 3:
+            dev.bsr3_inv_diag(self.node_ptr_loc, self.node_col_loc, v, out=self.inv_diag,
+                              node0=self.node0)
+        else:
+            dev.csr_inv_diag(self.row_ptr, self.col_idx, v, out=self.inv_diag, row0=self.row0)
         if self.mg is not None and self.mg_enabled and vals is None:
             self.mg.setup()
 

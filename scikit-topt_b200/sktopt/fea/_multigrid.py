@@ -206,6 +206,19 @@ class Multigrid:
                 dev._ptr(tr["fT"]), dev._ptr(tr["wT"])))
             mask_f = mask_c
         self.setup_count = 0
+        # level 0 -> 1 tables T[cls][type][c] = Q_c^T Ke0[cls] Q_c (host, once)
+        ke0 = engine.unit_ke.cpu().numpy().reshape(-1, 24, 24)
+        Q = q_tables(bits)
+        self.T01 = None
+        if ke0.shape[0] <= 16:
+            T = np.zeros((ke0.shape[0], 8, 8, 24, 24))
+            eye3 = np.eye(3)
+            for k in range(ke0.shape[0]):
+                for ty_ in range(8):
+                    for ch in range(8):
+                        Qv = np.kron(Q[ty_, ch], eye3)          # (24 child dofs, 24 parent dofs)
+                        T[k, ty_, ch] = Qv.T @ ke0[k] @ Qv
+            self.T01 = dev.to_dev(T.ravel())
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -258,7 +271,11 @@ class Multigrid:
             dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
         for l in range(1, self.n_levels):
             lv = self.levels[l]
-            if l == 1:
+            if l == 1 and self.T01 is not None:
+                _lib.check(lib.sktb_elem_combine(
+                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.T01),
+                    dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale), dev._ptr(lv["ke"]), st))
+            elif l == 1:
                 _lib.check(lib.sktb_elem_restrict(
                     lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
                     None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
