@@ -178,7 +178,7 @@ def run_b200(args):
     opt.parameterize()
     opt.export_enabled = False
     eng = opt.fem.engine
-    n_elem, n_dof, nnz = eng.n_elem, eng.n_dof, int(eng.vals.numel())
+    n_elem, n_dof, nnz = eng.n_elem, eng.n_dof, eng.nnz
 
     # pinned host buffers of the per-step API edge
     rho_h = torch.empty(n_elem, dtype=torch.float64).pin_memory()

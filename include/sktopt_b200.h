@@ -186,6 +186,36 @@ int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
                        const double *fine_ke, const double *unit,
                        const int32_t *cls, const double *scale, double *out,
                        void *stream);
+/* ---- matrix-free operator for uniform hexahedral tensor grids ---------------
+ * Replaces the assembled K(rho) inside the solver where the reference hands
+ * scipy/pyamg the assembled matrix (fea/solver_elastic.py:94-104,189-260):
+ * y = K(rho) x with K = sum_e scale[e] Ke0 evaluated element-wise from the
+ * grid structure (node = iy + npy (ix + npx iz), element = ey + ny (ex + nx ez)).
+ * ke_cc_h: the 24x24 unit matrix with local vertices re-ordered by corner code
+ * cx + 2 cy + 4 cz (host).  dmask (device, per node): bit i = dof i fixed,
+ * bit 3 = some node of the 27-neighbourhood has a fixed dof.                   */
+typedef struct sktb_gridop sktb_gridop;
+int sktb_gridop_create(sktb_gridop **out, const int32_t *np_h,
+                       const double *ke_cc_h, int device);
+void sktb_gridop_destroy(sktb_gridop *op);
+int sktb_gridop_set_fields(sktb_gridop *op, const double *scale,
+                           const uint8_t *dmask);
+/* rows of the nodes [node0, node0 + n_nodes); x is full length, y local        */
+int sktb_gridop_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                      const double *x, double *y, void *stream);
+int sktb_gridop_inv_diag(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                         double *out, void *stream);
+/* PCG on the matrix-free operator; mg may be NULL (Jacobi)                     */
+int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg, const sktb_gridop *op,
+                        const double *inv_diag, const double *b, double *x,
+                        int use_x0, double rtol, int maxiter, int check_every,
+                        int32_t *info_h, double *relres_h, void *stream);
+int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
+                             const double *inv_diag, int iters, double *out_h,
+                             void *stream);
+/* level 0 of the multigrid hierarchy applied matrix-free                       */
+int sktb_mg_set_level0_grid(sktb_mg *m, const sktb_gridop *op, int64_t n_nodes,
+                            const double *inv_diag, const uint8_t *mask);
 /* level 0 -> 1 fast path: children are scale[e]*Ke0[cls[e]], so out[E] =
  * sum_c scale[child] * T[(cls*8 + ptype[E])*8 + c] with the precomputed tables
  * T = Q_c^T Ke0[cls] Q_c (576 doubles each)                                    */

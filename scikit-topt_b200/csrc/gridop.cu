@@ -1,0 +1,228 @@
+// Matrix-free K(rho) x for trilinear hexahedra on a tensor grid with ONE
+// geometry class (uniform spacing: create_box_hex).
+//
+//   K(rho) = sum_e E_e Ke0     =>     (K x)_n = sum_{e ∋ n} E_e Ke0[a(n,e), :] x_e
+//
+// The assembled operator streams 8.44 bytes per non-zero (2.1 GB per product at
+// 1M elements); this kernel reads x (24 B/node, mostly from L1/L2), E (8 B per
+// element) and writes y: the product becomes FP64-pipe bound instead of HBM
+// bound.  One thread owns a node: it walks the 27 neighbours plane by plane,
+// loads each neighbour's displacement once and feeds the <= 8 elements that
+// contain both nodes; the 576 matrix coefficients are kernel parameters
+// (constant bank), so every DFMA takes its coefficient as an immediate
+// constant operand -- no shared memory, no coefficient loads.  Node and
+// element numbering are MeshHex.init_tensor's: node = iy + npy (ix + npx iz),
+// element = ey + ny (ex + nx ez).  Gather formulation: deterministic, no
+// atomics.
+//
+// Dirichlet dofs are handled on the fly (same operator as csr_enforce builds:
+// identity rows/columns): fixed inputs are read as 0, fixed outputs pass x
+// through.  dmask[n] bit i = dof i of node n fixed, bit 3 = some node of the
+// 27-neighbourhood has a fixed dof (only those threads look at neighbour masks).
+#include "common.cuh"
+#include "linalg.cuh"
+
+using namespace sktb;
+
+struct HexGridParams {
+  double ke[576];  // corner-code order: row 3 ca + i, col 3 cb + j, c = cx + 2 cy + 4 cz
+  int32_t npx, npy, npz;
+  const double *scale;   // E per element
+  const uint8_t *dmask;  // per node
+};
+
+struct sktb_gridop {
+  HexGridParams P;
+  int device = 0;
+  int64_t n_nodes = 0;
+};
+
+__device__ __forceinline__ int clampi(int v, int hi) {
+  return v < 0 ? 0 : (v > hi ? hi : v);
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock, 2)
+    hexgrid_apply_kernel(const __grid_constant__ HexGridParams P, int64_t node0,
+                         int64_t n_loc, const double *__restrict__ x,
+                         double *__restrict__ y, const double *__restrict__ dotv,
+                         double *partials, unsigned int *ticket, double *dot_out,
+                         const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  double dot = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_loc;
+       r += stride) {
+    const int64_t n = node0 + r;
+    const int iy = (int)(n % npy);
+    const int64_t t = n / npy;
+    const int ix = (int)(t % npx);
+    const int iz = (int)(t / npx);
+    double E[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1),
+                ez = iz - 1 + (o >> 2);
+      const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+      E[o] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+    }
+    const unsigned dm = P.dmask[n];
+    const bool near = (dm & 8u) != 0;
+    double pe[8][3];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = 0.0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int kz = clampi(iz + dz, npz - 1);
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int kx = clampi(ix + dx, npx - 1);
+        const int64_t base = (int64_t)npy * (kx + (int64_t)npx * kz);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int ky = clampi(iy + dy, npy - 1);
+          const int64_t m = base + ky;
+          double u0 = __ldg(&x[3 * m]), u1 = __ldg(&x[3 * m + 1]),
+                 u2 = __ldg(&x[3 * m + 2]);
+          if (near) {
+            const unsigned mb = P.dmask[m];
+            if (mb & 1u) u0 = 0.0;
+            if (mb & 2u) u1 = 0.0;
+            if (mb & 4u) u2 = 0.0;
+          }
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+            const int cb = bx + 2 * by + 4 * bz;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int k = (3 * ca + i) * 24 + 3 * cb;
+              pe[o][i] += P.ke[k] * u0 + P.ke[k + 1] * u1 + P.ke[k + 2] * u2;
+            }
+          }
+        }
+      }
+    }
+    double out[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) a += E[o] * pe[o][i];
+      out[i] = a;
+    }
+    if (dm & 7u) {
+      if (dm & 1u) out[0] = x[3 * n];
+      if (dm & 2u) out[1] = x[3 * n + 1];
+      if (dm & 4u) out[2] = x[3 * n + 2];
+    }
+    y[3 * r] = out[0];
+    y[3 * r + 1] = out[1];
+    y[3 * r + 2] = out[2];
+    if (DOT)
+      dot += out[0] * dotv[3 * r] + out[1] * dotv[3 * r + 1] + out[2] * dotv[3 * r + 2];
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+// out[3r+i] = 1 / K_ii (1 at fixed dofs)
+__global__ void __launch_bounds__(kBlock)
+    hexgrid_inv_diag_kernel(const __grid_constant__ HexGridParams P, int64_t node0,
+                            int64_t n_loc, double *__restrict__ out) {
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_loc;
+       r += stride) {
+    const int64_t n = node0 + r;
+    const int iy = (int)(n % npy);
+    const int64_t t = n / npy;
+    const int ix = (int)(t % npx);
+    const int iz = (int)(t / npx);
+    double d[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+      const int ex = ix - 1 + ox, ey = iy - 1 + oy, ez = iz - 1 + oz;
+      const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+      const double E = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+      const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) d[i] += E * P.ke[(3 * ca + i) * 25];
+    }
+    const unsigned dm = P.dmask[n];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[3 * r + i] = ((dm >> i) & 1u) ? 1.0 : 1.0 / d[i];
+  }
+}
+
+int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                         const double *x, double *y, const double *dotv,
+                         ReduceScratch *rs, double *dot_out, const PcgScalars *S,
+                         cudaStream_t st) {
+  const int grid = grid_for(n_nodes, kBlock, 16);
+  if (dotv)
+    hexgrid_apply_kernel<true><<<grid, kBlock, 0, st>>>(
+        op->P, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+  else
+    hexgrid_apply_kernel<false><<<grid, kBlock, 0, st>>>(
+        op->P, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+extern "C" int sktb_gridop_create(sktb_gridop **out, const int32_t *np_h,
+                                  const double *ke_cc_h, int device) {
+  SKTB_REQUIRE(out && np_h && ke_cc_h, "null argument");
+  SKTB_REQUIRE(np_h[0] >= 2 && np_h[1] >= 2 && np_h[2] >= 2, "grid needs >= 1 cell per axis");
+  sktb_gridop *op = new sktb_gridop();
+  for (int i = 0; i < 576; ++i) op->P.ke[i] = ke_cc_h[i];
+  op->P.npx = np_h[0];
+  op->P.npy = np_h[1];
+  op->P.npz = np_h[2];
+  op->P.scale = nullptr;
+  op->P.dmask = nullptr;
+  op->device = device;
+  op->n_nodes = (int64_t)np_h[0] * np_h[1] * np_h[2];
+  *out = op;
+  return 0;
+}
+
+extern "C" void sktb_gridop_destroy(sktb_gridop *op) { delete op; }
+
+extern "C" int sktb_gridop_set_fields(sktb_gridop *op, const double *scale,
+                                      const uint8_t *dmask) {
+  SKTB_REQUIRE(op && scale && dmask, "null argument");
+  op->P.scale = scale;
+  op->P.dmask = dmask;
+  return 0;
+}
+
+bool gridop_ready(const sktb_gridop *op) { return op && op->P.scale && op->P.dmask; }
+
+extern "C" int sktb_gridop_apply(const sktb_gridop *op, int64_t node0,
+                                 int64_t n_nodes, const double *x, double *y,
+                                 void *stream) {
+  SKTB_REQUIRE(gridop_ready(op) && x && y, "null argument");
+  SKTB_REQUIRE(node0 >= 0 && n_nodes > 0 && node0 + n_nodes <= op->n_nodes, "bad node range");
+  return launch_hexgrid_apply(op, node0, n_nodes, x, y, nullptr, nullptr, nullptr,
+                              nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int sktb_gridop_inv_diag(const sktb_gridop *op, int64_t node0,
+                                    int64_t n_nodes, double *out, void *stream) {
+  SKTB_REQUIRE(gridop_ready(op) && out, "null argument");
+  SKTB_REQUIRE(node0 >= 0 && n_nodes > 0 && node0 + n_nodes <= op->n_nodes, "bad node range");
+  hexgrid_inv_diag_kernel<<<grid_for(n_nodes), kBlock, 0, (cudaStream_t)stream>>>(
+      op->P, node0, n_nodes, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}

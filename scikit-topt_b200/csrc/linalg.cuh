@@ -40,6 +40,15 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const double *dotv, sktb::ReduceScratch *rs,
                          double *dot_out, const PcgScalars *S, cudaStream_t st);
 
+// matrix-free hexahedral grid operator (gridop.cu): y[local rows] = K x with x
+// a full-length vector; same dot / early-exit contract as the SpMV launchers
+struct sktb_gridop;
+bool gridop_ready(const sktb_gridop *op);
+int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                         const double *x, double *y, const double *dotv,
+                         sktb::ReduceScratch *rs, double *dot_out,
+                         const PcgScalars *S, cudaStream_t st);
+
 // multigrid preconditioner z = M^-1 r (mg.cu)
 struct sktb_mg;
 struct sktb_pcg;

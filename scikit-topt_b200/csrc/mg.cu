@@ -25,6 +25,7 @@ struct MgLevel {
   const int32_t *node_ptr = nullptr, *node_col = nullptr;
   const double *vals = nullptr, *inv_diag = nullptr;
   const uint8_t *mask = nullptr;  // per dof, may be null
+  const sktb_gridop *gop = nullptr;  // level 0 only: matrix-free operator
   double *x = nullptr, *b = nullptr, *tmp = nullptr;  // owned work vectors
   // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
   // the operator is not sharded); x is always full length (n_global nodes)
@@ -99,11 +100,38 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
   }
   l.n_nodes = n_nodes;
+  l.gop = nullptr;
   l.n_blocks = n_blocks;
   l.max_deg = max_deg;
   l.node_ptr = node_ptr;
   l.node_col = node_col;
   l.vals = vals;
+  l.inv_diag = inv_diag;
+  l.mask = mask;
+  return 0;
+}
+
+// matrix-free level 0 (gridop.cu) instead of assembled values
+extern "C" int sktb_mg_set_level0_grid(sktb_mg *m, const sktb_gridop *op,
+                                       int64_t n_nodes, const double *inv_diag,
+                                       const uint8_t *mask) {
+  SKTB_REQUIRE(m && gridop_ready(op) && inv_diag && n_nodes > 0, "null argument");
+  SKTB_CUDA_OK(cudaSetDevice(m->device));
+  MgLevel &l = m->lv[0];
+  if (l.n_global < n_nodes) l.n_global = n_nodes;
+  if (l.n_nodes != n_nodes || !l.x) {
+    cudaFree(l.x);
+    cudaFree(l.b);
+    cudaFree(l.tmp);
+    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
+    SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
+    SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
+    SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
+  }
+  l.n_nodes = n_nodes;
+  l.gop = op;
+  l.node_ptr = l.node_col = nullptr;
+  l.vals = nullptr;
   l.inv_diag = inv_diag;
   l.mask = mask;
   return 0;
@@ -392,6 +420,9 @@ __global__ void __launch_bounds__(1024)
 }
 
 static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st) {
+  if (l.gop)
+    return launch_hexgrid_apply(l.gop, l.node0, l.n_nodes, x, y, nullptr, nullptr,
+                                nullptr, nullptr, st);
   int rc = launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
                                 l.node_col, l.vals, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
@@ -474,6 +505,6 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
 
 extern "C" int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stream) {
   SKTB_REQUIRE(m && r && z, "null argument");
-  for (auto &l : m->lv) SKTB_REQUIRE(l.node_ptr, "multigrid level not set");
+  for (auto &l : m->lv) SKTB_REQUIRE(l.node_ptr || l.gop, "multigrid level not set");
   return mg_vcycle(m, r, z, (cudaStream_t)stream, nullptr);
 }

@@ -307,8 +307,9 @@ static int reduce_scalars(sktb_pcg *s, double *loc, double *glob, int count,
   return comm_allreduce_sum(s->comm, loc, glob, count, st);
 }
 
-// matrix handed to the solver: CSR (kind 0) or node-block CSR for 3 dofs per
-// node (kind 1: rp/ci index node blocks, vals keep the CSR layout)
+// matrix handed to the solver: CSR (kind 0), node-block CSR for 3 dofs per
+// node (kind 1: rp/ci index node blocks, vals keep the CSR layout) or the
+// matrix-free grid operator (kind 2)
 struct PcgMat {
   int kind;
   int dpn_hint;
@@ -317,11 +318,16 @@ struct PcgMat {
   const double *vals;
   int64_t n_blocks = 0;  // kind 1: number of 3x3 blocks
   int max_deg = 0;       // kind 1: largest number of blocks in a node row
+  const sktb_gridop *gop = nullptr;  // kind 2
+  int64_t node0 = 0;                 // kind 2: first owned node
 };
 
 static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
                      const double *dotv, ReduceScratch *rs, double *dot_out,
                      const PcgScalars *S, cudaStream_t st) {
+  if (A.kind == 2)
+    return launch_hexgrid_apply(A.gop, A.node0, n / 3, x, y, dotv, rs, dot_out, S,
+                                st);
   if (A.kind == 1) {
     int rc = launch_spmv_bsr3_tma(n / 3, A.n_blocks, A.max_deg, A.rp, A.ci,
                                   A.vals, x, y, dotv, rs, dot_out, S, st);
@@ -357,7 +363,8 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                    int maxiter, int check_every, int32_t *info_h,
                    double *relres_h, void *stream, sktb_mg *mg = nullptr) {
 
-  SKTB_REQUIRE(s && A.rp && A.ci && A.vals && inv_diag && b && x,
+  SKTB_REQUIRE(s && inv_diag && b && x, "null argument");
+  SKTB_REQUIRE(A.kind == 2 ? gridop_ready(A.gop) : (A.rp && A.ci && A.vals),
                "null argument");
   SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
   if (check_every <= 0) check_every = 32;
@@ -521,19 +528,12 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 // lambda_max(D^-1 A) by power iteration on the (possibly row-sharded) operator
-extern "C" int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
-                                        const int32_t *node_col,
-                                        int64_t n_blocks, int max_deg,
-                                        const double *vals,
-                                        const double *inv_diag, int iters,
-                                        double *out_h, void *stream) {
-  SKTB_REQUIRE(s && node_ptr && node_col && vals && inv_diag && out_h && iters > 0,
-               "bad argument");
+static int lambda_max_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
+                          int iters, double *out_h, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = s->n;
   double *p_own = s->p + s->row0;
   const int vgrid = grid_for(n, kBlock, 8);
-  PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
   auto gdot = [&](const double *a, const double *b, double *res) -> int {
     pw_dot_kernel<<<vgrid, kBlock, 0, st>>>(n, a, b, s->partials, s->ticket,
                                            &s->Sloc->pq);
@@ -564,4 +564,44 @@ extern "C" int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
   }
   *out_h = lam;
   return 0;
+}
+
+extern "C" int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
+                                        const int32_t *node_col,
+                                        int64_t n_blocks, int max_deg,
+                                        const double *vals,
+                                        const double *inv_diag, int iters,
+                                        double *out_h, void *stream) {
+  SKTB_REQUIRE(s && node_ptr && node_col && vals && inv_diag && out_h && iters > 0,
+               "bad argument");
+  PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
+  return lambda_max_run(s, A, inv_diag, iters, out_h, stream);
+}
+
+// ------------------------------------------- matrix-free grid operator path --
+static PcgMat grid_mat(const sktb_pcg *s, const sktb_gridop *op) {
+  PcgMat A{2, 3, nullptr, nullptr, nullptr};
+  A.gop = op;
+  A.node0 = s->row0 / 3;
+  return A;
+}
+
+extern "C" int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg,
+                                   const sktb_gridop *op, const double *inv_diag,
+                                   const double *b, double *x, int use_x0,
+                                   double rtol, int maxiter, int check_every,
+                                   int32_t *info_h, double *relres_h,
+                                   void *stream) {
+  SKTB_REQUIRE(s && op && s->n % 3 == 0 && s->row0 % 3 == 0,
+               "grid solve needs 3 dofs per node");
+  return pcg_run(s, grid_mat(s, op), inv_diag, b, x, use_x0, rtol, maxiter,
+                 check_every, info_h, relres_h, stream, mg);
+}
+
+extern "C" int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
+                                        const double *inv_diag, int iters,
+                                        double *out_h, void *stream) {
+  SKTB_REQUIRE(s && gridop_ready(op) && inv_diag && out_h && iters > 0 && s->n % 3 == 0,
+               "bad argument");
+  return lambda_max_run(s, grid_mat(s, op), inv_diag, iters, out_h, stream);
 }

@@ -470,6 +470,90 @@ class PcgSolver:
         self.total_iters += self.last_iters
         return x
 
+    def solve_grid(self, gridop, inv_diag, b, x, rtol=1e-8, maxiter=1000, use_x0=False,
+                   check_every=32, mg=None):
+        """PCG on the matrix-free grid operator (``GridOp``)."""
+        info = (C.c_int32 * 2)()
+        relres = C.c_double()
+        _lib.check(self.lib.sktb_pcg_solve_grid(
+            self.handle, None if mg is None else mg.handle, gridop.handle,
+            _ptr(inv_diag), _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
+            int(maxiter), int(check_every), C.cast(info, C.c_void_p),
+            C.cast(C.byref(relres), C.c_void_p), _stream()))
+        self.last_iters = int(info[0])
+        self.last_converged = bool(info[1])
+        self.last_relres = float(relres.value)
+        self.total_iters += self.last_iters
+        return x
+
+
+class GridOp:
+    """Matrix-free K(rho) on a uniform hexahedral tensor grid (``csrc/gridop.cu``).
+
+    ``np_axes``: nodes per axis (x, y, z); ``ke0``: (24, 24) unit element matrix
+    in the mesh's local vertex order; ``bits``: (8, 3) 0/1 offsets of the local
+    vertices; ``dir_mask``: per-dof uint8 (host)."""
+
+    def __init__(self, np_axes, ke0: np.ndarray, bits: np.ndarray, dir_mask: np.ndarray):
+        require_cuda()
+        self.lib = _lib.load()
+        self.np_axes = np.ascontiguousarray(np_axes, dtype=np.int32)
+        npx, npy, npz = (int(v) for v in self.np_axes)
+        self.n_nodes = npx * npy * npz
+        code = bits[:, 0] + 2 * bits[:, 1] + 4 * bits[:, 2]
+        if sorted(code.tolist()) != list(range(8)):
+            raise ValueError("local vertices are not the 8 corners of a box")
+        loc = np.empty(8, dtype=np.int64)
+        loc[code] = np.arange(8)
+        perm = (3 * loc[:, None] + np.arange(3)[None, :]).ravel()
+        ke_cc = np.ascontiguousarray(np.asarray(ke0, dtype=np.float64).reshape(24, 24)[np.ix_(perm, perm)])
+        # per-node flags: bits 0-2 fixed dofs, bit 3 fixed dof in the 27-neighbourhood
+        m3 = np.asarray(dir_mask, dtype=np.uint8).reshape(-1, 3)
+        own = (m3[:, 0] | (m3[:, 1] << 1) | (m3[:, 2] << 2)).astype(np.uint8)
+        g = (own != 0).reshape(npz, npx, npy)
+        pad = np.pad(g, 1)
+        near = np.zeros_like(g)
+        for dz in range(3):
+            for dx in range(3):
+                for dy in range(3):
+                    near |= pad[dz:dz + npz, dx:dx + npx, dy:dy + npy]
+        self.dmask = to_dev(own | (near.ravel().astype(np.uint8) << 3), U8)
+        h = C.c_void_p()
+        _lib.check(self.lib.sktb_gridop_create(
+            C.byref(h), self.np_axes.ctypes.data_as(C.c_void_p),
+            ke_cc.ctypes.data_as(C.c_void_p), torch.cuda.current_device()))
+        self.handle = h
+        self.scale = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_gridop_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def set_scale(self, scale):
+        self.scale = scale          # keep the tensor alive
+        _lib.check(self.lib.sktb_gridop_set_fields(self.handle, _ptr(scale), _ptr(self.dmask)))
+
+    def apply(self, x, node0: int = 0, n_nodes: int | None = None, out=None):
+        n_nodes = self.n_nodes - node0 if n_nodes is None else int(n_nodes)
+        if out is None:
+            out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+        _lib.check(self.lib.sktb_gridop_apply(self.handle, int(node0), n_nodes, _ptr(x),
+                                              _ptr(out), _stream()))
+        return out
+
+    def inv_diag(self, node0: int = 0, n_nodes: int | None = None, out=None):
+        n_nodes = self.n_nodes - node0 if n_nodes is None else int(n_nodes)
+        if out is None:
+            out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+        _lib.check(self.lib.sktb_gridop_inv_diag(self.handle, int(node0), n_nodes, _ptr(out),
+                                                 _stream()))
+        return out
+
 
 # ------------------------------------------------------- elementwise kernels --
 def interpolate_modulus(rho, E0, Emin, p, ramp=False, out=None):

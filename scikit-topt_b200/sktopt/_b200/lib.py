@@ -51,6 +51,14 @@ SIGNATURES = {
     "sktb_mg_set_level0_range": [C.c_void_p, i64, i64],
     "sktb_mg_set_transfer": [C.c_void_p, i32, C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
     "sktb_mg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
+    "sktb_gridop_create": [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, i32],
+    "sktb_gridop_destroy": [C.c_void_p],
+    "sktb_gridop_set_fields": [C.c_void_p, c_f64p, c_u8p],
+    "sktb_gridop_apply": [C.c_void_p, i64, i64, c_f64p, c_f64p, c_stream],
+    "sktb_gridop_inv_diag": [C.c_void_p, i64, i64, c_f64p, c_stream],
+    "sktb_pcg_solve_grid": [C.c_void_p, C.c_void_p, C.c_void_p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
+    "sktb_pcg_lambda_max_grid": [C.c_void_p, C.c_void_p, c_f64p, i32, C.c_void_p, c_stream],
+    "sktb_mg_set_level0_grid": [C.c_void_p, C.c_void_p, i64, c_f64p, c_u8p],
     "sktb_elem_combine": [i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_restrict": [i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_solve_bsr3_mg": [C.c_void_p, C.c_void_p, c_i32p, c_i32p, i64, i32, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],

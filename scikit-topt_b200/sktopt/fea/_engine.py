@@ -53,14 +53,12 @@ class FeaEngine:
         self.comm = comm
         if comm is None:
             self.node0, self.node1 = 0, dm.n_nodes
-            self.row_ptr, self.col_idx = dm.dof_pattern(dpn)
             self.pcg = dev.PcgSolver(self.n_dof)
             self.cuts = None
         else:
             rp_h, ci_h = dm.node_graph_cached()
             self.cuts = bdist.partition_nodes(rp_h, comm.world)
             self.node0, self.node1 = int(self.cuts[comm.rank]), int(self.cuts[comm.rank + 1])
-            self.row_ptr, self.col_idx = dm.dof_pattern_rows(dpn, self.node0, self.node1)
             halo = bdist.build_halo(rp_h, ci_h, self.cuts, comm.rank, dpn)
             self.pcg = dev.PcgSolver(dpn * (self.node1 - self.node0), comm=comm,
                                      n_global=self.n_dof, row0=dpn * self.node0, halo=halo)
@@ -70,13 +68,20 @@ class FeaEngine:
         # node-block view of the owned rows (3 dofs per node): one column index
         # per 3x3 block for the PCG SpMV; "csr" keeps the per-entry indices
         self.spmv_format = "bsr3" if dpn == 3 else "csr"
-        if dpn == 3:
-            rp_h, ci_h = dm.node_graph_cached()
-            s, e = int(rp_h[self.node0]), int(rp_h[self.node1])
-            self.node_ptr_loc = dev.to_dev(rp_h[self.node0:self.node1 + 1] - s, dev.I32)
-            self.node_col_loc = dev.to_dev(ci_h[s:e], dev.I32)
-            self.max_deg = int(np.diff(rp_h[self.node0:self.node1 + 1]).max())
-        self.vals = torch.empty(self.col_idx.numel(), dtype=dev.F64, device="cuda")
+        self._pattern = None        # assembled-operator buffers, built on first use
+        # matrix-free operator: uniform hexahedral tensor grid (one geometry
+        # class), elasticity.  SKTOPT_B200_MATFREE=0 keeps the assembled SpMV.
+        self.gridop = None
+        axes = None
+        if dpn == 3 and dm.elem_class is not None:
+            from sktopt.fea._multigrid import detect_tensor_grid, vertex_bits
+            axes = detect_tensor_grid(basis.mesh)
+        if (axes is not None and dm.n_class == 1
+                and os.environ.get("SKTOPT_B200_MATFREE", "1") != "0"):
+            self.gridop = dev.GridOp([a.size for a in axes],
+                                     self.unit_ke[0].cpu().numpy(), vertex_bits(basis.mesh), mask)
+        if self.gridop is None:
+            self._ensure_pattern()
         self.inv_diag = torch.empty(self.n_local, dtype=dev.F64, device="cuda")
         self.scale = torch.empty(self.n_elem, dtype=dev.F64, device="cuda")
         self.rhs = torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
@@ -89,8 +94,7 @@ class FeaEngine:
         if want not in ("jacobi", "mg", "auto"):
             raise ValueError("SKTOPT_B200_PRECOND must be jacobi, mg or auto")
         if dpn == 3 and want != "jacobi" and dm.elem_class is not None:
-            from sktopt.fea._multigrid import Multigrid, detect_tensor_grid
-            axes = detect_tensor_grid(basis.mesh)
+            from sktopt.fea._multigrid import Multigrid
             big = dm.n_nodes >= Multigrid.MIN_FINE_NODES or want == "mg"
             if axes is not None and big:
                 try:
@@ -110,6 +114,45 @@ class FeaEngine:
     def sharded(self) -> bool:
         return self.comm is not None
 
+    @property
+    def matrix_free(self) -> bool:
+        return self.gridop is not None
+
+    # -- assembled operator (lazy: a matrix-free engine only builds it when the
+    #    caller asks for the matrix itself) ------------------------------------
+    def _ensure_pattern(self):
+        if self._pattern is not None:
+            return self._pattern
+        dm, dpn = self.dm, self.dpn
+        pt = {}
+        if self.comm is None:
+            pt["row_ptr"], pt["col_idx"] = dm.dof_pattern(dpn)
+        else:
+            pt["row_ptr"], pt["col_idx"] = dm.dof_pattern_rows(dpn, self.node0, self.node1)
+        if dpn == 3:
+            rp_h, ci_h = dm.node_graph_cached()
+            s, e = int(rp_h[self.node0]), int(rp_h[self.node1])
+            pt["node_ptr_loc"] = dev.to_dev(rp_h[self.node0:self.node1 + 1] - s, dev.I32)
+            pt["node_col_loc"] = dev.to_dev(ci_h[s:e], dev.I32)
+            pt["max_deg"] = int(np.diff(rp_h[self.node0:self.node1 + 1]).max())
+        pt["vals"] = torch.empty(pt["col_idx"].numel(), dtype=dev.F64, device="cuda")
+        self._pattern = pt
+        return pt
+
+    row_ptr = property(lambda self: self._ensure_pattern()["row_ptr"])
+    col_idx = property(lambda self: self._ensure_pattern()["col_idx"])
+    vals = property(lambda self: self._ensure_pattern()["vals"])
+    node_ptr_loc = property(lambda self: self._ensure_pattern()["node_ptr_loc"])
+    node_col_loc = property(lambda self: self._ensure_pattern()["node_col_loc"])
+    max_deg = property(lambda self: self._ensure_pattern().get("max_deg", 0))
+
+    @property
+    def nnz(self) -> int:
+        """Non-zeros of the (owned rows of the) assembled operator, without
+        building it."""
+        rp_h, _ = self.dm.node_graph_cached()
+        return int(self.dpn * self.dpn * (int(rp_h[self.node1]) - int(rp_h[self.node0])))
+
     # ------------------------------------------------------------------
     def set_modulus(self, rho, c_max, c_min, p, ramp=False):
         dev.interpolate_modulus(rho, c_max, c_min, p, ramp=ramp, out=self.scale)
@@ -123,7 +166,21 @@ class FeaEngine:
                                      scale=self.scale, dir_mask=mask,
                                      out=self.vals if out is None else out)
 
+    def prepare(self):
+        """Operator + preconditioner for the current modulus field: the
+        matrix-free path only needs the diagonal and the coarse operators, the
+        assembled path gathers K first."""
+        if not self.matrix_free:
+            self.assemble(enforce=True)
+        self.update_preconditioner()
+
     def update_preconditioner(self, vals=None):
+        if self.matrix_free and vals is None:
+            self.gridop.set_scale(self.scale)
+            self.gridop.inv_diag(self.node0, self.node1 - self.node0, out=self.inv_diag)
+            if self.mg is not None and self.mg_enabled:
+                self.mg.setup()
+            return
         v = self.vals if vals is None else vals
         if self.dpn == 3:
             dev.bsr3_inv_diag(self.node_ptr_loc, self.node_col_loc, v, out=self.inv_diag,
@@ -147,6 +204,16 @@ class FeaEngine:
         block3 = self.spmv_format == "bsr3"
         use_mg = self.mg is not None and self.mg_enabled and vals is None
         mi_first = min(mi, 400) if use_mg else mi
+        if self.matrix_free and vals is None:
+            self.pcg.solve_grid(self.gridop, self.inv_diag, rhs[lo:hi], x[lo:hi], rtol=rtol,
+                                maxiter=mi_first, use_x0=self.warm_start,
+                                check_every=2 if use_mg else 32,
+                                mg=self.mg if use_mg else None)
+            if use_mg and not self.pcg.last_converged:
+                logger.warning("multigrid PCG did not converge; continuing with Jacobi PCG")
+                self.pcg.solve_grid(self.gridop, self.inv_diag, rhs[lo:hi], x[lo:hi], rtol=rtol,
+                                    maxiter=mi, use_x0=True, check_every=32)
+            return self._finish_solve(x, rtol)
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,
@@ -163,6 +230,9 @@ class FeaEngine:
             self.pcg.solve(self.node_ptr_loc, self.node_col_loc, self.vals, self.inv_diag,
                            rhs[lo:hi], x[lo:hi], dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
                            use_x0=True, check_every=32, block3=True, max_deg=self.max_deg)
+        return self._finish_solve(x, rtol)
+
+    def _finish_solve(self, x, rtol):
         if self.sharded:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]
@@ -176,6 +246,8 @@ class FeaEngine:
         return x
 
     def spmv(self, x, vals=None, out=None):
+        if self.matrix_free and vals is None and self.gridop.scale is not None:
+            return self.gridop.apply(x, self.node0, self.node1 - self.node0, out=out)
         if self.sharded:
             raise RuntimeError("full-vector SpMV is not available on a sharded operator")
         return dev.spmv(self.row_ptr, self.col_idx,

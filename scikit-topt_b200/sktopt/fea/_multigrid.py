@@ -233,6 +233,13 @@ class Multigrid:
         """Largest eigenvalue of D^-1 A of level ``l`` by power iteration.  Level
         0 runs inside the PCG workspace (it may be row-sharded); the replicated
         coarse levels use plain device kernels.  Every rank gets the same value."""
+        if l == 0 and self.eng.matrix_free:
+            eng = self.eng
+            out = C.c_double()
+            _lib.check(self.lib.sktb_pcg_lambda_max_grid(
+                eng.pcg.handle, eng.gridop.handle, dev._ptr(eng.inv_diag), int(iters),
+                C.cast(C.byref(out), C.c_void_p), dev._stream()))
+            return float(out.value)
         if l == 0:
             eng = self.eng
             out = C.c_double()
@@ -265,10 +272,15 @@ class Multigrid:
         st = dev._stream()
         lib = self.lib
         _lib.check(lib.sktb_mg_set_level0_range(self.handle, int(eng.node0), int(eng.dm.n_nodes)))
-        _lib.check(lib.sktb_mg_set_level(
-            self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()), int(eng.max_deg),
-            dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc), dev._ptr(eng.vals),
-            dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        if eng.matrix_free:
+            _lib.check(lib.sktb_mg_set_level0_grid(
+                self.handle, eng.gridop.handle, int(eng.node1 - eng.node0),
+                dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        else:
+            _lib.check(lib.sktb_mg_set_level(
+                self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()),
+                int(eng.max_deg), dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc),
+                dev._ptr(eng.vals), dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
         for l in range(1, self.n_levels):
             lv = self.levels[l]
             if l == 1 and self.T01 is not None:

@@ -110,9 +110,9 @@ def _run_loads(basis, dirichlet_dofs, force_list, E0, Emin, p, nu0, rho, u_all,
     with _section(timer, "assemble"):
         eng.set_modulus(rho_d, E0, Emin, p, ramp=composer.is_ramp(elem_func))
     with _section(timer, "enforce_bc"):
-        # the Dirichlet mask is applied while the values are gathered
-        eng.assemble(enforce=True)
-        eng.update_preconditioner()
+        # assembled path: the Dirichlet mask is applied while the values are
+        # gathered; matrix-free path: only the diagonal + coarse operators
+        eng.prepare()
     n_loads = len(force_list)
     comp = np.empty(n_loads)
     with _section(timer, "solve"):

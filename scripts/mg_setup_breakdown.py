@@ -13,7 +13,7 @@ tsk.exlude_dirichlet_from_design()
 eng = get_engine(tsk.basis, tsk.dirichlet_dofs, KE_ELASTIC, tsk.nu)
 rho = dev.to_dev(np.random.default_rng(0).uniform(0.2, 1.0, eng.n_elem))
 eng.set_modulus(rho, tsk.E, tsk.E * 1e-3, 3.0)
-eng.assemble(); eng.update_preconditioner()
+eng.prepare()
 mg = eng.mg
 
 def t(fn, reps=5):
