@@ -213,6 +213,10 @@ int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg, const sktb_gridop *op,
 int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
                              const double *inv_diag, int iters, double *out_h,
                              void *stream);
+/* exact coarsest-level solve: dense Gauss-Jordan inverse of the last level's
+ * operator (<= 160 dofs; larger levels keep damped-Jacobi sweeps).  Call after
+ * sktb_mg_set_level(last, ...) whenever its values changed.                    */
+int sktb_mg_factor_coarsest(sktb_mg *m, void *stream);
 /* level 0 of the multigrid hierarchy applied matrix-free                       */
 int sktb_mg_set_level0_grid(sktb_mg *m, const sktb_gridop *op, int64_t n_nodes,
                             const double *inv_diag, const uint8_t *mask);

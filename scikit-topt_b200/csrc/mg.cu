@@ -26,6 +26,8 @@ struct MgLevel {
   const double *vals = nullptr, *inv_diag = nullptr;
   const uint8_t *mask = nullptr;  // per dof, may be null
   const sktb_gridop *gop = nullptr;  // level 0 only: matrix-free operator
+  double *dense_inv = nullptr;       // coarsest level only: dense inverse (owned)
+  int dense_n = 0;                   // 0: not factored
   double *x = nullptr, *b = nullptr, *tmp = nullptr;  // owned work vectors
   // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
   // the operator is not sharded); x is always full length (n_global nodes)
@@ -62,6 +64,7 @@ extern "C" void sktb_mg_destroy(sktb_mg *m) {
     cudaFree(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
+    cudaFree(l.dense_inv);
   }
   delete m;
 }
@@ -101,6 +104,7 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   }
   l.n_nodes = n_nodes;
   l.gop = nullptr;
+  l.dense_n = 0;
   l.n_blocks = n_blocks;
   l.max_deg = max_deg;
   l.node_ptr = node_ptr;
@@ -298,7 +302,8 @@ __global__ void __launch_bounds__(kBlock)
   GS(i, n) x[i] += omega * dinv[i] * (b[i] - Ax[i]);
 }
 
-// b_c = mask_c * P^T (b_f - Ax_f) ; one thread per coarse node
+// b_c = mask_c * P^T (b_f - Ax_f) ; one WARP per coarse node, one lane per
+// fine node of its 3x3x3 stencil (fixed-order shuffle reduction: deterministic)
 __global__ void __launch_bounds__(kBlock)
     mg_restrict_kernel(int cnx, int cny, int cnz, int fnx, int fny, int fnz,
                        const int32_t *__restrict__ axT_f,
@@ -309,36 +314,40 @@ __global__ void __launch_bounds__(kBlock)
                        double *__restrict__ bc, int64_t f_lo, int64_t f_hi) {
   const int64_t nc = (int64_t)cnx * cny * cnz;
   const int tot = cnx + cny + cnz;
-  GS(I, nc) {
+  const int lane = threadIdx.x & 31;
+  const int sy = lane % 3, sx = (lane / 3) % 3, sz = lane / 9;  // lanes >= 27 idle
+  const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t I = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); I < nc;
+       I += wstride) {
     const int iy = (int)(I % cny);
     const int ix = (int)((I / cny) % cnx);
     const int iz = (int)(I / ((int64_t)cny * cnx));
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int sz = 0; sz < 3; ++sz) {
+    if (lane < 27) {
       const int fz = axT_f[sz * tot + cnx + cny + iz];
-      if (fz < 0) continue;
-      const double wz = axT_w[sz * tot + cnx + cny + iz];
-      for (int sx = 0; sx < 3; ++sx) {
-        const int fx = axT_f[sx * tot + ix];
-        if (fx < 0) continue;
-        const double wx = axT_w[sx * tot + ix] * wz;
-        for (int sy = 0; sy < 3; ++sy) {
-          const int fy = axT_f[sy * tot + cnx + iy];
-          if (fy < 0) continue;
-          const double w = axT_w[sy * tot + cnx + iy] * wx;
-          const int64_t fn = (int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz;
-          if (fn < f_lo || fn >= f_hi) continue;  // another rank's fine node
-          const int64_t f = 3 * (fn - f_lo);      // bf / Axf hold the owned rows
-          a0 += w * (bf[f] - Axf[f]);
-          a1 += w * (bf[f + 1] - Axf[f + 1]);
-          a2 += w * (bf[f + 2] - Axf[f + 2]);
+      const int fx = axT_f[sx * tot + ix];
+      const int fy = axT_f[sy * tot + cnx + iy];
+      if (fz >= 0 && fx >= 0 && fy >= 0) {
+        const int64_t fn = (int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz;
+        if (fn >= f_lo && fn < f_hi) {          // else: another rank's fine node
+          const double w = axT_w[sz * tot + cnx + cny + iz] * axT_w[sx * tot + ix] *
+                           axT_w[sy * tot + cnx + iy];
+          const int64_t f = 3 * (fn - f_lo);    // bf / Axf hold the owned rows
+          a0 = w * (bf[f] - Axf[f]);
+          a1 = w * (bf[f + 1] - Axf[f + 1]);
+          a2 = w * (bf[f + 2] - Axf[f + 2]);
         }
       }
     }
-    const int64_t o = 3 * I;
-    bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
-    bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
-    bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      const int64_t o = 3 * I;
+      bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
+      bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+      bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+    }
   }
 }
 
@@ -419,6 +428,100 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// Exact coarsest-level solve: the (enforced, SPD) operator of the last level is
+// expanded to a dense n x n matrix in shared memory and inverted in place by
+// Gauss-Jordan elimination (diagonal pivots) once per set-up; the V-cycle then
+// applies x = A^-1 b as one dense product.  Single CTA, n <= kDenseMax.
+constexpr int kDenseMax = 160;
+
+__global__ void __launch_bounds__(1024)
+    mg_dense_invert_kernel(int n_nodes, const int32_t *__restrict__ node_ptr,
+                           const int32_t *__restrict__ node_col,
+                           const double *__restrict__ vals,
+                           double *__restrict__ inv) {
+  extern __shared__ double sm[];
+  const int n = 3 * n_nodes;
+  double *A = sm;            // n x n
+  double *col = sm + n * n;  // n
+  __shared__ double piv_inv;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) A[i] = 0.0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int nd = r / 3, ri = r - 3 * nd;
+    const int32_t s0 = node_ptr[nd], deg = node_ptr[nd + 1] - s0;
+    const double *vp = vals + (int64_t)9 * s0 + (int64_t)ri * 3 * deg;
+    for (int k = 0; k < deg; ++k) {
+      const int c = 3 * node_col[s0 + k];
+      A[r * n + c] = vp[3 * k];
+      A[r * n + c + 1] = vp[3 * k + 1];
+      A[r * n + c + 2] = vp[3 * k + 2];
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) col[i] = A[i * n + k];
+    if (threadIdx.x == 0) piv_inv = 1.0 / A[k * n + k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+      A[k * n + j] = ((j == k) ? 1.0 : A[k * n + j]) * piv_inv;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (i == k) continue;
+      const double old = (j == k) ? 0.0 : A[e];
+      A[e] = old - col[i] * A[k * n + j];
+    }
+    __syncthreads();
+  }
+  // symmetrised copy (the exact inverse is symmetric; rounding is not)
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    inv[e] = 0.5 * (A[e] + A[j * n + i]);
+  }
+}
+
+// x = Ainv b ; one warp per row
+__global__ void __launch_bounds__(kBlock)
+    mg_dense_apply_kernel(int n, const double *__restrict__ Ainv,
+                          const double *__restrict__ b, double *__restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  double a = 0.0;
+  for (int j = lane; j < n; j += 32) a += Ainv[(int64_t)r * n + j] * b[j];
+  a = warp_sum(a);
+  if (lane == 0) x[r] = a;
+}
+
+// factor the coarsest level (call after its values are set); levels too large
+// for the dense path keep the damped-Jacobi sweeps
+extern "C" int sktb_mg_factor_coarsest(sktb_mg *m, void *stream) {
+  SKTB_REQUIRE(m && m->lv.size() >= 2, "bad argument");
+  MgLevel &l = m->lv.back();
+  SKTB_REQUIRE(l.node_ptr && l.vals, "coarsest level not set");
+  const int n = (int)(3 * l.n_nodes);
+  if (n > kDenseMax) {
+    l.dense_n = 0;
+    return 0;
+  }
+  SKTB_CUDA_OK(cudaSetDevice(m->device));
+  if (!l.dense_inv)
+    SKTB_CUDA_OK(cudaMalloc(&l.dense_inv, sizeof(double) * kDenseMax * kDenseMax));
+  const size_t smem = sizeof(double) * ((size_t)n * n + n);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SKTB_CUDA_OK(cudaFuncSetAttribute(mg_dense_invert_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * (kDenseMax * kDenseMax + kDenseMax))));
+    attr_set = true;
+  }
+  mg_dense_invert_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(
+      (int)l.n_nodes, l.node_ptr, l.node_col, l.vals, l.dense_inv);
+  SKTB_KERNEL_OK();
+  l.dense_n = n;
+  return 0;
+}
+
 static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st) {
   if (l.gop)
     return launch_hexgrid_apply(l.gop, l.node0, l.n_nodes, x, y, nullptr, nullptr,
@@ -449,6 +552,12 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;       // owned rows
     const int g = grid_for(n);
     const double om = l.omega > 0.0 ? l.omega : m->omega;
+    if (k == L - 1 && k > 0 && l.dense_n == n) {
+      mg_dense_apply_kernel<<<(int)((n + kBlock / 32 - 1) / (kBlock / 32)), kBlock, 0, st>>>(
+          (int)n, l.dense_inv, b, x);
+      SKTB_COUNT(1);
+      break;
+    }
     mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
     SKTB_COUNT(1);
     if (k == L - 1 && k > 0 && l.n_nodes <= 4096) {
@@ -469,7 +578,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       MgLevel &c = m->lv[k + 1];
       const int64_t lo = (k == 0) ? f_lo : 0;
       const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
-      mg_restrict_kernel<<<grid_for(c.n_nodes), kBlock, 0, st>>>(
+      mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
           l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
           l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
       SKTB_COUNT(1);

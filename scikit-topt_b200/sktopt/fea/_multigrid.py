@@ -11,6 +11,7 @@ solution, so parity tests are unaffected.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -129,6 +130,7 @@ class Multigrid:
     """Grid hierarchy + Galerkin set-up for one elasticity engine."""
 
     MIN_FINE_NODES = 1500
+    DENSE_MAX_DOFS = 160
 
     def __init__(self, engine, axes, omega: float | None = None, nu_coarse: int = 30,
                  coarsest_max_cells: int = 6):
@@ -136,6 +138,7 @@ class Multigrid:
         self.eng = engine
         self.omega_auto = omega is None
         self.omega = 0.5 if omega is None else float(omega)
+        nu_coarse = int(os.environ.get("SKTOPT_B200_MG_NU_COARSE", nu_coarse))
         self.nu_coarse = int(nu_coarse)
         self.lambda_max = None
         omega = self.omega
@@ -143,7 +146,9 @@ class Multigrid:
         coords = [(xs, ys, zs)]
         while True:
             cx, cy, cz = (c.size - 1 for c in coords[-1])
-            if max(cx, cy, cz) <= coarsest_max_cells or min(cx, cy, cz) <= 2:
+            # stop once the coarsest level fits the dense exact solve
+            # (csrc/mg.cu: kDenseMax dofs) or cannot be halved any more
+            if 3 * (cx + 1) * (cy + 1) * (cz + 1) <= self.DENSE_MAX_DOFS or max(cx, cy, cz) <= 1:
                 break
             coords.append(tuple(a[coarse_index_map(a.size - 1)] for a in coords[-1]))
         self.coords = coords
@@ -303,6 +308,7 @@ class Multigrid:
                 self.handle, l, lv["n_nodes"], int(lv["node_col"].numel()), lv["max_deg"],
                 dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
                 dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+        _lib.check(lib.sktb_mg_factor_coarsest(self.handle, st))
         if self.omega_auto and self.setup_count == 0:
             # per-level damping: omega_l * lambda_max_l ~ 1.75, inside the
             # stability bound 2 (the power iteration approaches lambda_max from
