@@ -41,6 +41,92 @@ __device__ __forceinline__ int clampi(int v, int hi) {
   return v < 0 ? 0 : (v > hi ? hi : v);
 }
 
+// Rows of one node.  FAST: the node is interior in x and z and no node of its
+// neighbourhood carries a Dirichlet dof -- neighbour addresses are plain
+// offsets from the centre (a y-boundary neighbour wraps into the adjacent grid
+// line, harmless: its elements have E = 0), no clamps, no mask look-ups.
+template <bool FAST>
+__device__ __forceinline__ void hexgrid_node_rows(const HexGridParams &P, int64_t n,
+                                                  int ix, int iy, int iz, unsigned dm,
+                                                  const double *__restrict__ x,
+                                                  double (&out)[3]) {
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  double E[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1), ez = iz - 1 + (o >> 2);
+    const bool ok = FAST ? (ey >= 0 && ey < ny)
+                         : (ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz);
+    E[o] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+  }
+  double pe[8][3];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = 0.0;
+  const double *xc = x + 3 * n;
+  const int64_t sx = 3 * (int64_t)npy, sz = 3 * (int64_t)npy * npx;
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const double *line;
+      if (FAST) {
+        line = xc + dx * sx + dz * sz;
+      } else {
+        const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
+        line = x + 3 * ((int64_t)npy * (kx + (int64_t)npx * kz));
+      }
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        double u0, u1, u2;
+        if (FAST) {
+          u0 = __ldg(line + 3 * dy);
+          u1 = __ldg(line + 3 * dy + 1);
+          u2 = __ldg(line + 3 * dy + 2);
+        } else {
+          const int ky = clampi(iy + dy, npy - 1);
+          u0 = __ldg(line + 3 * ky);
+          u1 = __ldg(line + 3 * ky + 1);
+          u2 = __ldg(line + 3 * ky + 2);
+          if (dm & 8u) {
+            const unsigned mb = P.dmask[(line - x) / 3 + ky];
+            if (mb & 1u) u0 = 0.0;
+            if (mb & 2u) u1 = 0.0;
+            if (mb & 4u) u2 = 0.0;
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+          const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+          if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+          const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+          const int cb = bx + 2 * by + 4 * bz;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = (3 * ca + i) * 24 + 3 * cb;
+            pe[o][i] = fma(P.ke[k], u0, pe[o][i]);
+            pe[o][i] = fma(P.ke[k + 1], u1, pe[o][i]);
+            pe[o][i] = fma(P.ke[k + 2], u2, pe[o][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) a = fma(E[o], pe[o][i], a);
+    out[i] = a;
+  }
+  if (!FAST && (dm & 7u)) {
+    if (dm & 1u) out[0] = xc[0];
+    if (dm & 2u) out[1] = xc[1];
+    if (dm & 4u) out[2] = xc[2];
+  }
+}
+
 template <bool DOT>
 __global__ void __launch_bounds__(kBlock, 2)
     hexgrid_apply_kernel(const __grid_constant__ HexGridParams P, int64_t node0,
@@ -50,7 +136,6 @@ __global__ void __launch_bounds__(kBlock, 2)
                          const PcgScalars *S) {
   if (S && S->rr <= S->tol2) return;
   const int npx = P.npx, npy = P.npy, npz = P.npz;
-  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
   double dot = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_loc;
@@ -60,67 +145,12 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int64_t t = n / npy;
     const int ix = (int)(t % npx);
     const int iz = (int)(t / npx);
-    double E[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1),
-                ez = iz - 1 + (o >> 2);
-      const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
-      E[o] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
-    }
     const unsigned dm = P.dmask[n];
-    const bool near = (dm & 8u) != 0;
-    double pe[8][3];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = 0.0;
-#pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-      const int kz = clampi(iz + dz, npz - 1);
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int kx = clampi(ix + dx, npx - 1);
-        const int64_t base = (int64_t)npy * (kx + (int64_t)npx * kz);
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int ky = clampi(iy + dy, npy - 1);
-          const int64_t m = base + ky;
-          double u0 = __ldg(&x[3 * m]), u1 = __ldg(&x[3 * m + 1]),
-                 u2 = __ldg(&x[3 * m + 2]);
-          if (near) {
-            const unsigned mb = P.dmask[m];
-            if (mb & 1u) u0 = 0.0;
-            if (mb & 2u) u1 = 0.0;
-            if (mb & 4u) u2 = 0.0;
-          }
-#pragma unroll
-          for (int o = 0; o < 8; ++o) {
-            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
-            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
-            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
-            const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
-            const int cb = bx + 2 * by + 4 * bz;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const int k = (3 * ca + i) * 24 + 3 * cb;
-              pe[o][i] += P.ke[k] * u0 + P.ke[k + 1] * u1 + P.ke[k + 2] * u2;
-            }
-          }
-        }
-      }
-    }
     double out[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double a = 0.0;
-#pragma unroll
-      for (int o = 0; o < 8; ++o) a += E[o] * pe[o][i];
-      out[i] = a;
-    }
-    if (dm & 7u) {
-      if (dm & 1u) out[0] = x[3 * n];
-      if (dm & 2u) out[1] = x[3 * n + 1];
-      if (dm & 4u) out[2] = x[3 * n + 2];
-    }
+    if (ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1 && !(dm & 8u))
+      hexgrid_node_rows<true>(P, n, ix, iy, iz, dm, x, out);
+    else
+      hexgrid_node_rows<false>(P, n, ix, iy, iz, dm, x, out);
     y[3 * r] = out[0];
     y[3 * r + 1] = out[1];
     y[3 * r + 2] = out[2];
