@@ -231,40 +231,46 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # SURVEY.md 8(d), for the rows this rank owns
-        spmv_bytes = nnz * 12 + int(eng.n_local) * 12 + n_dof * 8
         spmv_ms = spmv_ms_sum / max(spmv_n, 1)
-        achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                with open(tpath) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_step / args.steps,
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-            "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
-                "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
-                "solver": ("device PCG rtol 1e-8, warm start, preconditioner: "
-                           + ("geometric multigrid V(1,1) (Galerkin coarse operators, damped Jacobi)"
-                              if eng.precond == "mg" else "Jacobi")),
-                "pcg_iters_per_step": pcg_iters,
-                "l2": "inputs larger than L2 (CSR 3.0 GB >> 126 MB)",
-                "parallelism": "single GPU" if world == 1 else (
-                    f"elasticity operator row-sharded over {world} GPUs (NCCL halo exchange + "
-                    f"dot all-reduce); filter/element stages replicated"),
-                "rows_per_rank": int(eng.n_local), "halo_dofs": int(getattr(eng, "halo_dofs", 0)),
-                "last_compliance": comp_last,
-            },
-            "roofline": {
+        n_loc_nodes = int(eng.n_local) // 3
+        if eng.matrix_free:
+            # dominant kernel: matrix-free K(rho) p (3 launches per PCG iteration:
+            # q = A p and the two level-0 products of the V-cycle).  It is bound
+            # by the FP64 FMA pipe, not by HBM: 576 DFMA per node row block + 24
+            # for the modulus scaling (DESIGN.md "grid operator").
+            flops = n_loc_nodes * (576 + 24) * 2
+            fp64_peak = dev.fp64_peak_tflops()
+            achieved = flops / (spmv_ms * 1e-3) / 1e12 if spmv_n else None
+            alg_bytes = n_loc_nodes * (24 + 24 + 24 + 1) + n_elem * 8
+            roofline = {
+                "bound": "fp64",
+                "kernel": "hexgrid_apply_kernel<true> (matrix-free q = K(rho) p + p.q; 3 of these per PCG iteration)",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (achieved / fp64_peak) if achieved else None,
+                "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "alg_flops_per_launch": flops, "avg_launch_ms": spmv_ms, "samples": spmv_n,
+                "traffic": None,
+                "hbm": {"alg_bytes_per_launch": alg_bytes,
+                        "achieved_GBs": alg_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None,
+                        "peak_GBs": peak, "peak_source": peak_src},
+                "note": "the assembled-operator SpMV this replaces streamed 8.44 B/nnz (2.1 GB per "
+                        "launch, 0.44 ms at the HBM roofline); the matrix-free product moves "
+                        "~85 MB and is limited by FP64 issue/latency",
+            }
+        else:
+            # SURVEY.md 8(d), for the rows this rank owns
+            spmv_bytes = nnz * 12 + int(eng.n_local) * 12 + n_dof * 8
+            achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+            if os.path.exists(tpath):
+                try:
+                    with open(tpath) as f:
+                        traffic = json.load(f).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roofline = {
                 "bound": "hbm", "kernel": "spmv_bsr3_tma_kernel<true> (PCG q=Ap + p.q, node-block columns, cp.async.bulk ring)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
@@ -277,7 +283,32 @@ def run_b200(args):
                 "note": "achieved uses SURVEY 8(d) CSR bytes (12 B/nnz); the kernel reads one int32 "
                         "column per 3x3 block (8.44 B/nnz), so a value above the copy roofline is "
                         "format compression, see traffic",
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_step / args.steps,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
+                "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
+                "solver": ("device PCG rtol 1e-8, warm start, operator: "
+                           + ("matrix-free grid stencil" if eng.matrix_free else "assembled node-block CSR")
+                           + ", preconditioner: "
+                           + ("geometric multigrid V(1,1) (Galerkin coarse operators, damped Jacobi, "
+                              "exact dense coarsest solve)" if eng.precond == "mg" else "Jacobi")),
+                "pcg_iters_per_step": pcg_iters,
+                "l2": ("per-step working set (u, rho, filter CSR 0.34 GB, level-1 operator 0.27 GB, "
+                       "work vectors) larger than the 126 MB L2; nothing is flushed explicitly"),
+                "parallelism": "single GPU" if world == 1 else (
+                    f"elasticity operator row-sharded over {world} GPUs (NCCL halo exchange + "
+                    f"dot all-reduce); filter/element stages replicated"),
+                "rows_per_rank": int(eng.n_local), "halo_dofs": int(getattr(eng, "halo_dofs", 0)),
+                "last_compliance": comp_last,
             },
+            "roofline": roofline,
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": n_elem * 8, "d2h_bytes_per_step": n_elem * 8 + 8},
             "gpu_launches": int(launches),

@@ -425,6 +425,9 @@ int sktb_enforce_rhs(int64_t n, const double *b, const double *t,
 
 /* benchmark utility: overwrite a > L2-sized scratch buffer                     */
 int sktb_flush_l2(void *scratch, int64_t bytes, void *stream);
+/* benchmark utility: FP64 FMA throughput probe; out holds 148*8*256 doubles,
+ * *flops_h receives the flops of the launch                                    */
+int sktb_fp64_probe(int iters, double *out, int64_t *flops_h, void *stream);
 
 #ifdef __cplusplus
 }

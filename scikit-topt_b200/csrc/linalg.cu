@@ -233,3 +233,31 @@ extern "C" int sktb_flush_l2(void *scratch, int64_t bytes, void *stream) {
   SKTB_KERNEL_OK();
   return 0;
 }
+
+// benchmark utility: FP64 FMA throughput probe (8 independent DFMA chains per
+// thread); out gets one value per thread so the work is not optimised away.
+// Flops of one call = 2 * 8 * iters * (148 * 8 * 256).
+__global__ void __launch_bounds__(kBlock)
+    fp64_probe_kernel(int iters, double a, double *__restrict__ out) {
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+  const double b = 1e-9 * blockIdx.x;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int sktb_fp64_probe(int iters, double *out, int64_t *flops_h, void *stream) {
+  SKTB_REQUIRE(out && iters > 0, "bad argument");
+  const int grid = kNumSM * 8;
+  fp64_probe_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(iters, 0.999999, out);
+  SKTB_KERNEL_OK();
+  if (flops_h) *flops_h = (int64_t)2 * 8 * iters * grid * kBlock;
+  return 0;
+}
