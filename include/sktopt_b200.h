@@ -186,17 +186,21 @@ int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
                        const double *fine_ke, const double *unit,
                        const int32_t *cls, const double *scale, double *out,
                        void *stream);
-/* ---- matrix-free operator for uniform hexahedral tensor grids ---------------
- * Replaces the assembled K(rho) inside the solver where the reference hands
- * scipy/pyamg the assembled matrix (fea/solver_elastic.py:94-104,189-260):
- * y = K(rho) x with K = sum_e scale[e] Ke0 evaluated element-wise from the
- * grid structure (node = iy + npy (ix + npx iz), element = ey + ny (ex + nx ez)).
- * ke_cc_h: the 24x24 unit matrix with local vertices re-ordered by corner code
- * cx + 2 cy + 4 cz (host).  dmask (device, per node): bit i = dof i fixed,
- * bit 3 = some node of the 27-neighbourhood has a fixed dof.                   */
+/* ---- matrix-free operators for uniform hexahedral tensor grids --------------
+ * Replace the assembled matrix inside the solvers where the reference hands
+ * scipy/pyamg an assembled one (elasticity: fea/solver_elastic.py:94-104,
+ * 189-260; Helmholtz filter: filters/helmholtz_filter_nodal.py solve calls):
+ * y = A x with A = sum_e scale[e] Ae0 evaluated element-wise from the grid
+ * structure (node = iy + npy (ix + npx iz), element = ey + ny (ex + nx ez)).
+ * dpn = 3 (elasticity, Ae0 24x24) or 1 (scalar, Ae0 8x8; scale may be NULL = 1).
+ * ke_cc_h: Ae0 with local vertices re-ordered by corner code cx + 2 cy + 4 cz
+ * (host).  dmask (device, per node): bit i = dof i fixed, bit 3 = some node of
+ * the 27-neighbourhood has a fixed dof.                                        */
 typedef struct sktb_gridop sktb_gridop;
-int sktb_gridop_create(sktb_gridop **out, const int32_t *np_h,
+int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_h,
                        const double *ke_cc_h, int device);
+/* tile_h[3] <- node brick (x, y, z) one CTA of the tiled kernel owns           */
+int sktb_gridop_tile_shape(const sktb_gridop *op, int32_t *tile_h);
 void sktb_gridop_destroy(sktb_gridop *op);
 int sktb_gridop_set_fields(sktb_gridop *op, const double *scale,
                            const uint8_t *dmask);

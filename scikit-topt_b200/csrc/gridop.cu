@@ -1,52 +1,235 @@
-// Matrix-free K(rho) x for trilinear hexahedra on a tensor grid with ONE
+// Matrix-free operators for trilinear hexahedra on a tensor grid with ONE
 // geometry class (uniform spacing: create_box_hex).
 //
-//   K(rho) = sum_e E_e Ke0     =>     (K x)_n = sum_{e ∋ n} E_e Ke0[a(n,e), :] x_e
+//   A = sum_e s_e Ae0     =>     (A x)_n = sum_{e ∋ n} s_e Ae0[a(n,e), :] x_e
 //
-// The assembled operator streams 8.44 bytes per non-zero (2.1 GB per product at
-// 1M elements); this kernel reads x (24 B/node, mostly from L1/L2), E (8 B per
-// element) and writes y: the product becomes FP64-pipe bound instead of HBM
-// bound.  One thread owns a node: it walks the 27 neighbours plane by plane,
-// loads each neighbour's displacement once and feeds the <= 8 elements that
-// contain both nodes; the 576 matrix coefficients are kernel parameters
-// (constant bank), so every DFMA takes its coefficient as an immediate
-// constant operand -- no shared memory, no coefficient loads.  Node and
-// element numbering are MeshHex.init_tensor's: node = iy + npy (ix + npx iz),
-// element = ey + ny (ex + nx ez).  Gather formulation: deterministic, no
-// atomics.
+// DPN = 3: elasticity, A = K(rho), s_e = E(rho_e), Ae0 the 24x24 unit stiffness.
+// DPN = 1: scalar operators (Helmholtz filter M + r^2 K, conduction), Ae0 8x8,
+//          s_e optional (1 where the element exists).
 //
-// Dirichlet dofs are handled on the fly (same operator as csr_enforce builds:
-// identity rows/columns): fixed inputs are read as 0, fixed outputs pass x
-// through.  dmask[n] bit i = dof i of node n fixed, bit 3 = some node of the
-// 27-neighbourhood has a fixed dof (only those threads look at neighbour masks).
+// The assembled elasticity operator streams 8.44 bytes per non-zero (2.1 GB per
+// product at 1M elements); here a product reads x (8 DPN B/node), s (8 B per
+// element) and writes y, so it is bound by the FP64 pipe instead of HBM.
+//
+// Tiled kernel: a CTA owns a TY x TX x TZ brick of nodes (one thread per node,
+// tile shape chosen on the host to fit the grid), stages the brick's halo of x
+// (Dirichlet dofs and out-of-grid nodes as 0) and of s (0 for elements outside
+// the grid) in shared memory, and every thread then walks its 27 neighbours
+// plane by plane: each neighbour value is read once (LDS) and feeds the <= 8
+// elements that contain both nodes.  The Ae0 coefficients are kernel parameters
+// (constant bank -> uniform registers), so the inner loop is DFMA + LDCU only;
+// boundaries and Dirichlet conditions cost nothing in the inner loop.  Gather
+// formulation: deterministic, no atomics.  Node / element numbering are
+// MeshHex.init_tensor's: node = iy + npy (ix + npx iz), element = ey + ny (ex +
+// nx ez); coefficient rows/cols are ordered by corner code cx + 2 cy + 4 cz.
+//
+// Dirichlet dofs reproduce what csr_enforce builds (identity rows/columns):
+// fixed inputs are read as 0, fixed outputs pass x through.  dmask[n] bit i =
+// dof i of node n fixed (bit 3 = a fixed dof somewhere in the 27-neighbourhood,
+// used by the untiled reference kernel only).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "linalg.cuh"
 
 using namespace sktb;
 
-struct HexGridParams {
-  double ke[576];  // corner-code order: row 3 ca + i, col 3 cb + j, c = cx + 2 cy + 4 cz
+template <int DPN>
+struct GridParams {
+  double ke[64 * DPN * DPN];
   int32_t npx, npy, npz;
-  const double *scale;   // E per element
-  const uint8_t *dmask;  // per node
+  int32_t ty, tx, tz;     // tile shape (nodes)
+  int32_t nty, ntx, ntz;  // tiles per axis
+  const double *scale;    // per element, may be null (DPN = 1: 1.0)
+  const uint8_t *dmask;   // per node
 };
 
 struct sktb_gridop {
-  HexGridParams P;
+  int dpn = 3;
+  GridParams<3> P3;
+  GridParams<1> P1;
   int device = 0;
   int64_t n_nodes = 0;
+  bool fields_set = false;
+  bool direct = false;  // SKTB_GRIDOP_DIRECT=1: untiled kernel (DPN = 3 only)
+  size_t smem = 0;
 };
 
 __device__ __forceinline__ int clampi(int v, int hi) {
   return v < 0 ? 0 : (v > hi ? hi : v);
 }
 
-// Rows of one node.  FAST: the node is interior in x and z and no node of its
-// neighbourhood carries a Dirichlet dof -- neighbour addresses are plain
-// offsets from the centre (a y-boundary neighbour wraps into the adjacent grid
-// line, harmless: its elements have E = 0), no clamps, no mask look-ups.
+constexpr int kMaxHalo = 1100;  // (TY+2)(TX+2)(TZ+2) bound enforced by the host
+constexpr int kMaxElemTile = 640;
+
+// ------------------------------------------------------------- tiled kernel --
+template <int DPN, bool DOT>
+__global__ void __launch_bounds__(kBlock, 2)
+    grid_apply_tiled_kernel(const __grid_constant__ GridParams<DPN> P, int64_t node0,
+                            int64_t n_loc, int tz_lo, int tz_cnt,
+                            const double *__restrict__ x, double *__restrict__ y,
+                            const double *__restrict__ dotv, double *partials,
+                            unsigned int *ticket, double *dot_out,
+                            const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  extern __shared__ double sm[];
+  const int TY = P.ty, TX = P.tx, TZ = P.tz;
+  const int HY = TY + 2, HX = TX + 2, HZ = TZ + 2;
+  const int EY = TY + 1, EX = TX + 1, EZ = TZ + 1;
+  const int nH = DPN * HY * HX * HZ, nE = EY * EX * EZ;
+  double *su = sm;
+  double *sE = sm + nH;
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int t = threadIdx.x;
+  const bool active = t < TY * TX * TZ;
+  const int lt = active ? t : 0;
+  const int lty = lt % TY, ltx = (lt / TY) % TX, ltz = lt / (TY * TX);
+
+  // staging descriptors: the tile shape is fixed, so which halo entry a thread
+  // copies in pass k never changes -- decode it once
+  constexpr int KU = (DPN * kMaxHalo + kBlock - 1) / kBlock;
+  constexpr int KE = (kMaxElemTile + kBlock - 1) / kBlock;
+  unsigned du[KU], de[KE];
+#pragma unroll
+  for (int k = 0; k < KU; ++k) {
+    const int idx = t + kBlock * k;
+    if (idx < nH) {
+      const int line = idx / (DPN * HY), q = idx - line * (DPN * HY);
+      const int hy = q / DPN, c = q - hy * DPN;
+      const int hz = line / HX, hx = line - hz * HX;
+      du[k] = (unsigned)hy | ((unsigned)hx << 8) | ((unsigned)hz << 16) | ((unsigned)c << 24);
+    } else {
+      du[k] = 0xffffffffu;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KE; ++k) {
+    const int idx = t + kBlock * k;
+    if (idx < nE) {
+      const int ez = idx / (EY * EX), r = idx - ez * (EY * EX);
+      const int ex = r / EY, ey = r - ex * EY;
+      de[k] = (unsigned)ey | ((unsigned)ex << 8) | ((unsigned)ez << 16);
+    } else {
+      de[k] = 0xffffffffu;
+    }
+  }
+  // smem addresses of this thread's stencil: 9 (dx, dz) lines + the element corner
+  const double *ul[9];
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+      ul[dz * 3 + dx] = su + DPN * (((ltz + dz) * HX + ltx + dx) * HY + lty);
+  const double *el = sE + ((ltz * EX + ltx) * EY + lty);
+
+  double dot = 0.0;
+  const int n_tiles = P.nty * P.ntx * tz_cnt;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tyi = tile % P.nty;
+    const int rest = tile / P.nty;
+    const int txi = rest % P.ntx;
+    const int tzi = tz_lo + rest / P.ntx;
+    const int y0 = tyi * TY, x0 = txi * TX, z0 = tzi * TZ;
+    // ---- stage the halo of x (masked) and of the element scale
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+      const unsigned d = du[k];
+      if (d != 0xffffffffu) {
+        const int gy = y0 - 1 + (int)(d & 255u), gx = x0 - 1 + (int)((d >> 8) & 255u),
+                  gz = z0 - 1 + (int)((d >> 16) & 255u);
+        const unsigned c = d >> 24;
+        double v = 0.0;
+        if (gy >= 0 && gy < npy && gx >= 0 && gx < npx && gz >= 0 && gz < npz) {
+          const int64_t m = gy + (int64_t)npy * (gx + (int64_t)npx * gz);
+          if (!((P.dmask[m] >> c) & 1u)) v = __ldg(&x[DPN * m + c]);
+        }
+        su[t + kBlock * k] = v;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KE; ++k) {
+      const unsigned d = de[k];
+      if (d != 0xffffffffu) {
+        const int ey = y0 - 1 + (int)(d & 255u), ex = x0 - 1 + (int)((d >> 8) & 255u),
+                  ez = z0 - 1 + (int)((d >> 16) & 255u);
+        double v = 0.0;
+        if (ey >= 0 && ey < ny && ex >= 0 && ex < nx && ez >= 0 && ez < nz)
+          v = P.scale ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 1.0;
+        sE[t + kBlock * k] = v;
+      }
+    }
+    __syncthreads();
+    // ---- this thread's node
+    double pe[8][DPN];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int i = 0; i < DPN; ++i) pe[o][i] = 0.0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const double *line = ul[(dz + 1) * 3 + dx + 1];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          double u[DPN];
+#pragma unroll
+          for (int j = 0; j < DPN; ++j) u[j] = line[DPN * (dy + 1) + j];
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+            const int cb = bx + 2 * by + 4 * bz;
+#pragma unroll
+            for (int i = 0; i < DPN; ++i)
+#pragma unroll
+              for (int j = 0; j < DPN; ++j)
+                pe[o][i] = fma(P.ke[(DPN * ca + i) * (8 * DPN) + DPN * cb + j], u[j], pe[o][i]);
+          }
+        }
+      }
+    }
+    double out[DPN];
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) out[i] = 0.0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const double E = el[(((o >> 2) * EX + (o & 1)) * EY) + ((o >> 1) & 1)];
+#pragma unroll
+      for (int i = 0; i < DPN; ++i) out[i] = fma(E, pe[o][i], out[i]);
+    }
+    const int gy = y0 + lty, gx = x0 + ltx, gz = z0 + ltz;
+    if (active && gy < npy && gx < npx && gz < npz) {
+      const int64_t n = gy + (int64_t)npy * (gx + (int64_t)npx * gz);
+      const int64_t r = n - node0;
+      if (r >= 0 && r < n_loc) {
+        const unsigned dm = P.dmask[n];
+#pragma unroll
+        for (int i = 0; i < DPN; ++i) {
+          if ((dm >> i) & 1u) out[i] = x[DPN * n + i];
+          y[DPN * r + i] = out[i];
+          if (DOT) dot = fma(out[i], dotv[DPN * r + i], dot);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+// ------------------------------------- untiled kernel (DPN = 3, reference) --
+// One thread per node straight from global memory / L1.  FAST: the node is
+// interior in x and z and no node of its neighbourhood carries a Dirichlet dof
+// (a y-boundary neighbour wraps into the adjacent grid line, harmless: its
+// elements have E = 0).
 template <bool FAST>
-__device__ __forceinline__ void hexgrid_node_rows(const HexGridParams &P, int64_t n,
+__device__ __forceinline__ void hexgrid_node_rows(const GridParams<3> &P, int64_t n,
                                                   int ix, int iy, int iz, unsigned dm,
                                                   const double *__restrict__ x,
                                                   double (&out)[3]) {
@@ -129,7 +312,7 @@ __device__ __forceinline__ void hexgrid_node_rows(const HexGridParams &P, int64_
 
 template <bool DOT>
 __global__ void __launch_bounds__(kBlock, 2)
-    hexgrid_apply_kernel(const __grid_constant__ HexGridParams P, int64_t node0,
+    hexgrid_apply_kernel(const __grid_constant__ GridParams<3> P, int64_t node0,
                          int64_t n_loc, const double *__restrict__ x,
                          double *__restrict__ y, const double *__restrict__ dotv,
                          double *partials, unsigned int *ticket, double *dot_out,
@@ -163,10 +346,11 @@ __global__ void __launch_bounds__(kBlock, 2)
   }
 }
 
-// out[3r+i] = 1 / K_ii (1 at fixed dofs)
+// out[DPN r + i] = 1 / A_ii (1 at fixed dofs)
+template <int DPN>
 __global__ void __launch_bounds__(kBlock)
-    hexgrid_inv_diag_kernel(const __grid_constant__ HexGridParams P, int64_t node0,
-                            int64_t n_loc, double *__restrict__ out) {
+    grid_inv_diag_kernel(const __grid_constant__ GridParams<DPN> P, int64_t node0,
+                         int64_t n_loc, double *__restrict__ out) {
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -177,51 +361,131 @@ __global__ void __launch_bounds__(kBlock)
     const int64_t t = n / npy;
     const int ix = (int)(t % npx);
     const int iz = (int)(t / npx);
-    double d[3] = {0.0, 0.0, 0.0};
+    double d[DPN];
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) d[i] = 0.0;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
       const int ex = ix - 1 + ox, ey = iy - 1 + oy, ez = iz - 1 + oz;
       const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
-      const double E = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+      const double E =
+          ok ? (P.scale ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 1.0)
+             : 0.0;
       const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) d[i] += E * P.ke[(3 * ca + i) * 25];
+      for (int i = 0; i < DPN; ++i) d[i] += E * P.ke[(DPN * ca + i) * (8 * DPN + 1)];
     }
     const unsigned dm = P.dmask[n];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) out[3 * r + i] = ((dm >> i) & 1u) ? 1.0 : 1.0 / d[i];
+    for (int i = 0; i < DPN; ++i) out[DPN * r + i] = ((dm >> i) & 1u) ? 1.0 : 1.0 / d[i];
   }
+}
+
+// ------------------------------------------------------------------ launch --
+template <int DPN>
+static int launch_tiled(const sktb_gridop *op, const GridParams<DPN> &P, int64_t node0,
+                        int64_t n_nodes, const double *x, double *y, const double *dotv,
+                        ReduceScratch *rs, double *dot_out, const PcgScalars *S,
+                        cudaStream_t st) {
+  // tiles whose z range meets the owned nodes (all of them when not sharded)
+  const int64_t plane = (int64_t)P.npx * P.npy;
+  const int z_lo = (int)(node0 / plane), z_hi = (int)((node0 + n_nodes - 1) / plane);
+  const int tz_lo = z_lo / P.tz, tz_cnt = z_hi / P.tz - tz_lo + 1;
+  const int64_t n_tiles = (int64_t)P.nty * P.ntx * tz_cnt;
+  const int grid = (int)(n_tiles < 2 * kNumSM ? n_tiles : 2 * kNumSM);
+  if (dotv)
+    grid_apply_tiled_kernel<DPN, true><<<grid, kBlock, op->smem, st>>>(
+        P, node0, n_nodes, tz_lo, tz_cnt, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+  else
+    grid_apply_tiled_kernel<DPN, false><<<grid, kBlock, op->smem, st>>>(
+        P, node0, n_nodes, tz_lo, tz_cnt, x, y, nullptr, nullptr, nullptr, nullptr, S);
+  SKTB_KERNEL_OK();
+  return 0;
 }
 
 int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
                          const double *x, double *y, const double *dotv,
                          ReduceScratch *rs, double *dot_out, const PcgScalars *S,
                          cudaStream_t st) {
+  if (op->dpn == 1)
+    return launch_tiled<1>(op, op->P1, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
+  if (!op->direct)
+    return launch_tiled<3>(op, op->P3, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
   const int grid = grid_for(n_nodes, kBlock, 16);
   if (dotv)
     hexgrid_apply_kernel<true><<<grid, kBlock, 0, st>>>(
-        op->P, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+        op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
   else
     hexgrid_apply_kernel<false><<<grid, kBlock, 0, st>>>(
-        op->P, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+        op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
   SKTB_KERNEL_OK();
   return 0;
 }
 
-extern "C" int sktb_gridop_create(sktb_gridop **out, const int32_t *np_h,
+int gridop_dpn(const sktb_gridop *op) { return op->dpn; }
+
+// tile shape: as many of the 256 threads busy as possible, small halo
+template <int DPN>
+static void choose_tiles(GridParams<DPN> &P, size_t *smem) {
+  const double a = DPN == 3 ? 1300.0 : 150.0;  // per-thread compute vs staging weight
+  double best = 1e300;
+  for (int ty = 4; ty <= 64; ++ty)
+    for (int tx = 1; tx <= 16; ++tx)
+      for (int tz = 1; tz <= 8; ++tz) {
+        const int T = ty * tx * tz;
+        if (T > kBlock || T < 128) continue;
+        const int halo = (ty + 2) * (tx + 2) * (tz + 2);
+        const int et = (ty + 1) * (tx + 1) * (tz + 1);
+        if (halo > kMaxHalo || et > kMaxElemTile) continue;
+        const int64_t nt = (int64_t)((P.npy + ty - 1) / ty) * ((P.npx + tx - 1) / tx) *
+                           ((P.npz + tz - 1) / tz);
+        const double cost = (double)nt * (a + 25.0 * (DPN * halo + et) / (double)kBlock);
+        if (cost < best) {
+          best = cost;
+          P.ty = ty;
+          P.tx = tx;
+          P.tz = tz;
+        }
+      }
+  P.nty = (P.npy + P.ty - 1) / P.ty;
+  P.ntx = (P.npx + P.tx - 1) / P.tx;
+  P.ntz = (P.npz + P.tz - 1) / P.tz;
+  *smem = sizeof(double) * ((size_t)DPN * (P.ty + 2) * (P.tx + 2) * (P.tz + 2) +
+                            (size_t)(P.ty + 1) * (P.tx + 1) * (P.tz + 1));
+}
+
+extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_h,
                                   const double *ke_cc_h, int device) {
   SKTB_REQUIRE(out && np_h && ke_cc_h, "null argument");
+  SKTB_REQUIRE(dpn == 1 || dpn == 3, "dofs per node must be 1 or 3");
   SKTB_REQUIRE(np_h[0] >= 2 && np_h[1] >= 2 && np_h[2] >= 2, "grid needs >= 1 cell per axis");
   sktb_gridop *op = new sktb_gridop();
-  for (int i = 0; i < 576; ++i) op->P.ke[i] = ke_cc_h[i];
-  op->P.npx = np_h[0];
-  op->P.npy = np_h[1];
-  op->P.npz = np_h[2];
-  op->P.scale = nullptr;
-  op->P.dmask = nullptr;
+  op->dpn = dpn;
   op->device = device;
   op->n_nodes = (int64_t)np_h[0] * np_h[1] * np_h[2];
+  const char *env = getenv("SKTB_GRIDOP_DIRECT");
+  op->direct = dpn == 3 && env && env[0] == '1';
+  auto fill = [&](auto &P, int nke) {
+    for (int i = 0; i < nke; ++i) P.ke[i] = ke_cc_h[i];
+    P.npx = np_h[0];
+    P.npy = np_h[1];
+    P.npz = np_h[2];
+    P.scale = nullptr;
+    P.dmask = nullptr;
+  };
+  SKTB_CUDA_OK(cudaSetDevice(device));
+  if (dpn == 3) {
+    fill(op->P3, 576);
+    choose_tiles<3>(op->P3, &op->smem);
+    SKTB_CUDA_OK(cudaFuncSetAttribute(grid_apply_tiled_kernel<3, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    SKTB_CUDA_OK(cudaFuncSetAttribute(grid_apply_tiled_kernel<3, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  } else {
+    fill(op->P1, 64);
+    choose_tiles<1>(op->P1, &op->smem);
+  }
   *out = op;
   return 0;
 }
@@ -230,13 +494,23 @@ extern "C" void sktb_gridop_destroy(sktb_gridop *op) { delete op; }
 
 extern "C" int sktb_gridop_set_fields(sktb_gridop *op, const double *scale,
                                       const uint8_t *dmask) {
-  SKTB_REQUIRE(op && scale && dmask, "null argument");
-  op->P.scale = scale;
-  op->P.dmask = dmask;
+  SKTB_REQUIRE(op && dmask, "null argument");
+  SKTB_REQUIRE(scale || op->dpn == 1, "the elasticity operator needs the element moduli");
+  op->P3.scale = op->P1.scale = scale;
+  op->P3.dmask = op->P1.dmask = dmask;
+  op->fields_set = true;
   return 0;
 }
 
-bool gridop_ready(const sktb_gridop *op) { return op && op->P.scale && op->P.dmask; }
+extern "C" int sktb_gridop_tile_shape(const sktb_gridop *op, int32_t *tile_h) {
+  SKTB_REQUIRE(op && tile_h, "null argument");
+  tile_h[0] = op->dpn == 3 ? op->P3.tx : op->P1.tx;
+  tile_h[1] = op->dpn == 3 ? op->P3.ty : op->P1.ty;
+  tile_h[2] = op->dpn == 3 ? op->P3.tz : op->P1.tz;
+  return 0;
+}
+
+bool gridop_ready(const sktb_gridop *op) { return op && op->fields_set; }
 
 extern "C" int sktb_gridop_apply(const sktb_gridop *op, int64_t node0,
                                  int64_t n_nodes, const double *x, double *y,
@@ -251,8 +525,12 @@ extern "C" int sktb_gridop_inv_diag(const sktb_gridop *op, int64_t node0,
                                     int64_t n_nodes, double *out, void *stream) {
   SKTB_REQUIRE(gridop_ready(op) && out, "null argument");
   SKTB_REQUIRE(node0 >= 0 && n_nodes > 0 && node0 + n_nodes <= op->n_nodes, "bad node range");
-  hexgrid_inv_diag_kernel<<<grid_for(n_nodes), kBlock, 0, (cudaStream_t)stream>>>(
-      op->P, node0, n_nodes, out);
+  if (op->dpn == 3)
+    grid_inv_diag_kernel<3><<<grid_for(n_nodes), kBlock, 0, (cudaStream_t)stream>>>(
+        op->P3, node0, n_nodes, out);
+  else
+    grid_inv_diag_kernel<1><<<grid_for(n_nodes), kBlock, 0, (cudaStream_t)stream>>>(
+        op->P1, node0, n_nodes, out);
   SKTB_KERNEL_OK();
   return 0;
 }

@@ -44,6 +44,7 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
 // a full-length vector; same dot / early-exit contract as the SpMV launchers
 struct sktb_gridop;
 bool gridop_ready(const sktb_gridop *op);
+int gridop_dpn(const sktb_gridop *op);
 int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
                          const double *x, double *y, const double *dotv,
                          sktb::ReduceScratch *rs, double *dot_out,

@@ -326,8 +326,8 @@ static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
                      const double *dotv, ReduceScratch *rs, double *dot_out,
                      const PcgScalars *S, cudaStream_t st) {
   if (A.kind == 2)
-    return launch_hexgrid_apply(A.gop, A.node0, n / 3, x, y, dotv, rs, dot_out, S,
-                                st);
+    return launch_hexgrid_apply(A.gop, A.node0, n / gridop_dpn(A.gop), x, y, dotv, rs,
+                                dot_out, S, st);
   if (A.kind == 1) {
     int rc = launch_spmv_bsr3_tma(n / 3, A.n_blocks, A.max_deg, A.rp, A.ci,
                                   A.vals, x, y, dotv, rs, dot_out, S, st);
@@ -580,9 +580,9 @@ extern "C" int sktb_pcg_lambda_max_bsr3(sktb_pcg *s, const int32_t *node_ptr,
 
 // ------------------------------------------- matrix-free grid operator path --
 static PcgMat grid_mat(const sktb_pcg *s, const sktb_gridop *op) {
-  PcgMat A{2, 3, nullptr, nullptr, nullptr};
+  PcgMat A{2, gridop_dpn(op), nullptr, nullptr, nullptr};
   A.gop = op;
-  A.node0 = s->row0 / 3;
+  A.node0 = s->row0 / gridop_dpn(op);
   return A;
 }
 
@@ -592,8 +592,10 @@ extern "C" int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg,
                                    double rtol, int maxiter, int check_every,
                                    int32_t *info_h, double *relres_h,
                                    void *stream) {
-  SKTB_REQUIRE(s && op && s->n % 3 == 0 && s->row0 % 3 == 0,
-               "grid solve needs 3 dofs per node");
+  SKTB_REQUIRE(s && gridop_ready(op), "null argument");
+  SKTB_REQUIRE(s->n % gridop_dpn(op) == 0 && s->row0 % gridop_dpn(op) == 0,
+               "row range is not a whole number of nodes");
+  SKTB_REQUIRE(!mg || gridop_dpn(op) == 3, "multigrid needs the 3-dof operator");
   return pcg_run(s, grid_mat(s, op), inv_diag, b, x, use_x0, rtol, maxiter,
                  check_every, info_h, relres_h, stream, mg);
 }
@@ -601,7 +603,8 @@ extern "C" int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg,
 extern "C" int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
                                         const double *inv_diag, int iters,
                                         double *out_h, void *stream) {
-  SKTB_REQUIRE(s && gridop_ready(op) && inv_diag && out_h && iters > 0 && s->n % 3 == 0,
+  SKTB_REQUIRE(s && gridop_ready(op) && inv_diag && out_h && iters > 0 &&
+                   s->n % gridop_dpn(op) == 0,
                "bad argument");
   return lambda_max_run(s, grid_mat(s, op), inv_diag, iters, out_h, stream);
 }

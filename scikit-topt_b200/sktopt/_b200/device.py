@@ -488,15 +488,17 @@ class PcgSolver:
 
 
 class GridOp:
-    """Matrix-free K(rho) on a uniform hexahedral tensor grid (``csrc/gridop.cu``).
+    """Matrix-free operator on a uniform hexahedral tensor grid (``csrc/gridop.cu``).
 
-    ``np_axes``: nodes per axis (x, y, z); ``ke0``: (24, 24) unit element matrix
-    in the mesh's local vertex order; ``bits``: (8, 3) 0/1 offsets of the local
-    vertices; ``dir_mask``: per-dof uint8 (host)."""
+    ``np_axes``: nodes per axis (x, y, z); ``ke0``: (8 dpn, 8 dpn) unit element
+    matrix in the mesh's local vertex order; ``bits``: (8, 3) 0/1 offsets of the
+    local vertices; ``dir_mask``: per-dof uint8 (host) or None; ``dpn``: dofs per
+    node (3: elasticity, 1: scalar)."""
 
-    def __init__(self, np_axes, ke0: np.ndarray, bits: np.ndarray, dir_mask: np.ndarray):
+    def __init__(self, np_axes, ke0: np.ndarray, bits: np.ndarray, dir_mask, dpn: int = 3):
         require_cuda()
         self.lib = _lib.load()
+        self.dpn = int(dpn)
         self.np_axes = np.ascontiguousarray(np_axes, dtype=np.int32)
         npx, npy, npz = (int(v) for v in self.np_axes)
         self.n_nodes = npx * npy * npz
@@ -505,11 +507,28 @@ class GridOp:
             raise ValueError("local vertices are not the 8 corners of a box")
         loc = np.empty(8, dtype=np.int64)
         loc[code] = np.arange(8)
-        perm = (3 * loc[:, None] + np.arange(3)[None, :]).ravel()
-        ke_cc = np.ascontiguousarray(np.asarray(ke0, dtype=np.float64).reshape(24, 24)[np.ix_(perm, perm)])
-        # per-node flags: bits 0-2 fixed dofs, bit 3 fixed dof in the 27-neighbourhood
-        m3 = np.asarray(dir_mask, dtype=np.uint8).reshape(-1, 3)
-        own = (m3[:, 0] | (m3[:, 1] << 1) | (m3[:, 2] << 2)).astype(np.uint8)
+        perm = (dpn * loc[:, None] + np.arange(dpn)[None, :]).ravel()
+        nd = 8 * dpn
+        ke_cc = np.ascontiguousarray(np.asarray(ke0, dtype=np.float64).reshape(nd, nd)[np.ix_(perm, perm)])
+        self.dmask = self.node_flags(dir_mask)
+        h = C.c_void_p()
+        _lib.check(self.lib.sktb_gridop_create(
+            C.byref(h), self.dpn, self.np_axes.ctypes.data_as(C.c_void_p),
+            ke_cc.ctypes.data_as(C.c_void_p), torch.cuda.current_device()))
+        self.handle = h
+        self.scale = None
+        self._fields = False
+
+    def node_flags(self, dir_mask):
+        """Per-node uint8 device flags: bits 0..dpn-1 fixed dofs, bit 3 fixed dof
+        in the 27-neighbourhood."""
+        npx, npy, npz = (int(v) for v in self.np_axes)
+        if dir_mask is None:
+            return to_dev(np.zeros(self.n_nodes, dtype=np.uint8), U8)
+        m = np.asarray(dir_mask, dtype=np.uint8).reshape(-1, self.dpn)
+        own = np.zeros(self.n_nodes, dtype=np.uint8)
+        for i in range(self.dpn):
+            own |= (m[:, i] != 0).astype(np.uint8) << i
         g = (own != 0).reshape(npz, npx, npy)
         pad = np.pad(g, 1)
         near = np.zeros_like(g)
@@ -517,13 +536,13 @@ class GridOp:
             for dx in range(3):
                 for dy in range(3):
                     near |= pad[dz:dz + npz, dx:dx + npx, dy:dy + npy]
-        self.dmask = to_dev(own | (near.ravel().astype(np.uint8) << 3), U8)
-        h = C.c_void_p()
-        _lib.check(self.lib.sktb_gridop_create(
-            C.byref(h), self.np_axes.ctypes.data_as(C.c_void_p),
-            ke_cc.ctypes.data_as(C.c_void_p), torch.cuda.current_device()))
-        self.handle = h
-        self.scale = None
+        return to_dev(own | (near.ravel().astype(np.uint8) << 3), U8)
+
+    @property
+    def tile_shape(self):
+        t = (C.c_int32 * 3)()
+        _lib.check(self.lib.sktb_gridop_tile_shape(self.handle, C.cast(t, C.c_void_p)))
+        return tuple(int(v) for v in t)
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -534,14 +553,20 @@ class GridOp:
                 pass
             self.handle = None
 
-    def set_scale(self, scale):
-        self.scale = scale          # keep the tensor alive
-        _lib.check(self.lib.sktb_gridop_set_fields(self.handle, _ptr(scale), _ptr(self.dmask)))
+    def set_scale(self, scale=None, dmask=None):
+        """Element scale (device fp64, None = 1 for the scalar operator) and,
+        optionally, another per-node flag array (``node_flags``)."""
+        self.scale = scale          # keep the tensors alive
+        if dmask is not None:
+            self.dmask = dmask
+        _lib.check(self.lib.sktb_gridop_set_fields(
+            self.handle, None if scale is None else _ptr(scale), _ptr(self.dmask)))
+        self._fields = True
 
     def apply(self, x, node0: int = 0, n_nodes: int | None = None, out=None):
         n_nodes = self.n_nodes - node0 if n_nodes is None else int(n_nodes)
         if out is None:
-            out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+            out = torch.empty(self.dpn * n_nodes, dtype=F64, device="cuda")
         _lib.check(self.lib.sktb_gridop_apply(self.handle, int(node0), n_nodes, _ptr(x),
                                               _ptr(out), _stream()))
         return out
@@ -549,7 +574,7 @@ class GridOp:
     def inv_diag(self, node0: int = 0, n_nodes: int | None = None, out=None):
         n_nodes = self.n_nodes - node0 if n_nodes is None else int(n_nodes)
         if out is None:
-            out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+            out = torch.empty(self.dpn * n_nodes, dtype=F64, device="cuda")
         _lib.check(self.lib.sktb_gridop_inv_diag(self.handle, int(node0), n_nodes, _ptr(out),
                                                  _stream()))
         return out

@@ -51,7 +51,8 @@ SIGNATURES = {
     "sktb_mg_set_level0_range": [C.c_void_p, i64, i64],
     "sktb_mg_set_transfer": [C.c_void_p, i32, C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
     "sktb_mg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
-    "sktb_gridop_create": [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, i32],
+    "sktb_gridop_create": [C.POINTER(C.c_void_p), i32, C.c_void_p, C.c_void_p, i32],
+    "sktb_gridop_tile_shape": [C.c_void_p, C.c_void_p],
     "sktb_gridop_destroy": [C.c_void_p],
     "sktb_gridop_set_fields": [C.c_void_p, c_f64p, c_u8p],
     "sktb_gridop_apply": [C.c_void_p, i64, i64, c_f64p, c_f64p, c_stream],

@@ -246,7 +246,7 @@ class FeaEngine:
         return x
 
     def spmv(self, x, vals=None, out=None):
-        if self.matrix_free and vals is None and self.gridop.scale is not None:
+        if self.matrix_free and vals is None and self.gridop._fields:
             return self.gridop.apply(x, self.node0, self.node1 - self.node0, out=out)
         if self.sharded:
             raise RuntimeError("full-vector SpMV is not available on a sharded operator")
