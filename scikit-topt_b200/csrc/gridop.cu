@@ -131,21 +131,27 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int txi = rest % P.ntx;
     const int tzi = tz_lo + rest / P.ntx;
     const int y0 = tyi * TY, x0 = txi * TX, z0 = tzi * TZ;
-    // ---- stage the halo of x (masked) and of the element scale
+    // ---- stage the halo of x (masked) and of the element scale; all loads of
+    // the tile are issued before the first use (clamped addresses, select after)
+    {
+      double v[KU];
+      unsigned mb[KU];
+      bool ok[KU];
 #pragma unroll
-    for (int k = 0; k < KU; ++k) {
-      const unsigned d = du[k];
-      if (d != 0xffffffffu) {
+      for (int k = 0; k < KU; ++k) {
+        const unsigned d = du[k];
         const int gy = y0 - 1 + (int)(d & 255u), gx = x0 - 1 + (int)((d >> 8) & 255u),
                   gz = z0 - 1 + (int)((d >> 16) & 255u);
-        const unsigned c = d >> 24;
-        double v = 0.0;
-        if (gy >= 0 && gy < npy && gx >= 0 && gx < npx && gz >= 0 && gz < npz) {
-          const int64_t m = gy + (int64_t)npy * (gx + (int64_t)npx * gz);
-          if (!((P.dmask[m] >> c) & 1u)) v = __ldg(&x[DPN * m + c]);
-        }
-        su[t + kBlock * k] = v;
+        const unsigned c = (d >> 24) & 3u;
+        ok[k] = d != 0xffffffffu && gy >= 0 && gy < npy && gx >= 0 && gx < npx && gz >= 0 &&
+                gz < npz;
+        const int64_t m = ok[k] ? gy + (int64_t)npy * (gx + (int64_t)npx * gz) : 0;
+        mb[k] = (P.dmask[m] >> c) & 1u;
+        v[k] = __ldg(&x[DPN * m + (ok[k] ? c : 0u)]);
       }
+#pragma unroll
+      for (int k = 0; k < KU; ++k)
+        if (du[k] != 0xffffffffu) su[t + kBlock * k] = (ok[k] && !mb[k]) ? v[k] : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < KE; ++k) {
@@ -153,9 +159,9 @@ __global__ void __launch_bounds__(kBlock, 2)
       if (d != 0xffffffffu) {
         const int ey = y0 - 1 + (int)(d & 255u), ex = x0 - 1 + (int)((d >> 8) & 255u),
                   ez = z0 - 1 + (int)((d >> 16) & 255u);
-        double v = 0.0;
-        if (ey >= 0 && ey < ny && ex >= 0 && ex < nx && ez >= 0 && ez < nz)
-          v = P.scale ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 1.0;
+        const bool in = ey >= 0 && ey < ny && ex >= 0 && ex < nx && ez >= 0 && ez < nz;
+        double v = in ? 1.0 : 0.0;
+        if (P.scale) v = in ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
         sE[t + kBlock * k] = v;
       }
     }

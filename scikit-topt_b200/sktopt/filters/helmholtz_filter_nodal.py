@@ -14,9 +14,15 @@ solver on every application; here M and K are assembled once on the device
 rebuilt only when the radius changes, and each application is one gather
 kernel, one SpMV, one Jacobi-PCG solve (tight tolerance, warm-started from the
 previous application) and one gather kernel.
+
+On uniform hexahedral tensor grids (``create_box_hex``) neither M nor A is
+assembled: both are applied matrix-free by the scalar grid operator
+(``csrc/gridop.cu``, 8x8 element matrix Me + r^2 Ke as kernel constants);
+``SKTOPT_B200_MATFREE=0`` keeps the assembled CSR path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -48,11 +54,10 @@ class _HelmholtzDevice:
         dev.require_cuda()
         self.dm = dev.device_mesh(mesh)
         basis = Basis(mesh, infer_element_from_mesh(mesh))  # default intorder
-        self.row_ptr, self.col_idx = self.dm.dof_pattern(1)
         n = self.dm.n_nodes
         self.n_nodes = n
-        self.M = self.dm.assemble(1, self.dm.unit_ke(KE_MASS, basis.X, basis.W))
-        self.K = self.dm.assemble(1, self.dm.unit_ke(KE_LAPLACE, basis.X, basis.W))
+        ke_m = self.dm.unit_ke(KE_MASS, basis.X, basis.W)
+        ke_k = self.dm.unit_ke(KE_LAPLACE, basis.X, basis.W)
         self.w = dev.to_dev(elements_volume)
         self.wsum = self.dm.e2n_wsum(self.w)
         if design_mask is None:
@@ -67,8 +72,27 @@ class _HelmholtzDevice:
         fm[fixed_nodes] = 1
         self.fixed_u8 = dev.to_dev(fm, dev.U8)
         self.x_fixed = dev.to_dev(fm.astype(np.float64))  # x0: 1 on fixed nodes
-        self.A = torch.empty_like(self.M)
-        self.A_fwd = torch.empty_like(self.M) if self.has_fixed else None
+        # matrix-free on uniform tensor grids, assembled CSR otherwise
+        self.grid = None
+        if (isinstance(mesh, MeshHex) and self.dm.elem_class is not None and self.dm.n_class == 1
+                and os.environ.get("SKTOPT_B200_MATFREE", "1") != "0"):
+            from sktopt.fea._multigrid import detect_tensor_grid, vertex_bits
+            axes = detect_tensor_grid(mesh)
+            if axes is not None:
+                self.grid = dict(np_axes=[a.size for a in axes], bits=vertex_bits(mesh),
+                                 me=ke_m[0].cpu().numpy(), ke=ke_k[0].cpu().numpy())
+                self.gop_M = dev.GridOp(self.grid["np_axes"], self.grid["me"], self.grid["bits"],
+                                        None, dpn=1)
+                self.gop_M.set_scale(None)
+                self.flags_free = self.gop_M.dmask
+                self.flags_fixed = self.gop_M.node_flags(fm)
+                self.gop_A = None
+        if self.grid is None:
+            self.row_ptr, self.col_idx = self.dm.dof_pattern(1)
+            self.M = self.dm.assemble(1, ke_m)
+            self.K = self.dm.assemble(1, ke_k)
+            self.A = torch.empty_like(self.M)
+            self.A_fwd = torch.empty_like(self.M) if self.has_fixed else None
         self.minv = torch.empty(n, dtype=dev.F64, device="cuda")
         self.minv_fwd = torch.empty(n, dtype=dev.F64, device="cuda") if self.has_fixed else None
         self.c = torch.empty(n, dtype=dev.F64, device="cuda")
@@ -84,6 +108,18 @@ class _HelmholtzDevice:
     def set_radius(self, r: float):
         if self.radius == r:
             return
+        if self.grid is not None:
+            g = self.grid
+            self.gop_A = dev.GridOp(g["np_axes"], g["me"] + float(r) ** 2 * g["ke"], g["bits"],
+                                    None, dpn=1)
+            self.gop_A.set_scale(None, dmask=self.flags_free)
+            self.gop_A.inv_diag(out=self.minv)
+            if self.has_fixed:
+                self.gop_A.apply(self.x_fixed, out=self.c)
+                self.gop_A.set_scale(None, dmask=self.flags_fixed)
+                self.gop_A.inv_diag(out=self.minv_fwd)
+            self.radius = r
+            return
         self.A.copy_(self.M)
         dev.axpby(float(r) ** 2, self.K, 1.0, self.A)  # A = M + r^2 K
         dev.csr_inv_diag(self.row_ptr, self.col_idx, self.A, out=self.minv)
@@ -94,10 +130,22 @@ class _HelmholtzDevice:
             dev.csr_inv_diag(self.row_ptr, self.col_idx, self.A_fwd, out=self.minv_fwd)
         self.radius = r
 
-    def _solve(self, A, minv, rhs, x):
-        self.pcg.solve(self.row_ptr, self.col_idx, A, minv, rhs, x, dpn_hint=1,
-                       rtol=self.RTOL, maxiter=self.MAXITER, use_x0=True,
-                       check_every=8)
+    def _mass_times(self, v, out):
+        if self.grid is not None:
+            return self.gop_M.apply(v, out=out)
+        return dev.spmv(self.row_ptr, self.col_idx, self.M, v, 1, out=out)
+
+    def _solve(self, enforced: bool, rhs, x):
+        minv = self.minv_fwd if enforced else self.minv
+        if self.grid is not None:
+            self.gop_A.set_scale(None, dmask=self.flags_fixed if enforced else self.flags_free)
+            self.pcg.solve_grid(self.gop_A, minv, rhs, x, rtol=self.RTOL, maxiter=self.MAXITER,
+                                use_x0=True, check_every=8)
+        else:
+            A = self.A_fwd if enforced else self.A
+            self.pcg.solve(self.row_ptr, self.col_idx, A, minv, rhs, x, dpn_hint=1,
+                           rtol=self.RTOL, maxiter=self.MAXITER, use_x0=True,
+                           check_every=8)
         self.solve_iters.append(self.pcg.last_iters)
         if not self.pcg.last_converged:
             raise RuntimeError(
@@ -107,18 +155,18 @@ class _HelmholtzDevice:
 
     def forward(self, rho, out=None):
         self.dm.e2n(self.w, rho, self.design_u8, 1.0, self.wsum, out=self.node)
-        dev.spmv(self.row_ptr, self.col_idx, self.M, self.node, 1, out=self.b)
+        self._mass_times(self.node, self.b)
         if self.has_fixed:
             dev.enforce_rhs(self.b, self.c, self.fixed_u8, self.x_fixed, out=self.rhs)
-            x = self._solve(self.A_fwd, self.minv_fwd, self.rhs, self.x_fwd)
+            x = self._solve(True, self.rhs, self.x_fwd)
         else:
-            x = self._solve(self.A, self.minv, self.b, self.x_fwd)
+            x = self._solve(False, self.b, self.x_fwd)
         return self.dm.n2e_mean(x, clamp_max0=False, out=out)
 
     def gradient(self, v, out=None):
         self.dm.e2n(self.w, v, self.design_u8, 0.0, self.wsum, out=self.node)
-        dev.spmv(self.row_ptr, self.col_idx, self.M, self.node, 1, out=self.b)
-        x = self._solve(self.A, self.minv, self.b, self.x_adj)
+        self._mass_times(self.node, self.b)
+        x = self._solve(False, self.b, self.x_adj)
         return self.dm.n2e_mean(x, clamp_max0=True, out=out)
 
 

@@ -92,3 +92,30 @@ def test_matrix_free_solve_matches_oracle(gpu, monkeypatch):
         uj = eng.solve(dev.to_dev(f), 1, 1e-10, None).cpu().numpy()
         assert np.max(np.abs(uj - u_ref)) <= 1e-7 * np.max(np.abs(u_ref))
     assert abs(its["mf"] - its["asm"]) <= 2
+
+
+def test_helmholtz_filter_matrix_free_matches_assembled(gpu, monkeypatch):
+    """Scalar grid operator inside the Helmholtz filter (forward with fixed
+    non-design nodes, adjoint without) against the assembled CSR path."""
+    sktopt, dev = gpu
+    from sktopt.filters.helmholtz_filter_nodal import HelmholtzFilterNodal
+    mesh = sktopt.mesh.toy_problem.create_box_hex(2.8, 2.0, 1.6, 0.2)
+    from sktopt._fem import Basis, ElementHex1
+    basis = Basis(mesh, ElementHex1())
+    vol = np.full(mesh.nelements, 0.2 ** 3)
+    rng = np.random.default_rng(5)
+    design = np.ones(mesh.nelements, dtype=bool)
+    design[rng.choice(mesh.nelements, 40, replace=False)] = False
+    rho = rng.uniform(0.05, 1.0, mesh.nelements)
+    v = -rng.uniform(0.0, 1.0, mesh.nelements)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SKTOPT_B200_MATFREE", flag)
+        f = HelmholtzFilterNodal.from_defaults(mesh, vol, radius=0.35, design_mask=design)
+        st = f._device()
+        assert (st.grid is not None) == (flag == "1")
+        out[flag] = (f.forward(rho), f.gradient(v), list(st.solve_iters))
+    for k in (0, 1):
+        a, b = out["1"][k], out["0"][k]
+        assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b)))
+    assert out["1"][2] == out["0"][2]          # same PCG iteration counts
