@@ -44,6 +44,7 @@ def main():
     err_c = abs(c[0] - c1) / abs(c1)
     # the sharded matrix rows equal the corresponding rows of the full matrix
     eng = fem.engine
+    eng.assemble(enforce=True)     # (a matrix-free engine never assembled them)
     lo = int(eng.col_idx.numel())
     full_vals = eng1.vals.cpu().numpy()
     rp_full = eng1.row_ptr.cpu().numpy()
