@@ -52,6 +52,8 @@ struct sktb_gridop {
   int64_t n_nodes = 0;
   bool fields_set = false;
   bool direct = false;  // untiled kernel (DPN = 3 only; default there)
+  bool split = false;   // two warps per node (SKTB_GRIDOP_SPLIT=1)
+  bool shfl = true;     // y-neighbours by warp shuffle (SKTB_GRIDOP_SHFL=0: all from L1)
   size_t smem = 0;
 };
 
@@ -234,11 +236,21 @@ __global__ void __launch_bounds__(kBlock, 2)
 // interior in x and z and no node of its neighbourhood carries a Dirichlet dof
 // (a y-boundary neighbour wraps into the adjacent grid line, harmless: its
 // elements have E = 0).
+#ifdef SKTB_KE_SMEM
+#define KE_SRC(k) ske[k]
+#define KE_ARG , const double *__restrict__ ske
+#define KE_PASS , ske
+#else
+#define KE_SRC(k) P.ke[k]
+#define KE_ARG
+#define KE_PASS
+#endif
+
 template <bool FAST>
 __device__ __forceinline__ void hexgrid_node_rows(const GridParams<3> &P, int64_t n,
                                                   int ix, int iy, int iz, unsigned dm,
                                                   const double *__restrict__ x,
-                                                  double (&out)[3]) {
+                                                  double (&out)[3] KE_ARG) {
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
   double E[8];
@@ -294,9 +306,9 @@ __device__ __forceinline__ void hexgrid_node_rows(const GridParams<3> &P, int64_
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int k = (3 * ca + i) * 24 + 3 * cb;
-            pe[o][i] = fma(P.ke[k], u0, pe[o][i]);
-            pe[o][i] = fma(P.ke[k + 1], u1, pe[o][i]);
-            pe[o][i] = fma(P.ke[k + 2], u2, pe[o][i]);
+            pe[o][i] = fma(KE_SRC(k), u0, pe[o][i]);
+            pe[o][i] = fma(KE_SRC(k + 1), u1, pe[o][i]);
+            pe[o][i] = fma(KE_SRC(k + 2), u2, pe[o][i]);
           }
         }
       }
@@ -324,6 +336,11 @@ __global__ void __launch_bounds__(kBlock, 2)
                          double *partials, unsigned int *ticket, double *dot_out,
                          const PcgScalars *S) {
   if (S && S->rr <= S->tol2) return;
+#ifdef SKTB_KE_SMEM
+  __shared__ double ske[576];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) ske[i] = P.ke[i];
+  __syncthreads();
+#endif
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   double dot = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -337,14 +354,276 @@ __global__ void __launch_bounds__(kBlock, 2)
     const unsigned dm = P.dmask[n];
     double out[3];
     if (ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1 && !(dm & 8u))
-      hexgrid_node_rows<true>(P, n, ix, iy, iz, dm, x, out);
+      hexgrid_node_rows<true>(P, n, ix, iy, iz, dm, x, out KE_PASS);
     else
-      hexgrid_node_rows<false>(P, n, ix, iy, iz, dm, x, out);
+      hexgrid_node_rows<false>(P, n, ix, iy, iz, dm, x, out KE_PASS);
     y[3 * r] = out[0];
     y[3 * r + 1] = out[1];
     y[3 * r + 2] = out[2];
     if (DOT)
       dot += out[0] * dotv[3 * r] + out[1] * dotv[3 * r + 1] + out[2] * dotv[3 * r + 2];
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+// ------------------- shuffle kernel (DPN = 3): y-neighbours from the warp --
+// Same per-node work as the untiled kernel, but of the 27 neighbours only the 9
+// with dy = 0 are loaded; dy = -1 / +1 come from the adjacent lanes by shuffle
+// (consecutive lanes own consecutive nodes of a grid line), the two edge lanes
+// fetch theirs.  The interleaved (x, y, z) layout makes every warp load touch
+// 6-7 cache lines, so this cuts the L1 look-ups per node row from ~530 to ~230.
+// A lane whose neighbour lane sits on another grid line (iy = 0 or npy-1) gets
+// a meaningless value there; it only feeds elements with E = 0.
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock, 2)
+    hexgrid_apply_shfl_kernel(const __grid_constant__ GridParams<3> P, int64_t node0,
+                              int64_t n_loc, const double *__restrict__ x,
+                              double *__restrict__ y, const double *__restrict__ dotv,
+                              double *partials, unsigned int *ticket, double *dot_out,
+                              const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int lane = threadIdx.x & 31;
+  double dot = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_pad = (n_loc + 31) / 32 * 32;  // whole warps run every trip (shuffles)
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+    const bool live = r < n_loc;
+    // a dead tail lane still serves its left neighbour's dy = +1 shuffle: it
+    // takes the node that follows in the grid (not owned by this rank); past the
+    // end of the grid it mirrors the last node, whose dy = +1 feeds nothing
+    const int64_t n = node0 + r;
+    const int64_t n_total = (int64_t)npx * npy * npz;
+    const int64_t nc = n < n_total ? n : n_total - 1;
+    const int iy = (int)(nc % npy);
+    const int64_t t = nc / npy;
+    const int ix = (int)(t % npx);
+    const int iz = (int)(t / npx);
+    const unsigned dm = P.dmask[nc];
+    double E[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1), ez = iz - 1 + (o >> 2);
+      const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+      E[o] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+    }
+    double pe[8][3];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = 0.0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
+        const int64_t mc = (int64_t)npy * (kx + (int64_t)npx * kz) + iy;
+        const double *cp = x + 3 * mc;
+        double u[3][3];  // [dy + 1][component]
+#pragma unroll
+        for (int j = 0; j < 3; ++j) u[1][j] = __ldg(cp + j);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          u[0][j] = __shfl_up_sync(0xffffffffu, u[1][j], 1);
+          u[2][j] = __shfl_down_sync(0xffffffffu, u[1][j], 1);
+        }
+        if (lane == 0 && iy > 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) u[0][j] = __ldg(cp - 3 + j);
+        }
+        if (lane == 31 && iy < npy - 1) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) u[2][j] = __ldg(cp + 3 + j);
+        }
+        if (dm & 8u) {  // a fixed dof somewhere around: mask the inputs
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int ky = iy + dy;
+            if (ky < 0 || ky >= npy) continue;
+            const unsigned mb = P.dmask[mc + dy];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if ((mb >> j) & 1u) u[dy + 1][j] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+            const int cb = bx + 2 * by + 4 * bz;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int k = (3 * ca + i) * 24 + 3 * cb;
+              pe[o][i] = fma(P.ke[k], u[dy + 1][0], pe[o][i]);
+              pe[o][i] = fma(P.ke[k + 1], u[dy + 1][1], pe[o][i]);
+              pe[o][i] = fma(P.ke[k + 2], u[dy + 1][2], pe[o][i]);
+            }
+          }
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a = fma(E[o], pe[o][i], a);
+        if ((dm >> i) & 1u) a = x[3 * n + i];
+        y[3 * r + i] = a;
+        if (DOT) dot = fma(a, dotv[3 * r + i], dot);
+      }
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+// ------------------------------ split kernel (DPN = 3): two warps per node --
+// The untiled kernel holds 24 accumulators + 8 moduli per thread (128
+// registers, 16 warps/SM) and is latency bound.  Here a warp PAIR owns 32
+// nodes: the even warp takes each node's four lower elements (oz = 0, neighbour
+// planes dz = -1, 0), the odd warp the four upper ones (oz = 1, planes 0, +1):
+// 12 accumulators per thread, twice the resident warps.  The odd warp hands its
+// three partial sums over through shared memory (named barrier per pair), the
+// even warp adds, applies the Dirichlet pass-through and stores.  Fixed
+// summation order: deterministic.
+template <int H, bool FAST>
+__device__ __forceinline__ void hexgrid_node_half(const GridParams<3> &P, int64_t n,
+                                                  int ix, int iy, int iz, unsigned dm,
+                                                  const double *__restrict__ x,
+                                                  double (&out)[3]) {
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  double E[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ex = ix - 1 + (q & 1), ey = iy - 1 + (q >> 1), ez = iz - 1 + H;
+    const bool ok = FAST ? (ey >= 0 && ey < ny)
+                         : (ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz);
+    E[q] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+  }
+  double pe[4][3];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pe[q][0] = pe[q][1] = pe[q][2] = 0.0;
+  const double *xc = x + 3 * n;
+  const int64_t sx = 3 * (int64_t)npy, sz = 3 * (int64_t)npy * npx;
+#pragma unroll
+  for (int dzi = 0; dzi < 2; ++dzi) {
+    const int dz = H - 1 + dzi;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const double *line;
+      if (FAST) {
+        line = xc + dx * sx + dz * sz;
+      } else {
+        const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
+        line = x + 3 * ((int64_t)npy * (kx + (int64_t)npx * kz));
+      }
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        double u0, u1, u2;
+        if (FAST) {
+          u0 = __ldg(line + 3 * dy);
+          u1 = __ldg(line + 3 * dy + 1);
+          u2 = __ldg(line + 3 * dy + 2);
+        } else {
+          const int ky = clampi(iy + dy, npy - 1);
+          u0 = __ldg(line + 3 * ky);
+          u1 = __ldg(line + 3 * ky + 1);
+          u2 = __ldg(line + 3 * ky + 2);
+          if (dm & 8u) {
+            const unsigned mb = P.dmask[(line - x) / 3 + ky];
+            if (mb & 1u) u0 = 0.0;
+            if (mb & 2u) u1 = 0.0;
+            if (mb & 4u) u2 = 0.0;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ox = q & 1, oy = q >> 1, oz = H;
+          const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+          if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+          const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+          const int cb = bx + 2 * by + 4 * bz;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = (3 * ca + i) * 24 + 3 * cb;
+            pe[q][i] = fma(P.ke[k], u0, pe[q][i]);
+            pe[q][i] = fma(P.ke[k + 1], u1, pe[q][i]);
+            pe[q][i] = fma(P.ke[k + 2], u2, pe[q][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a = fma(E[q], pe[q][i], a);
+    out[i] = a;
+  }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock, 4)
+    hexgrid_apply_split_kernel(const __grid_constant__ GridParams<3> P, int64_t node0,
+                               int64_t n_loc, const double *__restrict__ x,
+                               double *__restrict__ y, const double *__restrict__ dotv,
+                               double *partials, unsigned int *ticket, double *dot_out,
+                               const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  __shared__ double sp[kBlock / 64][3][32];
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pair = w >> 1, h = w & 1;
+  double dot = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * (kBlock / 2);
+  const int64_t n_pad = (n_loc + 31) / 32 * 32;  // both warps of a pair run the same trips
+  for (int64_t r = ((int64_t)blockIdx.x * (kBlock / 64) + pair) * 32 + lane; r < n_pad;
+       r += stride) {
+    const bool live = r < n_loc;
+    const int64_t n = node0 + (live ? r : n_loc - 1);
+    const int iy = (int)(n % npy);
+    const int64_t t = n / npy;
+    const int ix = (int)(t % npx);
+    const int iz = (int)(t / npx);
+    const unsigned dm = P.dmask[n];
+    const bool fast = ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1 && !(dm & 8u);
+    double out[3];
+    if (h == 0) {
+      if (fast)
+        hexgrid_node_half<0, true>(P, n, ix, iy, iz, dm, x, out);
+      else
+        hexgrid_node_half<0, false>(P, n, ix, iy, iz, dm, x, out);
+    } else {
+      if (fast)
+        hexgrid_node_half<1, true>(P, n, ix, iy, iz, dm, x, out);
+      else
+        hexgrid_node_half<1, false>(P, n, ix, iy, iz, dm, x, out);
+      sp[pair][0][lane] = out[0];
+      sp[pair][1][lane] = out[1];
+      sp[pair][2][lane] = out[2];
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+    if (h == 0 && live) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double v = out[i] + sp[pair][i][lane];
+        if ((dm >> i) & 1u) v = x[3 * n + i];
+        y[3 * r + i] = v;
+        if (DOT) dot = fma(v, dotv[3 * r + i], dot);
+      }
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
   }
   if (DOT) {
     double v[1] = {dot};
@@ -418,6 +697,28 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
     return launch_tiled<1>(op, op->P1, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
   if (!op->direct)
     return launch_tiled<3>(op, op->P3, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
+  if (op->shfl) {
+    const int g = grid_for(n_nodes, kBlock, 16);
+    if (dotv)
+      hexgrid_apply_shfl_kernel<true><<<g, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+    else
+      hexgrid_apply_shfl_kernel<false><<<g, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+    SKTB_KERNEL_OK();
+    return 0;
+  }
+  if (op->split) {
+    const int sgrid = grid_for(n_nodes, kBlock / 2, 16);
+    if (dotv)
+      hexgrid_apply_split_kernel<true><<<sgrid, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+    else
+      hexgrid_apply_split_kernel<false><<<sgrid, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+    SKTB_KERNEL_OK();
+    return 0;
+  }
   const int grid = grid_for(n_nodes, kBlock, 16);
   if (dotv)
     hexgrid_apply_kernel<true><<<grid, kBlock, 0, st>>>(
@@ -475,6 +776,10 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   // shared-memory variant, which is the only one for the scalar operator
   const char *env = getenv("SKTB_GRIDOP_TILED");
   op->direct = dpn == 3 && !(env && env[0] == '1');
+  const char *env2 = getenv("SKTB_GRIDOP_SPLIT");
+  op->split = env2 && env2[0] == '1';
+  const char *env3 = getenv("SKTB_GRIDOP_SHFL");
+  op->shfl = !(env3 && env3[0] == '0');
   auto fill = [&](auto &P, int nke) {
     for (int i = 0; i < nke; ++i) P.ke[i] = ke_cc_h[i];
     P.npx = np_h[0];
