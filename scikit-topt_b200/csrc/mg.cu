@@ -185,7 +185,12 @@ extern "C" int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_n
        i < (n); i += _st)
 
 // ------------------------------------------------ Galerkin element matrices --
-// out[E] = sum_c Q_c^T K_child Q_c ; block per coarse element, thread per entry
+// out[E] = sum_c Q_c^T K_child Q_c (Q_c = trilinear weights x I3).  One CTA per
+// coarse element, three output entries per thread.  Per child: the 24x24 child
+// matrix is staged in shared memory (coalesced), T = K_child (Q x I3) is formed
+// there (8 FMAs per entry), then out += (Q x I3)^T T (8 FMAs per entry): two
+// small dense products from shared memory instead of a sparse triple sum over
+// strided global loads.
 __global__ void __launch_bounds__(192)
     elem_restrict_kernel(int64_t n_coarse, const int32_t *__restrict__ child,
                          const uint8_t *__restrict__ ptype,
@@ -198,42 +203,58 @@ __global__ void __launch_bounds__(192)
   const int64_t E = blockIdx.x;
   const int type = ptype[E];
   __shared__ int32_t ch[8];
-  __shared__ double Q[8][64];
+  __shared__ double Q[8][64];     // Q[c][a * 8 + A]: weight of parent vertex A in child vertex a
+  __shared__ double Kc[24][25];   // padded: column reads of the second product
+  __shared__ double T[24][25];
   if (threadIdx.x < 8) ch[threadIdx.x] = child[(int64_t)threadIdx.x * n_coarse + E];
   for (int k = threadIdx.x; k < 512; k += blockDim.x)
     Q[k >> 6][k & 63] = Qtab[(type * 8 + (k >> 6)) * 64 + (k & 63)];
+  double acc[3] = {0.0, 0.0, 0.0};
   __syncthreads();
-  for (int ent = threadIdx.x; ent < 576; ent += blockDim.x) {
-    const int r = ent / 24, c = ent - 24 * r;
-    const int A = r / 3, i = r - 3 * A, B = c / 3, j = c - 3 * B;
-    double acc = 0.0;
-    for (int cc = 0; cc < 8; ++cc) {
-      const int32_t ce = ch[cc];
-      if (ce < 0) continue;
-      const double *Kc;
-      double sc = 1.0;
-      if (fine_ke) {
-        Kc = fine_ke + (int64_t)ce * 576;
-      } else {
-        Kc = unit + (int64_t)(cls ? cls[ce] : 0) * 576;
-        sc = scale[ce];
-      }
-      double part = 0.0;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const double wa = Q[cc][a * 8 + A];
-        if (wa == 0.0) continue;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const double wb = Q[cc][b * 8 + B];
-          if (wb == 0.0) continue;
-          part += wa * wb * __ldg(&Kc[(3 * a + i) * 24 + 3 * b + j]);
-        }
-      }
-      acc += sc * part;
+  for (int cc = 0; cc < 8; ++cc) {
+    const int32_t ce = ch[cc];
+    if (ce < 0) continue;  // uniform across the CTA
+    const double *src;
+    double sc = 1.0;
+    if (fine_ke) {
+      src = fine_ke + (int64_t)ce * 576;
+    } else {
+      src = unit + (int64_t)(cls ? cls[ce] : 0) * 576;
+      sc = scale[ce];
     }
-    out[E * 576 + ent] = acc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ent = threadIdx.x + 192 * k;
+      Kc[ent / 24][ent % 24] = sc * __ldg(&src[ent]);
+    }
+    __syncthreads();
+    // T[r][3B + j] = sum_b Kc[r][3b + j] Q[b][B]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ent = threadIdx.x + 192 * k;
+      const int r = ent / 24, c = ent - 24 * r;
+      const int B = c / 3, j = c - 3 * B;
+      double t = 0.0;
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) t = fma(Kc[r][3 * bb + j], Q[cc][bb * 8 + B], t);
+      T[r][c] = t;
+    }
+    __syncthreads();
+    // out[3A + i][c] += sum_a Q[a][A] T[3a + i][c]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int ent = threadIdx.x + 192 * k;
+      const int r = ent / 24, c = ent - 24 * r;
+      const int A = r / 3, i = r - 3 * A;
+      double t = acc[k];
+#pragma unroll
+      for (int aa = 0; aa < 8; ++aa) t = fma(Q[cc][aa * 8 + A], T[3 * aa + i][c], t);
+      acc[k] = t;
+    }
+    __syncthreads();
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[E * 576 + threadIdx.x + 192 * k] = acc[k];
 }
 
 // Level 0 -> 1 fast path: children are scale[e] * Ke0[class], so the Galerkin
