@@ -217,6 +217,9 @@ int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg, const sktb_gridop *op,
 int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
                              const double *inv_diag, int iters, double *out_h,
                              void *stream);
+/* fp32_level0 != 0: the two products with a matrix-free level-0 operator inside
+ * the V-cycle are formed in single precision (vectors stay fp64)              */
+int sktb_mg_set_precision(sktb_mg *m, int fp32_level0);
 /* exact coarsest-level solve: dense Gauss-Jordan inverse of the last level's
  * operator (<= 160 dofs; larger levels keep damped-Jacobi sweeps).  Call after
  * sktb_mg_set_level(last, ...) whenever its values changed.                    */

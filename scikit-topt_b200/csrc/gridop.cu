@@ -37,6 +37,7 @@ using namespace sktb;
 template <int DPN>
 struct GridParams {
   double ke[64 * DPN * DPN];
+  float kef[64 * DPN * DPN];  // same, rounded: single-precision products of the V-cycle
   int32_t npx, npy, npz;
   int32_t ty, tx, tz;     // tile shape (nodes)
   int32_t nty, ntx, ntz;  // tiles per axis
@@ -377,13 +378,30 @@ __global__ void __launch_bounds__(kBlock, 2)
 // 6-7 cache lines, so this cuts the L1 look-ups per node row from ~530 to ~230.
 // A lane whose neighbour lane sits on another grid line (iy = 0 or npy-1) gets
 // a meaningless value there; it only feeds elements with E = 0.
-template <bool DOT>
+//
+// T = float: the products are formed in single precision (vectors stay fp64 in
+// memory); used for the two level-0 products inside the multigrid V-cycle, where
+// the result only steers a preconditioner.  MODE 1 fuses the damped-Jacobi
+// update: y = x + omega * dinv * (b - A x).
+template <typename T>
+__device__ __forceinline__ T grid_coef(const GridParams<3> &P, int k);
+template <>
+__device__ __forceinline__ double grid_coef<double>(const GridParams<3> &P, int k) {
+  return P.ke[k];
+}
+template <>
+__device__ __forceinline__ float grid_coef<float>(const GridParams<3> &P, int k) {
+  return P.kef[k];
+}
+
+template <typename T, int MODE, bool DOT>
 __global__ void __launch_bounds__(kBlock, 2)
     hexgrid_apply_shfl_kernel(const __grid_constant__ GridParams<3> P, int64_t node0,
                               int64_t n_loc, const double *__restrict__ x,
                               double *__restrict__ y, const double *__restrict__ dotv,
                               double *partials, unsigned int *ticket, double *dot_out,
-                              const PcgScalars *S) {
+                              const PcgScalars *S, const double *__restrict__ sm_b,
+                              const double *__restrict__ sm_dinv, double sm_omega) {
   if (S && S->rr <= S->tol2) return;
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
@@ -404,16 +422,16 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int ix = (int)(t % npx);
     const int iz = (int)(t / npx);
     const unsigned dm = P.dmask[nc];
-    double E[8];
+    T E[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1), ez = iz - 1 + (o >> 2);
       const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
-      E[o] = ok ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 0.0;
+      E[o] = ok ? (T)__ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : (T)0;
     }
-    double pe[8][3];
+    T pe[8][3];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = 0.0;
+    for (int o = 0; o < 8; ++o) pe[o][0] = pe[o][1] = pe[o][2] = (T)0;
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
@@ -421,9 +439,9 @@ __global__ void __launch_bounds__(kBlock, 2)
         const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
         const int64_t mc = (int64_t)npy * (kx + (int64_t)npx * kz) + iy;
         const double *cp = x + 3 * mc;
-        double u[3][3];  // [dy + 1][component]
+        T u[3][3];  // [dy + 1][component]
 #pragma unroll
-        for (int j = 0; j < 3; ++j) u[1][j] = __ldg(cp + j);
+        for (int j = 0; j < 3; ++j) u[1][j] = (T)__ldg(cp + j);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           u[0][j] = __shfl_up_sync(0xffffffffu, u[1][j], 1);
@@ -431,11 +449,11 @@ __global__ void __launch_bounds__(kBlock, 2)
         }
         if (lane == 0 && iy > 0) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) u[0][j] = __ldg(cp - 3 + j);
+          for (int j = 0; j < 3; ++j) u[0][j] = (T)__ldg(cp - 3 + j);
         }
         if (lane == 31 && iy < npy - 1) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) u[2][j] = __ldg(cp + 3 + j);
+          for (int j = 0; j < 3; ++j) u[2][j] = (T)__ldg(cp + 3 + j);
         }
         if (dm & 8u) {  // a fixed dof somewhere around: mask the inputs
 #pragma unroll
@@ -445,7 +463,7 @@ __global__ void __launch_bounds__(kBlock, 2)
             const unsigned mb = P.dmask[mc + dy];
 #pragma unroll
             for (int j = 0; j < 3; ++j)
-              if ((mb >> j) & 1u) u[dy + 1][j] = 0.0;
+              if ((mb >> j) & 1u) u[dy + 1][j] = (T)0;
           }
         }
 #pragma unroll
@@ -460,9 +478,9 @@ __global__ void __launch_bounds__(kBlock, 2)
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               const int k = (3 * ca + i) * 24 + 3 * cb;
-              pe[o][i] = fma(P.ke[k], u[dy + 1][0], pe[o][i]);
-              pe[o][i] = fma(P.ke[k + 1], u[dy + 1][1], pe[o][i]);
-              pe[o][i] = fma(P.ke[k + 2], u[dy + 1][2], pe[o][i]);
+              pe[o][i] = fma(grid_coef<T>(P, k), u[dy + 1][0], pe[o][i]);
+              pe[o][i] = fma(grid_coef<T>(P, k + 1), u[dy + 1][1], pe[o][i]);
+              pe[o][i] = fma(grid_coef<T>(P, k + 2), u[dy + 1][2], pe[o][i]);
             }
           }
         }
@@ -471,10 +489,13 @@ __global__ void __launch_bounds__(kBlock, 2)
     if (live) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        double a = 0.0;
+        T acc = (T)0;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) a = fma(E[o], pe[o][i], a);
+        for (int o = 0; o < 8; ++o) acc = fma(E[o], pe[o][i], acc);
+        double a = (double)acc;
         if ((dm >> i) & 1u) a = x[3 * n + i];
+        if (MODE == 1)
+          a = x[3 * n + i] + sm_omega * sm_dinv[3 * r + i] * (sm_b[3 * r + i] - a);
         y[3 * r + i] = a;
         if (DOT) dot = fma(a, dotv[3 * r + i], dot);
       }
@@ -700,11 +721,13 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
   if (op->shfl) {
     const int g = grid_for(n_nodes, kBlock, 16);
     if (dotv)
-      hexgrid_apply_shfl_kernel<true><<<g, kBlock, 0, st>>>(
-          op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+      hexgrid_apply_shfl_kernel<double, 0, true><<<g, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S, nullptr,
+          nullptr, 0.0);
     else
-      hexgrid_apply_shfl_kernel<false><<<g, kBlock, 0, st>>>(
-          op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+      hexgrid_apply_shfl_kernel<double, 0, false><<<g, kBlock, 0, st>>>(
+          op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S, nullptr,
+          nullptr, 0.0);
     SKTB_KERNEL_OK();
     return 0;
   }
@@ -731,6 +754,28 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
 }
 
 int gridop_dpn(const sktb_gridop *op) { return op->dpn; }
+
+// products of the multigrid V-cycle: optional single precision, optional fused
+// damped-Jacobi update y = x + omega dinv (b - A x).  Returns -1 when this
+// operator has no such kernel (the caller then composes it from plain products).
+int launch_hexgrid_apply_ex(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                            const double *x, double *y, bool fp32, const double *b,
+                            const double *dinv, double omega, cudaStream_t st) {
+  if (op->dpn != 3 || !op->shfl || !op->direct) return -1;
+  const int g = grid_for(n_nodes, kBlock, 16);
+#define SKTB_EX(T, MODE)                                                               \
+  hexgrid_apply_shfl_kernel<T, MODE, false><<<g, kBlock, 0, st>>>(                     \
+      op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, nullptr, b, dinv, \
+      omega)
+  if (b) {
+    if (fp32) SKTB_EX(float, 1); else SKTB_EX(double, 1);
+  } else {
+    if (fp32) SKTB_EX(float, 0); else SKTB_EX(double, 0);
+  }
+#undef SKTB_EX
+  SKTB_KERNEL_OK();
+  return 0;
+}
 
 // tile shape: as many of the 256 threads busy as possible, small halo
 template <int DPN>
@@ -782,6 +827,7 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   op->shfl = !(env3 && env3[0] == '0');
   auto fill = [&](auto &P, int nke) {
     for (int i = 0; i < nke; ++i) P.ke[i] = ke_cc_h[i];
+    for (int i = 0; i < nke; ++i) P.kef[i] = (float)ke_cc_h[i];
     P.npx = np_h[0];
     P.npy = np_h[1];
     P.npz = np_h[2];

@@ -50,6 +50,10 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
                          sktb::ReduceScratch *rs, double *dot_out,
                          const PcgScalars *S, cudaStream_t st);
 
+int launch_hexgrid_apply_ex(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
+                            const double *x, double *y, bool fp32, const double *b,
+                            const double *dinv, double omega, cudaStream_t st);
+
 // multigrid preconditioner z = M^-1 r (mg.cu)
 struct sktb_mg;
 struct sktb_pcg;

@@ -46,6 +46,7 @@ struct sktb_mg {
   std::vector<MgLevel> lv;
   double omega = 0.5;
   int nu_coarse = 20;
+  bool fp32_level0 = false;  // single-precision products on a matrix-free level 0
 };
 
 extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
@@ -73,6 +74,12 @@ extern "C" int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse) {
   SKTB_REQUIRE(m && omega > 0.0 && omega < 2.0 && nu_coarse >= 0, "bad argument");
   m->omega = omega;
   m->nu_coarse = nu_coarse;
+  return 0;
+}
+
+extern "C" int sktb_mg_set_precision(sktb_mg *m, int fp32_level0) {
+  SKTB_REQUIRE(m, "null argument");
+  m->fp32_level0 = fp32_level0 != 0;
   return 0;
 }
 
@@ -260,27 +267,48 @@ __global__ void __launch_bounds__(192)
 // Level 0 -> 1 fast path: children are scale[e] * Ke0[class], so the Galerkin
 // element matrix is a linear combination of precomputed tables
 //   T[(cls * 8 + type) * 8 + c] = Q_c^T Ke0[cls] Q_c   (576 doubles each)
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(192)
     elem_combine_kernel(int64_t n_coarse, const int32_t *__restrict__ child,
                         const uint8_t *__restrict__ ptype,
                         const double *__restrict__ T,
                         const int32_t *__restrict__ cls,
                         const double *__restrict__ scale,
                         double *__restrict__ out) {
-  const int64_t total = n_coarse * 576;
-  GS(idx, total) {
-    const int64_t E = idx / 576;
-    const int ent = (int)(idx - E * 576);
-    const int type = ptype[E];
-    double acc = 0.0;
+  // persistent CTAs, one coarse element per trip, three entries per thread; the
+  // tables of the common case (class 0, full 2x2x2 parent) live in registers
+  double t0[8][3];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t0[c][k] = __ldg(&T[(int64_t)c * 576 + threadIdx.x + 192 * k]);
+  __shared__ double s_sc[2][8];
+  __shared__ int s_tab[2][8];  // table index (cls * 8 + type) * 8 + c, -1 = no child
+  int buf = 0;
+  for (int64_t E = blockIdx.x; E < n_coarse; E += gridDim.x, buf ^= 1) {
+    if (threadIdx.x < 8) {
+      const int c = threadIdx.x;
+      const int32_t ce = child[(int64_t)c * n_coarse + E];
+      s_sc[buf][c] = ce >= 0 ? scale[ce] : 0.0;
+      s_tab[buf][c] = ce >= 0 ? ((cls ? cls[ce] : 0) * 8 + ptype[E]) * 8 + c : -1;
+    }
+    __syncthreads();  // (double-buffered: one barrier per trip)
+    double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const int32_t ce = child[(int64_t)c * n_coarse + E];
-      if (ce < 0) continue;
-      const int k = cls ? cls[ce] : 0;
-      acc += scale[ce] * __ldg(&T[((int64_t)(k * 8 + type) * 8 + c) * 576 + ent]);
+      const int tab = s_tab[buf][c];
+      if (tab < 0) continue;
+      const double sc = s_sc[buf][c];
+      if (tab == c) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = fma(sc, t0[c][k], acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          acc[k] = fma(sc, __ldg(&T[(int64_t)tab * 576 + threadIdx.x + 192 * k]), acc[k]);
+      }
     }
-    out[idx] = acc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[E * 576 + threadIdx.x + 192 * k] = acc[k];
   }
 }
 
@@ -289,7 +317,8 @@ extern "C" int sktb_elem_combine(int64_t n_coarse, const int32_t *child,
                                  const int32_t *cls, const double *scale,
                                  double *out, void *stream) {
   SKTB_REQUIRE(child && ptype && T && scale && out && n_coarse > 0, "null argument");
-  elem_combine_kernel<<<grid_for(n_coarse * 576, kBlock, 16), kBlock, 0,
+  const int64_t cap = (int64_t)kNumSM * 10;
+  elem_combine_kernel<<<(unsigned)(n_coarse < cap ? n_coarse : cap), 192, 0,
                         (cudaStream_t)stream>>>(n_coarse, child, ptype, T, cls,
                                                 scale, out);
   SKTB_KERNEL_OK();
@@ -543,10 +572,17 @@ extern "C" int sktb_mg_factor_coarsest(sktb_mg *m, void *stream) {
   return 0;
 }
 
-static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st) {
-  if (l.gop)
+static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st,
+                      bool fp32 = false) {
+  if (l.gop) {
+    if (fp32) {
+      int rc = launch_hexgrid_apply_ex(l.gop, l.node0, l.n_nodes, x, y, true, nullptr,
+                                       nullptr, 0.0, st);
+      if (rc != -1) return rc;
+    }
     return launch_hexgrid_apply(l.gop, l.node0, l.n_nodes, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
+  }
   int rc = launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
                                 l.node_col, l.vals, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
@@ -595,7 +631,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       }
     } else {
       if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
-      if (level_spmv(l, xfull, l.tmp, st)) return 1;
+      if (level_spmv(l, xfull, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
       MgLevel &c = m->lv[k + 1];
       const int64_t lo = (k == 0) ? f_lo : 0;
       const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
@@ -608,6 +644,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     }
   }
   // upward sweep
+  bool z_done = false;
   for (int k = L - 2; k >= 0; --k) {
     MgLevel &l = m->lv[k];
     MgLevel &c = m->lv[k + 1];
@@ -623,12 +660,23 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
         l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, xfull, lo, hi);
     SKTB_COUNT(1);
     if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
+    if (k == 0 && l.gop) {
+      // fused post-smoothing straight into z: z = x + om D^-1 (r - A x)
+      int rc = launch_hexgrid_apply_ex(l.gop, l.node0, l.n_nodes, xfull, z, m->fp32_level0,
+                                       b, l.inv_diag, om, st);
+      if (rc == 0) {
+        z_done = true;
+        continue;
+      }
+      if (rc != -1) return rc;
+    }
     if (level_spmv(l, xfull, l.tmp, st)) return 1;
     mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
     SKTB_COUNT(1);
   }
-  SKTB_CUDA_OK(cudaMemcpyAsync(z, l0.x + 3 * l0.node0, sizeof(double) * 3 * l0.n_nodes,
-                               cudaMemcpyDeviceToDevice, st));
+  if (!z_done)
+    SKTB_CUDA_OK(cudaMemcpyAsync(z, l0.x + 3 * l0.node0, sizeof(double) * 3 * l0.n_nodes,
+                                 cudaMemcpyDeviceToDevice, st));
   SKTB_KERNEL_CHECK();
   return 0;
 }

@@ -162,6 +162,10 @@ class Multigrid:
         _lib.check(self.lib.sktb_mg_create(C.byref(h), self.n_levels, torch.cuda.current_device()))
         self.handle = h
         _lib.check(self.lib.sktb_mg_set_params(h, float(omega), int(nu_coarse)))
+        # level-0 products of the V-cycle in single precision (matrix-free level 0
+        # only; SKTOPT_B200_MG_FP32=0 keeps them in fp64)
+        self.fp32 = os.environ.get("SKTOPT_B200_MG_FP32", "1") != "0"
+        _lib.check(self.lib.sktb_mg_set_precision(h, int(self.fp32)))
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
