@@ -407,9 +407,14 @@ __global__ void __launch_bounds__(kBlock, 2)
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
   const int lane = threadIdx.x & 31;
   double dot = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_pad = (n_loc + 31) / 32 * 32;  // whole warps run every trip (shuffles)
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+  // blocked assignment: a CTA walks a CONTIGUOUS run of grid lines, so the
+  // dx = +-1 lines of one trip are the dx = 0 lines of the next and come from L1
+  const int64_t trips = (n_pad + kBlock - 1) / kBlock;
+  const int64_t per_cta = (trips + gridDim.x - 1) / gridDim.x;
+  const int64_t r_end = min(n_pad, (int64_t)(blockIdx.x + 1) * per_cta * kBlock);
+  for (int64_t r = (int64_t)blockIdx.x * per_cta * kBlock + threadIdx.x; r < r_end;
+       r += kBlock) {
     const bool live = r < n_loc;
     // a dead tail lane still serves its left neighbour's dy = +1 shuffle: it
     // takes the node that follows in the grid (not owned by this rank); past the
@@ -719,7 +724,7 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
   if (!op->direct)
     return launch_tiled<3>(op, op->P3, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
   if (op->shfl) {
-    const int g = grid_for(n_nodes, kBlock, 16);
+    const int g = grid_for(n_nodes, kBlock, 2);
     if (dotv)
       hexgrid_apply_shfl_kernel<double, 0, true><<<g, kBlock, 0, st>>>(
           op->P3, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S, nullptr,
@@ -762,7 +767,7 @@ int launch_hexgrid_apply_ex(const sktb_gridop *op, int64_t node0, int64_t n_node
                             const double *x, double *y, bool fp32, const double *b,
                             const double *dinv, double omega, cudaStream_t st) {
   if (op->dpn != 3 || !op->shfl || !op->direct) return -1;
-  const int g = grid_for(n_nodes, kBlock, 16);
+  const int g = grid_for(n_nodes, kBlock, 2);
 #define SKTB_EX(T, MODE)                                                               \
   hexgrid_apply_shfl_kernel<T, MODE, false><<<g, kBlock, 0, st>>>(                     \
       op->P3, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, nullptr, b, dinv, \
