@@ -217,9 +217,19 @@ int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg, const sktb_gridop *op,
 int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,
                              const double *inv_diag, int iters, double *out_h,
                              void *stream);
+/* nu pre- and nu post-smoothing sweeps on one level (default 1)                 */
+int sktb_mg_set_level_sweeps(sktb_mg *m, int level, int nu);
+/* Chebyshev polynomial smoother of degree nu on a coarse level (>= 1) instead of
+ * nu damped-Jacobi sweeps: d_k = c1_h[k] d_{k-1} + c2_h[k] D^-1 r_k, x += d_k    */
+int sktb_mg_set_level_cheby(sktb_mg *m, int level, int nu, const double *c1_h,
+                            const double *c2_h);
 /* fp32_level0 != 0: the two products with a matrix-free level-0 operator inside
  * the V-cycle are formed in single precision (vectors stay fp64)              */
 int sktb_mg_set_precision(sktb_mg *m, int fp32_level0);
+/* on (default): all levels with <= 4096 nodes run inside one cooperative kernel
+ * (grid-wide barriers instead of ~14 launches per level); off: one launch per
+ * operation on every level                                                    */
+int sktb_mg_set_fused_tail(sktb_mg *m, int on);
 /* exact coarsest-level solve: dense Gauss-Jordan inverse of the last level's
  * operator (<= 160 dofs; larger levels keep damped-Jacobi sweeps).  Call after
  * sktb_mg_set_level(last, ...) whenever its values changed.                    */

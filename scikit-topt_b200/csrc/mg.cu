@@ -12,12 +12,18 @@
 //  * V(1,1) cycle with damped Jacobi; residual and restriction are fused.
 //  * Dirichlet dofs are masked on every level (coarse dof fixed iff the
 //    coincident fine dof is fixed), so M^-1 stays symmetric positive definite.
+#include <cooperative_groups.h>
+
 #include <vector>
 
 #include "common.cuh"
 #include "linalg.cuh"
 
 using namespace sktb;
+
+constexpr int kTailMaxLevels = 8;   // fused coarse tail (mg_tail_kernel)
+constexpr int kTailMaxNodes = 4096;
+constexpr int kTailGrid = 64;
 
 struct MgLevel {
   int64_t n_nodes = 0, n_blocks = 0;
@@ -33,6 +39,11 @@ struct MgLevel {
   // the operator is not sharded); x is always full length (n_global nodes)
   int64_t node0 = 0, n_global = 0;
   double omega = 0.0;  // damping of this level's Jacobi smoother (0: use the global one)
+  int nu = 1;          // pre- and post-smoothing sweeps on this level
+  bool cheb = false;   // Chebyshev polynomial smoother of degree nu instead of nu Jacobi sweeps
+  double cheb_c1[8] = {0}, cheb_c2[8] = {0};
+  double *d = nullptr; // Chebyshev direction (owned)
+  double *x2 = nullptr; // second iterate of the fused tail kernel (owned)
   // transfer to the next coarser level (tensor grid tables, device)
   int32_t fnp[3] = {0, 0, 0}, cnp[3] = {0, 0, 0};  // nodes per axis (x, y, z)
   const int32_t *ax_c0 = nullptr, *ax_c1 = nullptr;  // [fnx | fny | fnz]
@@ -47,6 +58,7 @@ struct sktb_mg {
   double omega = 0.5;
   int nu_coarse = 20;
   bool fp32_level0 = false;  // single-precision products on a matrix-free level 0
+  bool fused_tail = true;    // levels <= kTailMaxNodes nodes in one cooperative kernel
 };
 
 extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
@@ -66,6 +78,8 @@ extern "C" void sktb_mg_destroy(sktb_mg *m) {
     cudaFree(l.b);
     cudaFree(l.tmp);
     cudaFree(l.dense_inv);
+    cudaFree(l.d);
+    cudaFree(l.x2);
   }
   delete m;
 }
@@ -77,9 +91,42 @@ extern "C" int sktb_mg_set_params(sktb_mg *m, double omega, int nu_coarse) {
   return 0;
 }
 
+extern "C" int sktb_mg_set_level_sweeps(sktb_mg *m, int level, int nu) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size() && nu >= 1 && nu <= 8,
+               "bad argument");
+  m->lv[level].nu = nu;
+  return 0;
+}
+
+// Chebyshev smoother of degree nu on one level (>= 1): d_k = c1[k] d_{k-1} +
+// c2[k] D^-1 r_k, x += d_k (c1[0] is ignored); replaces the nu Jacobi sweeps
+extern "C" int sktb_mg_set_level_cheby(sktb_mg *m, int level, int nu, const double *c1_h,
+                                       const double *c2_h) {
+  SKTB_REQUIRE(m && level >= 1 && level < (int)m->lv.size() && nu >= 1 && nu <= 8 && c1_h &&
+                   c2_h,
+               "bad argument");
+  MgLevel &l = m->lv[level];
+  SKTB_REQUIRE(l.n_nodes > 0, "set the level before its smoother");
+  SKTB_CUDA_OK(cudaSetDevice(m->device));
+  if (!l.d) SKTB_CUDA_OK(cudaMalloc(&l.d, sizeof(double) * 3 * l.n_nodes));
+  l.nu = nu;
+  l.cheb = true;
+  for (int k = 0; k < nu; ++k) {
+    l.cheb_c1[k] = c1_h[k];
+    l.cheb_c2[k] = c2_h[k];
+  }
+  return 0;
+}
+
 extern "C" int sktb_mg_set_precision(sktb_mg *m, int fp32_level0) {
   SKTB_REQUIRE(m, "null argument");
   m->fp32_level0 = fp32_level0 != 0;
+  return 0;
+}
+
+extern "C" int sktb_mg_set_fused_tail(sktb_mg *m, int on) {
+  SKTB_REQUIRE(m, "null argument");
+  m->fused_tail = on != 0;
   return 0;
 }
 
@@ -108,6 +155,10 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
     SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
     SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
+    cudaFree(l.x2);
+    l.x2 = nullptr;
+    if (level > 0 && n_nodes <= kTailMaxNodes)
+      SKTB_CUDA_OK(cudaMalloc(&l.x2, sizeof(double) * 3 * n_nodes));
   }
   l.n_nodes = n_nodes;
   l.gop = nullptr;
@@ -352,6 +403,19 @@ __global__ void __launch_bounds__(kBlock)
   GS(i, n) x[i] += omega * dinv[i] * (b[i] - Ax[i]);
 }
 
+// Chebyshev step: d = c1 d + c2 D^-1 (b - Ax) ; x = (from_zero ? d : x + d)
+__global__ void __launch_bounds__(kBlock)
+    mg_cheby_kernel(int64_t n, double c1, double c2, const double *__restrict__ dinv,
+                    const double *__restrict__ b, const double *__restrict__ Ax,
+                    int from_zero, double *__restrict__ d, double *__restrict__ x) {
+  GS(i, n) {
+    const double r = Ax ? b[i] - Ax[i] : b[i];
+    const double di = (c1 != 0.0 ? c1 * d[i] : 0.0) + c2 * dinv[i] * r;
+    d[i] = di;
+    x[i] = from_zero ? di : x[i] + di;
+  }
+}
+
 // b_c = mask_c * P^T (b_f - Ax_f) ; one WARP per coarse node, one lane per
 // fine node of its 3x3x3 stencil (fixed-order shuffle reduction: deterministic)
 __global__ void __launch_bounds__(kBlock)
@@ -572,6 +636,208 @@ extern "C" int sktb_mg_factor_coarsest(sktb_mg *m, void *stream) {
   return 0;
 }
 
+// ------------------------------------------------ fused coarse tail kernel --
+// The levels below a few thousand nodes are launch-latency bound (every kernel
+// is 3-5 us of ramp-up for < 1 us of work) and they need the most smoothing
+// sweeps.  One cooperative kernel walks all of them down and up with grid-wide
+// barriers in place of launches: sweeps are SpMV + Jacobi fused through a
+// ping-pong pair of iterates (one barrier per sweep).
+namespace cg = cooperative_groups;
+
+struct TailLevel {
+  int n_nodes;
+  const int32_t *node_ptr, *node_col;
+  const double *vals, *dinv;
+  const uint8_t *mask;
+  double *x, *x2, *b, *tmp;
+  double omega;
+  int nu;
+  int fnp[3], cnp[3];
+  const int32_t *c0, *c1;
+  const double *w0, *w1;
+  const int32_t *fT;
+  const double *wT;
+  const double *dense_inv;
+  int dense_n;
+};
+struct TailParams {
+  int n_levels;
+  TailLevel lv[kTailMaxLevels];
+};
+
+// row r of A x, four lanes per row (lanes of one row are adjacent)
+__device__ __forceinline__ double tail_row(const TailLevel &L, int r, int q,
+                                           const double *__restrict__ x) {
+  const int nd = r / 3, ri = r - 3 * nd;
+  const int32_t s0 = L.node_ptr[nd], deg = L.node_ptr[nd + 1] - s0;
+  const double *vp = L.vals + (int64_t)9 * s0 + (int64_t)ri * 3 * deg;
+  double acc = 0.0;
+  for (int k = q; k < deg; k += 4) {
+    const double *xb = x + 3 * L.node_col[s0 + k];
+    acc += vp[3 * k] * xb[0] + vp[3 * k + 1] * xb[1] + vp[3 * k + 2] * xb[2];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  return acc;
+}
+
+// dst = src + omega D^-1 (b - A src)   (or tmp = A src when residual_only)
+__device__ __forceinline__ void tail_sweep(const TailLevel &L, const double *src, double *dst,
+                                           bool residual_only, int gtid, int gsize) {
+  const int n = 3 * L.n_nodes;
+  const int n4 = (n * 4 + 31) / 32 * 32;  // whole warps: the row shuffles need all four lanes
+  for (int i = gtid; i < n4; i += gsize) {
+    const int r = i >> 2, q = i & 3;
+    const bool live = r < n;
+    const double ax = tail_row(L, live ? r : n - 1, q, src);
+    if (live && q == 0) {
+      if (residual_only)
+        dst[r] = ax;
+      else
+        dst[r] = src[r] + L.omega * L.dinv[r] * (L.b[r] - ax);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    mg_tail_kernel(const __grid_constant__ TailParams P) {
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gsize = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = gtid >> 5, nwarp = gsize >> 5;
+  const int NL = P.n_levels;
+  // ---- down
+  for (int k = 0; k < NL; ++k) {
+    const TailLevel &L = P.lv[k];
+    const int n = 3 * L.n_nodes;
+    if (k == NL - 1) {
+      if (L.dense_n == n) {
+        for (int r = gwarp; r < n; r += nwarp) {
+          double a = 0.0;
+          for (int j = lane; j < n; j += 32) a += L.dense_inv[(int64_t)r * n + j] * L.b[j];
+          a = warp_sum(a);
+          if (lane == 0) L.x[r] = a;
+        }
+      } else {  // no exact solve available: nu sweeps from zero
+        double *cur = (L.nu & 1) ? L.x : L.x2, *nxt = (L.nu & 1) ? L.x2 : L.x;
+        for (int i = gtid; i < n; i += gsize) cur[i] = L.omega * L.dinv[i] * L.b[i];
+        grid.sync();
+        for (int s = 1; s < L.nu; ++s) {
+          tail_sweep(L, cur, nxt, false, gtid, gsize);
+          grid.sync();
+          double *t = cur;
+          cur = nxt;
+          nxt = t;
+        }
+      }
+      grid.sync();
+      break;
+    }
+    // the level's iterate ends in L.x after (nu - 1) + nu swaps: start in x2
+    double *cur = L.x2, *nxt = L.x;
+    for (int i = gtid; i < n; i += gsize) cur[i] = L.omega * L.dinv[i] * L.b[i];
+    grid.sync();
+    for (int s = 1; s < L.nu; ++s) {
+      tail_sweep(L, cur, nxt, false, gtid, gsize);
+      grid.sync();
+      double *t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    tail_sweep(L, cur, L.tmp, true, gtid, gsize);
+    grid.sync();
+    // restrict b - A x into the next level (warp per coarse node, 27 lanes)
+    const TailLevel &Cn = P.lv[k + 1];
+    {
+      const int cnx = L.cnp[0], cny = L.cnp[1], cnz = L.cnp[2];
+      const int fnx = L.fnp[0], fny = L.fnp[1];
+      const int tot = cnx + cny + cnz;
+      const int sy = lane % 3, sx = (lane / 3) % 3, sz = lane / 9;
+      for (int I = gwarp; I < Cn.n_nodes; I += nwarp) {
+        const int iy = I % cny, ix = (I / cny) % cnx, iz = I / (cny * cnx);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (lane < 27) {
+          const int fz = L.fT[sz * tot + cnx + cny + iz];
+          const int fx = L.fT[sx * tot + ix];
+          const int fy = L.fT[sy * tot + cnx + iy];
+          if (fz >= 0 && fx >= 0 && fy >= 0) {
+            const double w = L.wT[sz * tot + cnx + cny + iz] * L.wT[sx * tot + ix] *
+                             L.wT[sy * tot + cnx + iy];
+            const int f = 3 * (fy + fny * (fx + fnx * fz));
+            a0 = w * (L.b[f] - L.tmp[f]);
+            a1 = w * (L.b[f + 1] - L.tmp[f + 1]);
+            a2 = w * (L.b[f + 2] - L.tmp[f + 2]);
+          }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+          const int o = 3 * I;
+          Cn.b[o] = (Cn.mask && Cn.mask[o]) ? 0.0 : a0;
+          Cn.b[o + 1] = (Cn.mask && Cn.mask[o + 1]) ? 0.0 : a1;
+          Cn.b[o + 2] = (Cn.mask && Cn.mask[o + 2]) ? 0.0 : a2;
+        }
+      }
+    }
+    grid.sync();
+  }
+  // ---- up
+  for (int k = NL - 2; k >= 0; --k) {
+    const TailLevel &L = P.lv[k];
+    const TailLevel &Cn = P.lv[k + 1];
+    const int n = 3 * L.n_nodes;
+    // where the down sweep left this level's iterate
+    double *cur = ((L.nu - 1) & 1) ? L.x : L.x2;
+    double *nxt = ((L.nu - 1) & 1) ? L.x2 : L.x;
+    {
+      const int cnx = L.cnp[0], cny = L.cnp[1];
+      const int fnx = L.fnp[0], fny = L.fnp[1];
+      for (int F = gtid; F < L.n_nodes; F += gsize) {
+        const int iy = F % fny, ix = (F / fny) % fnx, iz = F / (fny * fnx);
+        const int cx[2] = {L.c0[ix], L.c1[ix]};
+        const double wx[2] = {L.w0[ix], L.w1[ix]};
+        const int cy[2] = {L.c0[fnx + iy], L.c1[fnx + iy]};
+        const double wy[2] = {L.w0[fnx + iy], L.w1[fnx + iy]};
+        const int cz[2] = {L.c0[fnx + fny + iz], L.c1[fnx + fny + iz]};
+        const double wz[2] = {L.w0[fnx + fny + iz], L.w1[fnx + fny + iz]};
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+          if (wz[kz] == 0.0) continue;
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) {
+            if (wx[kx] == 0.0) continue;
+#pragma unroll
+            for (int ky = 0; ky < 2; ++ky) {
+              if (wy[ky] == 0.0) continue;
+              const double w = wz[kz] * wx[kx] * wy[ky];
+              const int c = 3 * (cy[ky] + cny * (cx[kx] + cnx * cz[kz]));
+              a0 += w * Cn.x[c];
+              a1 += w * Cn.x[c + 1];
+              a2 += w * Cn.x[c + 2];
+            }
+          }
+        }
+        const int o = 3 * F;
+        if (!(L.mask && L.mask[o])) cur[o] += a0;
+        if (!(L.mask && L.mask[o + 1])) cur[o + 1] += a1;
+        if (!(L.mask && L.mask[o + 2])) cur[o + 2] += a2;
+      }
+    }
+    grid.sync();
+    for (int s = 0; s < L.nu; ++s) {
+      tail_sweep(L, cur, nxt, false, gtid, gsize);
+      grid.sync();
+      double *t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    (void)n;
+  }
+}
+
 static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t st,
                       bool fp32 = false) {
   if (l.gop) {
@@ -594,14 +860,71 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
 // z = M^-1 r : V(1,1) cycle.  Level 0 may be row-sharded (its x is a
 // full-length vector whose ghost slots are refreshed before every SpMV, the
 // restricted residual is all-reduced); levels >= 1 are replicated.
+// first level of the fused tail (L: none)
+static int tail_start(const sktb_mg *m) {
+  const int L = (int)m->lv.size();
+  if (!m->fused_tail) return L;
+  int k0 = L;
+  for (int k = L - 1; k >= 1; --k) {
+    const MgLevel &l = m->lv[k];
+    if (l.n_nodes > kTailMaxNodes || !l.x2 || !l.vals || l.cheb || L - k > kTailMaxLevels) break;
+    k0 = k;
+  }
+  return k0;
+}
+
+static int launch_tail(sktb_mg *m, int k0, cudaStream_t st) {
+  const int L = (int)m->lv.size();
+  TailParams P;
+  P.n_levels = L - k0;
+  for (int k = k0; k < L; ++k) {
+    const MgLevel &l = m->lv[k];
+    TailLevel &t = P.lv[k - k0];
+    t.n_nodes = (int)l.n_nodes;
+    t.node_ptr = l.node_ptr;
+    t.node_col = l.node_col;
+    t.vals = l.vals;
+    t.dinv = l.inv_diag;
+    t.mask = l.mask;
+    t.x = l.x;
+    t.x2 = l.x2;
+    t.b = l.b;
+    t.tmp = l.tmp;
+    t.omega = l.omega > 0.0 ? l.omega : m->omega;
+    t.nu = (k == L - 1) ? (m->nu_coarse > 0 ? m->nu_coarse : 1) : l.nu;
+    for (int a = 0; a < 3; ++a) {
+      t.fnp[a] = l.fnp[a];
+      t.cnp[a] = l.cnp[a];
+    }
+    t.c0 = l.ax_c0;
+    t.c1 = l.ax_c1;
+    t.w0 = l.ax_w0;
+    t.w1 = l.ax_w1;
+    t.fT = l.axT_f;
+    t.wT = l.axT_w;
+    t.dense_inv = l.dense_inv;
+    t.dense_n = l.dense_n;
+  }
+  void *args[] = {(void *)&P};
+  SKTB_CUDA_OK(cudaLaunchCooperativeKernel((void *)mg_tail_kernel, dim3(kTailGrid),
+                                           dim3(kBlock), args, 0, st));
+  SKTB_COUNT(1);
+  return 0;
+}
+
 int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
               sktb_pcg *dist) {
   const int L = (int)m->lv.size();
+  const int k_tail = tail_start(m);
   const bool sharded = dist && pcg_is_dist(dist);
   MgLevel &l0 = m->lv[0];
   const int64_t f_lo = l0.node0, f_hi = l0.node0 + l0.n_nodes;
   // downward sweep
   for (int k = 0; k < L; ++k) {
+    if (k == k_tail) {
+      if (launch_tail(m, k_tail, st)) return 1;
+      break;
+    }
     MgLevel &l = m->lv[k];
     const int64_t n = 3 * l.n_nodes;
     const double *b = (k == 0) ? r : l.b;
@@ -614,6 +937,25 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
           (int)n, l.dense_inv, b, x);
       SKTB_COUNT(1);
       break;
+    }
+    if (l.cheb && k > 0 && k < L - 1) {
+      // Chebyshev pre-smoothing of degree nu from a zero initial guess
+      mg_cheby_kernel<<<g, kBlock, 0, st>>>(n, 0.0, l.cheb_c2[0], l.inv_diag, b, nullptr, 1,
+                                           l.d, x);
+      SKTB_COUNT(1);
+      for (int s = 1; s < l.nu; ++s) {
+        if (level_spmv(l, xfull, l.tmp, st)) return 1;
+        mg_cheby_kernel<<<g, kBlock, 0, st>>>(n, l.cheb_c1[s], l.cheb_c2[s], l.inv_diag, b,
+                                             l.tmp, 0, l.d, x);
+        SKTB_COUNT(1);
+      }
+      if (level_spmv(l, xfull, l.tmp, st)) return 1;
+      MgLevel &c = m->lv[k + 1];
+      mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
+          l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
+          l.axT_w, b, l.tmp, c.mask, c.b, 0, l.n_nodes);
+      SKTB_COUNT(1);
+      continue;
     }
     mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
     SKTB_COUNT(1);
@@ -630,6 +972,12 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
         SKTB_COUNT(1);
       }
     } else {
+      for (int s = 1; s < l.nu; ++s) {  // extra pre-smoothing sweeps
+        if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
+        if (level_spmv(l, xfull, l.tmp, st)) return 1;
+        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+        SKTB_COUNT(1);
+      }
       if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
       if (level_spmv(l, xfull, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
       MgLevel &c = m->lv[k + 1];
@@ -645,7 +993,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
   }
   // upward sweep
   bool z_done = false;
-  for (int k = L - 2; k >= 0; --k) {
+  for (int k = (k_tail < L ? k_tail - 1 : L - 2); k >= 0; --k) {
     MgLevel &l = m->lv[k];
     MgLevel &c = m->lv[k + 1];
     const int64_t n = 3 * l.n_nodes;
@@ -659,6 +1007,22 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.ax_c0,
         l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, xfull, lo, hi);
     SKTB_COUNT(1);
+    if (l.cheb && k > 0) {
+      for (int s = 0; s < l.nu; ++s) {
+        if (level_spmv(l, xfull, l.tmp, st)) return 1;
+        mg_cheby_kernel<<<grid_for(n), kBlock, 0, st>>>(n, s ? l.cheb_c1[s] : 0.0,
+                                                       l.cheb_c2[s], l.inv_diag, b, l.tmp, 0,
+                                                       l.d, x);
+        SKTB_COUNT(1);
+      }
+      continue;
+    }
+    for (int s = 1; s < l.nu; ++s) {  // extra post-smoothing sweeps
+      if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
+      if (level_spmv(l, xfull, l.tmp, st)) return 1;
+      mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+      SKTB_COUNT(1);
+    }
     if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
     if (k == 0 && l.gop) {
       // fused post-smoothing straight into z: z = x + om D^-1 (r - A x)

@@ -60,6 +60,9 @@ SIGNATURES = {
     "sktb_pcg_solve_grid": [C.c_void_p, C.c_void_p, C.c_void_p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_pcg_lambda_max_grid": [C.c_void_p, C.c_void_p, c_f64p, i32, C.c_void_p, c_stream],
     "sktb_mg_set_precision": [C.c_void_p, i32],
+    "sktb_mg_set_fused_tail": [C.c_void_p, i32],
+    "sktb_mg_set_level_sweeps": [C.c_void_p, i32, i32],
+    "sktb_mg_set_level_cheby": [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p],
     "sktb_mg_factor_coarsest": [C.c_void_p, c_stream],
     "sktb_mg_set_level0_grid": [C.c_void_p, C.c_void_p, i64, c_f64p, c_u8p],
     "sktb_elem_combine": [i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],

@@ -126,6 +126,22 @@ def child_tables(fine_cells, coarse_cells):
     return child, ptype
 
 
+def chebyshev_coefficients(lam_max: float, lam_min: float, degree: int):
+    """(c1, c2) of the Chebyshev iteration for a spectrum in [lam_min, lam_max]
+    (Saad, Iterative Methods, Alg. 12.1): d_k = c1[k] d_{k-1} + c2[k] z_k."""
+    theta, delta = 0.5 * (lam_max + lam_min), 0.5 * (lam_max - lam_min)
+    sigma = theta / delta
+    c1, c2 = np.zeros(degree), np.zeros(degree)
+    rho = 1.0 / sigma
+    c2[0] = 1.0 / theta
+    for k in range(1, degree):
+        rho_new = 1.0 / (2.0 * sigma - rho)
+        c1[k] = rho_new * rho
+        c2[k] = 2.0 * rho_new / delta
+        rho = rho_new
+    return c1, c2
+
+
 class Multigrid:
     """Grid hierarchy + Galerkin set-up for one elasticity engine."""
 
@@ -166,6 +182,8 @@ class Multigrid:
         # only; SKTOPT_B200_MG_FP32=0 keeps them in fp64)
         self.fp32 = os.environ.get("SKTOPT_B200_MG_FP32", "1") != "0"
         _lib.check(self.lib.sktb_mg_set_precision(h, int(self.fp32)))
+        self.fused_tail = os.environ.get("SKTOPT_B200_MG_FUSED_TAIL", "1") != "0"
+        _lib.check(self.lib.sktb_mg_set_fused_tail(h, int(self.fused_tail)))
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
@@ -214,6 +232,14 @@ class Multigrid:
                 dev._ptr(tr["c0"]), dev._ptr(tr["c1"]), dev._ptr(tr["w0"]), dev._ptr(tr["w1"]),
                 dev._ptr(tr["fT"]), dev._ptr(tr["wT"])))
             mask_f = mask_c
+        # smoothing sweeps per level: "a,b,c,..." for levels 0,1,2,... (last value
+        # repeats).  Levels 0/1 carry the cost, the cheap coarse levels get more sweeps
+        # (measured at C2: 34 -> 22 PCG iterations)
+        sweeps = [int(v) for v in os.environ.get("SKTOPT_B200_MG_SWEEPS", "1,1,2,3").split(",")]
+        self.sweeps = [sweeps[min(l, len(sweeps) - 1)] for l in range(self.n_levels)]
+        for l, nu in enumerate(self.sweeps):
+            _lib.check(self.lib.sktb_mg_set_level_sweeps(h, l, nu))
+        self.cheb_alpha = float(os.environ.get("SKTOPT_B200_MG_CHEB_ALPHA", "0"))
         self.setup_count = 0
         # level 0 -> 1 tables T[cls][type][c] = Q_c^T Ke0[cls] Q_c (host, once)
         ke0 = engine.unit_ke.cpu().numpy().reshape(-1, 24, 24)
@@ -324,6 +350,12 @@ class Multigrid:
                 self.lambda_max.append(lam)
                 _lib.check(self.lib.sktb_mg_set_level_omega(
                     self.handle, l, float(1.75 / (1.03 * lam))))
+                if self.cheb_alpha > 0.0 and 1 <= l < self.n_levels - 1 and self.sweeps[l] >= 2:
+                    c1, c2 = chebyshev_coefficients(1.1 * lam, 1.1 * lam / self.cheb_alpha,
+                                                    self.sweeps[l])
+                    _lib.check(self.lib.sktb_mg_set_level_cheby(
+                        self.handle, l, self.sweeps[l], c1.ctypes.data_as(C.c_void_p),
+                        c2.ctypes.data_as(C.c_void_p)))
         self.setup_count += 1
 
     def vcycle(self, r, z=None):

@@ -145,3 +145,23 @@ def test_selector_cg_jacobi_disables_multigrid(gpu):
     it_j = f_j.engine.pcg_log[-1][0]
     assert abs(c_mg[0] - c_j[0]) <= 1e-7 * abs(c_j[0])
     assert it_mg < it_j
+
+
+def test_fused_tail_matches_per_level_launches(gpu, monkeypatch):
+    """The cooperative coarse-tail kernel applies the same V-cycle as the
+    launch-per-operation path (only the summation order inside a row differs)."""
+    sktopt, dev = gpu
+    monkeypatch.setenv("SKTOPT_B200_PRECOND", "mg")
+    monkeypatch.setenv("SKTOPT_B200_MG_FP32", "0")
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SKTOPT_B200_MG_FUSED_TAIL", flag)
+        mesh, basis, D, eng = _engine(sktopt, dims=(4.0, 3.0, 2.0), h=0.25)
+        rho = np.random.default_rng(1).uniform(0.01, 1.0, mesh.nelements)
+        eng.set_modulus(dev.to_dev(rho), 210e3, 210.0, 3.0)
+        eng.prepare()
+        assert eng.mg.n_levels >= 3
+        a = np.random.default_rng(2).standard_normal(eng.n_dof)
+        a[D] = 0.0
+        out[flag] = eng.mg.vcycle(dev.to_dev(a)).cpu().numpy()
+    assert np.max(np.abs(out["1"] - out["0"])) <= 1e-11 * np.max(np.abs(out["0"]))
