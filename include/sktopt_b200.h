@@ -226,8 +226,8 @@ int sktb_mg_set_level_cheby(sktb_mg *m, int level, int nu, const double *c1_h,
 /* fp32_level0 != 0: the two products with a matrix-free level-0 operator inside
  * the V-cycle are formed in single precision (vectors stay fp64)              */
 int sktb_mg_set_precision(sktb_mg *m, int fp32_level0);
-/* on (default): all levels with <= 4096 nodes run inside one cooperative kernel
- * (grid-wide barriers instead of ~14 launches per level); off: one launch per
+/* on: all levels with <= 1024 nodes run inside one cooperative kernel (grid-wide
+ * barriers instead of ~14 launches per level); off (default): one launch per
  * operation on every level                                                    */
 int sktb_mg_set_fused_tail(sktb_mg *m, int on);
 /* exact coarsest-level solve: dense Gauss-Jordan inverse of the last level's

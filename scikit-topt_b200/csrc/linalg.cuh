@@ -40,6 +40,11 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const double *dotv, sktb::ReduceScratch *rs,
                          double *dot_out, const PcgScalars *S, cudaStream_t st);
 
+// below ~8k nodes the bulk-async pipeline's fixed start-up (~10 us) exceeds the
+// work and the warp-per-node kernel is faster (measured: 2.7k nodes 13 -> 7 us,
+// 16k nodes 13 vs 17 us)
+constexpr int64_t kTmaMinNodes = 8000;
+
 // matrix-free hexahedral grid operator (gridop.cu): y[local rows] = K x with x
 // a full-length vector; same dot / early-exit contract as the SpMV launchers
 struct sktb_gridop;

@@ -22,8 +22,8 @@
 using namespace sktb;
 
 constexpr int kTailMaxLevels = 8;   // fused coarse tail (mg_tail_kernel)
-constexpr int kTailMaxNodes = 4096;
-constexpr int kTailGrid = 64;
+constexpr int kTailMaxNodes = 1024;
+constexpr int kTailGrid = 148;
 
 struct MgLevel {
   int64_t n_nodes = 0, n_blocks = 0;
@@ -58,7 +58,7 @@ struct sktb_mg {
   double omega = 0.5;
   int nu_coarse = 20;
   bool fp32_level0 = false;  // single-precision products on a matrix-free level 0
-  bool fused_tail = true;    // levels <= kTailMaxNodes nodes in one cooperative kernel
+  bool fused_tail = false;   // levels <= kTailMaxNodes nodes in one cooperative kernel
 };
 
 extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
@@ -416,6 +416,51 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// b_c = mask_c * P^T (b_f - Ax_f) ; one thread per coarse node (large levels:
+// 136k coarse nodes at C2 take 29 us this way, 61 us with a warp per node)
+__global__ void __launch_bounds__(kBlock)
+    mg_restrict_thread_kernel(int cnx, int cny, int cnz, int fnx, int fny, int fnz,
+                              const int32_t *__restrict__ axT_f,
+                              const double *__restrict__ axT_w,
+                              const double *__restrict__ bf,
+                              const double *__restrict__ Axf,
+                              const uint8_t *__restrict__ mask_c,
+                              double *__restrict__ bc, int64_t f_lo, int64_t f_hi) {
+  const int64_t nc = (int64_t)cnx * cny * cnz;
+  const int tot = cnx + cny + cnz;
+  GS(I, nc) {
+    const int iy = (int)(I % cny);
+    const int ix = (int)((I / cny) % cnx);
+    const int iz = (int)(I / ((int64_t)cny * cnx));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int sz = 0; sz < 3; ++sz) {
+      const int fz = axT_f[sz * tot + cnx + cny + iz];
+      if (fz < 0) continue;
+      const double wz = axT_w[sz * tot + cnx + cny + iz];
+      for (int sx = 0; sx < 3; ++sx) {
+        const int fx = axT_f[sx * tot + ix];
+        if (fx < 0) continue;
+        const double wx = axT_w[sx * tot + ix] * wz;
+        for (int sy = 0; sy < 3; ++sy) {
+          const int fy = axT_f[sy * tot + cnx + iy];
+          if (fy < 0) continue;
+          const double w = axT_w[sy * tot + cnx + iy] * wx;
+          const int64_t fn = (int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz;
+          if (fn < f_lo || fn >= f_hi) continue;  // another rank's fine node
+          const int64_t f = 3 * (fn - f_lo);      // bf / Axf hold the owned rows
+          a0 += w * (bf[f] - Axf[f]);
+          a1 += w * (bf[f + 1] - Axf[f + 1]);
+          a2 += w * (bf[f + 2] - Axf[f + 2]);
+        }
+      }
+    }
+    const int64_t o = 3 * I;
+    bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
+    bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+    bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+  }
+}
+
 // b_c = mask_c * P^T (b_f - Ax_f) ; one WARP per coarse node, one lane per
 // fine node of its 3x3x3 stencil (fixed-order shuffle reduction: deterministic)
 __global__ void __launch_bounds__(kBlock)
@@ -665,32 +710,30 @@ struct TailParams {
   TailLevel lv[kTailMaxLevels];
 };
 
-// row r of A x, four lanes per row (lanes of one row are adjacent)
-__device__ __forceinline__ double tail_row(const TailLevel &L, int r, int q,
+// row r of A x by one warp: lanes stride the row's 3 deg entries (coalesced
+// values), all loads of the row in flight together
+__device__ __forceinline__ double tail_row(const TailLevel &L, int r, int lane,
                                            const double *__restrict__ x) {
   const int nd = r / 3, ri = r - 3 * nd;
   const int32_t s0 = L.node_ptr[nd], deg = L.node_ptr[nd + 1] - s0;
   const double *vp = L.vals + (int64_t)9 * s0 + (int64_t)ri * 3 * deg;
   double acc = 0.0;
-  for (int k = q; k < deg; k += 4) {
-    const double *xb = x + 3 * L.node_col[s0 + k];
-    acc += vp[3 * k] * xb[0] + vp[3 * k + 1] * xb[1] + vp[3 * k + 2] * xb[2];
+#pragma unroll 3
+  for (int e = lane; e < 3 * deg; e += 32) {
+    const int k = e / 3, j = e - 3 * k;
+    acc += vp[e] * x[3 * L.node_col[s0 + k] + j];
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  return acc;
+  return warp_sum(acc);
 }
 
 // dst = src + omega D^-1 (b - A src)   (or tmp = A src when residual_only)
 __device__ __forceinline__ void tail_sweep(const TailLevel &L, const double *src, double *dst,
                                            bool residual_only, int gtid, int gsize) {
   const int n = 3 * L.n_nodes;
-  const int n4 = (n * 4 + 31) / 32 * 32;  // whole warps: the row shuffles need all four lanes
-  for (int i = gtid; i < n4; i += gsize) {
-    const int r = i >> 2, q = i & 3;
-    const bool live = r < n;
-    const double ax = tail_row(L, live ? r : n - 1, q, src);
-    if (live && q == 0) {
+  const int lane = threadIdx.x & 31;
+  for (int r = gtid >> 5; r < n; r += gsize >> 5) {
+    const double ax = tail_row(L, r, lane, src);
+    if (lane == 0) {
       if (residual_only)
         dst[r] = ax;
       else
@@ -849,7 +892,7 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
     return launch_hexgrid_apply(l.gop, l.node0, l.n_nodes, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
   }
-  int rc = launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
+  int rc = l.n_nodes < kTmaMinNodes ? -1 : launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
                                 l.node_col, l.vals, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
   if (rc != -1) return rc;
@@ -983,9 +1026,14 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       MgLevel &c = m->lv[k + 1];
       const int64_t lo = (k == 0) ? f_lo : 0;
       const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
-      mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
-          l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
-          l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
+      if (c.n_nodes > 20000)
+        mg_restrict_thread_kernel<<<grid_for(c.n_nodes), kBlock, 0, st>>>(
+            l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
+            l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
+      else
+        mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
+            l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
+            l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
       SKTB_COUNT(1);
       if (k == 0 && sharded && pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st))
         return 1;

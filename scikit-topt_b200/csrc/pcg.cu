@@ -329,7 +329,7 @@ static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
     return launch_hexgrid_apply(A.gop, A.node0, n / gridop_dpn(A.gop), x, y, dotv, rs,
                                 dot_out, S, st);
   if (A.kind == 1) {
-    int rc = launch_spmv_bsr3_tma(n / 3, A.n_blocks, A.max_deg, A.rp, A.ci,
+    int rc = n / 3 < kTmaMinNodes ? -1 : launch_spmv_bsr3_tma(n / 3, A.n_blocks, A.max_deg, A.rp, A.ci,
                                   A.vals, x, y, dotv, rs, dot_out, S, st);
     if (rc != -1) return rc;
     return launch_spmv_bsr3(n / 3, A.rp, A.ci, A.vals, x, y, dotv, rs, dot_out,

@@ -182,7 +182,10 @@ class Multigrid:
         # only; SKTOPT_B200_MG_FP32=0 keeps them in fp64)
         self.fp32 = os.environ.get("SKTOPT_B200_MG_FP32", "1") != "0"
         _lib.check(self.lib.sktb_mg_set_precision(h, int(self.fp32)))
-        self.fused_tail = os.environ.get("SKTOPT_B200_MG_FUSED_TAIL", "1") != "0"
+        # one cooperative kernel for the levels <= 1024 nodes; measured equal to the
+        # launch-per-operation path at C2 (grid barriers cost what launches cost),
+        # so it is opt-in
+        self.fused_tail = os.environ.get("SKTOPT_B200_MG_FUSED_TAIL", "0") == "1"
         _lib.check(self.lib.sktb_mg_set_fused_tail(h, int(self.fused_tail)))
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
