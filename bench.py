@@ -244,7 +244,7 @@ def run_b200(args):
             alg_bytes = n_loc_nodes * (24 + 24 + 24 + 1) + n_elem * 8
             roofline = {
                 "bound": "fp64",
-                "kernel": "hexgrid_apply_kernel<true> (matrix-free q = K(rho) p + p.q; 3 of these per PCG iteration)",
+                "kernel": "hexgrid_apply_shfl_kernel<double,0,true> (matrix-free q = K(rho) p + p.q; the V-cycle runs two more per PCG iteration in fp32)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp64_peak) if achieved else None,
                 "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe); "
@@ -297,8 +297,10 @@ def run_b200(args):
                 "solver": ("device PCG rtol 1e-8, warm start, operator: "
                            + ("matrix-free grid stencil" if eng.matrix_free else "assembled node-block CSR")
                            + ", preconditioner: "
-                           + ("geometric multigrid V(1,1) (Galerkin coarse operators, damped Jacobi, "
-                              "exact dense coarsest solve)" if eng.precond == "mg" else "Jacobi")),
+                           + ("geometric multigrid V-cycle (Galerkin coarse operators, damped Jacobi "
+                              "sweeps per level %s, exact dense coarsest solve, fp32 level-0 products)"
+                              % ",".join(str(v) for v in eng.mg.sweeps)
+                              if eng.precond == "mg" else "Jacobi")),
                 "pcg_iters_per_step": pcg_iters,
                 "l2": ("per-step working set (u, rho, filter CSR 0.34 GB, level-1 operator 0.27 GB, "
                        "work vectors) larger than the 126 MB L2; nothing is flushed explicitly"),
