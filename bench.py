@@ -240,6 +240,7 @@ def run_b200(args):
             # for the modulus scaling (DESIGN.md "grid operator").
             flops = n_loc_nodes * (576 + 24) * 2
             fp64_peak = dev.fp64_peak_tflops()
+            fp64_peak_const = dev.fp64_peak_tflops(const_operand=True)
             achieved = flops / (spmv_ms * 1e-3) / 1e12 if spmv_n else None
             alg_bytes = n_loc_nodes * (24 + 24 + 24 + 1) + n_elem * 8
             roofline = {
@@ -249,6 +250,8 @@ def run_b200(args):
                 "frac": (achieved / fp64_peak) if achieved else None,
                 "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe); "
                                "MEASURED_PEAKS.json has no FP64 entry",
+                "peak_const_operand": fp64_peak_const,
+                "frac_of_const_operand_peak": (achieved / fp64_peak_const) if achieved else None,
                 "alg_flops_per_launch": flops, "avg_launch_ms": spmv_ms, "samples": spmv_n,
                 "traffic": None,
                 "hbm": {"alg_bytes_per_launch": alg_bytes,
@@ -256,7 +259,10 @@ def run_b200(args):
                         "peak_GBs": peak, "peak_source": peak_src},
                 "note": "the assembled-operator SpMV this replaces streamed 8.44 B/nnz (2.1 GB per "
                         "launch, 0.44 ms at the HBM roofline); the matrix-free product moves "
-                        "~85 MB and is limited by FP64 issue/latency",
+                        "~85 MB.  Its DFMAs take the stiffness coefficient as a constant-bank "
+                        "operand, which B200 issues at half the FP64 rate (peak_const_operand, "
+                        "measured by sktb_fp64_probe_const): that is the ceiling this formulation "
+                        "can reach",
             }
         else:
             # SURVEY.md 8(d), for the rows this rank owns

@@ -445,6 +445,8 @@ int sktb_flush_l2(void *scratch, int64_t bytes, void *stream);
 /* benchmark utility: FP64 FMA throughput probe; out holds 148*8*256 doubles,
  * *flops_h receives the flops of the launch                                    */
 int sktb_fp64_probe(int iters, double *out, int64_t *flops_h, void *stream);
+/* same with the multiplier read from the constant bank (iters % 8 == 0)        */
+int sktb_fp64_probe_const(int iters, double *out, int64_t *flops_h, void *stream);
 
 #ifdef __cplusplus
 }

@@ -253,6 +253,41 @@ __global__ void __launch_bounds__(kBlock)
   out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// same chains, multiplier taken from the constant bank (kernel parameter ->
+// uniform register operand), as the grid operator's DFMAs do
+struct ProbeConsts {
+  double c[64];
+};
+__global__ void __launch_bounds__(kBlock)
+    fp64_probe_const_kernel(const __grid_constant__ ProbeConsts P, int iters,
+                            double *__restrict__ out) {
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+  const double b = 1e-9 * blockIdx.x;
+  for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fma(v[k], P.c[8 * j + k], b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int sktb_fp64_probe_const(int iters, double *out, int64_t *flops_h, void *stream) {
+  SKTB_REQUIRE(out && iters > 0 && iters % 8 == 0, "bad argument");
+  const int grid = kNumSM * 8;
+  ProbeConsts P;
+  for (int i = 0; i < 64; ++i) P.c[i] = 0.999999 - 1e-9 * i;
+  fp64_probe_const_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(P, iters, out);
+  SKTB_KERNEL_OK();
+  if (flops_h) *flops_h = (int64_t)2 * 8 * iters * grid * kBlock;
+  return 0;
+}
+
 extern "C" int sktb_fp64_probe(int iters, double *out, int64_t *flops_h, void *stream) {
   SKTB_REQUIRE(out && iters > 0, "bad argument");
   const int grid = kNumSM * 8;

@@ -745,16 +745,19 @@ def launch_count() -> int:
     return int(_lib.load().sktb_launch_count())
 
 
-def fp64_peak_tflops(iters: int = 4096, reps: int = 5) -> float:
-    """Measured FP64 FMA throughput of this GPU (DFMA-chain probe, best of reps)."""
+def fp64_peak_tflops(iters: int = 4096, reps: int = 5, const_operand: bool = False) -> float:
+    """Measured FP64 FMA throughput of this GPU (DFMA-chain probe, best of reps).
+    ``const_operand``: the multiplier comes from the constant bank (uniform
+    register operand), as in the grid operator."""
     out = torch.empty(148 * 8 * 256, dtype=F64, device="cuda")
     flops = C.c_int64()
     lib = _lib.load()
+    fn = lib.sktb_fp64_probe_const if const_operand else lib.sktb_fp64_probe
     best = 0.0
     for _ in range(reps + 1):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _lib.check(lib.sktb_fp64_probe(int(iters), _ptr(out), C.cast(C.byref(flops), C.c_void_p), _stream()))
+        _lib.check(fn(int(iters), _ptr(out), C.cast(C.byref(flops), C.c_void_p), _stream()))
         b.record()
         torch.cuda.synchronize()
         best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)

@@ -113,6 +113,7 @@ SIGNATURES = {
     "sktb_enforce_rhs": [i64, c_f64p, c_f64p, c_u8p, c_f64p, c_f64p, c_stream],
     "sktb_flush_l2": [C.c_void_p, i64, c_stream],
     "sktb_fp64_probe": [i32, c_f64p, C.c_void_p, c_stream],
+    "sktb_fp64_probe_const": [i32, c_f64p, C.c_void_p, c_stream],
 }
 _RESTYPE = {
     "sktb_last_error": C.c_char_p,
