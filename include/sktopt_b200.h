@@ -319,6 +319,14 @@ int sktb_interpolate_modulus(int64_t n, const double *rho, double E0,
 int sktb_element_energy(const sktb_mesh *m, int dpn, const double *unit_ke,
                         const int32_t *elem_class, const double *scale,
                         const double *u, double *out, void *stream);
+/* out[e] = factor scale[e] u_e^T Ke0[class[e]] v_e : the elemental integrals of
+ * grad T . grad lambda behind energy_multi_load for the heat_exchange and
+ * averaged_temp objectives (fea/solver_heat.py:327-383,518-549; scale = NULL,
+ * factor = 1 there)                                                           */
+int sktb_element_bilinear(const sktb_mesh *m, int dpn, const double *unit_ke,
+                          const int32_t *elem_class, const double *scale,
+                          const double *u, const double *v, double factor,
+                          double *out, void *stream);
 /* K8: g = -2 U dE/drho / max(E,1e-12) * dH  (core/derivatives.py:42-68,
  * core/projection.py:80-118, common_density.py:1083-1097); dH may be NULL.    */
 int sktb_dc_drho(int64_t n, const double *rho_proj, const double *energy,
@@ -375,6 +383,19 @@ int sktb_robin_explicit_local(const sktb_mesh *m, int nqp,
                               const double *rho_node, const double *T, double h,
                               double T_env, double p, double q,
                               double *out_local, void *stream);
+/* heat_exchange objective on the interface measure |grad rho_n|
+ * (fea/solver_heat.py:306-324,385-413,416-446): per element den_e = int |g|,
+ * num_e = int -T_env h (T - T_env) |g| (num_out / T may be NULL) and the
+ * element-local adjoint load local[a][e] = int -T_env heff |g| N_a with heff
+ * interpolated from the nodal values h rho_n^p (1-rho_n)^q (local_out may be
+ * NULL)                                                                        */
+int sktb_heat_exchange_local(const sktb_mesh *m, int nqp,
+                             const int32_t *elem_class, const double *N_tab,
+                             const double *G_tab, const double *dx_tab,
+                             const double *rho_node, const double *T,
+                             double p, double q, double h, double T_env,
+                             double *den_out, double *num_out,
+                             double *local_out, void *stream);
 /* out[n] = sum over the node's (element, local) slots of local[a][e]
  * (optionally divided by divisor[n]): load-vector style assembly              */
 int sktb_local_to_nodes(const sktb_mesh *m, const double *local,

@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(kBlock)
                           const double *__restrict__ unit_ke,
                           const double *__restrict__ scale,
                           const double *__restrict__ u,
+                          const double *__restrict__ v, double factor,
                           double *__restrict__ out) {
   constexpr int NDE = D * NEN;
   static_assert(NDE <= 32, "element dofs must fit in one warp");
@@ -550,16 +551,19 @@ __global__ void __launch_bounds__(kBlock)
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t e = warp; e < n_elem; e += nwarps) {
-    double ue = 0.0;
+    double ue = 0.0, ve = 0.0;
     if (lane < NDE) {
       const int a = lane / D, c = lane - a * D;
-      ue = u[(int64_t)D * conn[(int64_t)a * n_elem + e] + c];
+      const int64_t dof = (int64_t)D * conn[(int64_t)a * n_elem + e] + c;
+      ue = u[dof];
+      ve = v ? v[dof] : ue;
     }
     // the stiffness / conduction element matrices annihilate translations:
     // subtracting local node 0 removes the cancellation a large mean value
     // (e.g. T ~ 600 K with 0.1 K variation) would cause in u^T Ke u
     ue -= __shfl_sync(0xffffffffu, ue, lane % D);
-    if (lane >= NDE) ue = 0.0;
+    ve -= __shfl_sync(0xffffffffu, ve, lane % D);
+    if (lane >= NDE) ue = ve = 0.0;
     const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
     const double *ke = unit_ke + cls * (NDE * NDE);
     double acc = 0.0;
@@ -569,26 +573,51 @@ __global__ void __launch_bounds__(kBlock)
       const bool ok = ent < NDE * NDE;
       const int r = ok ? ent / NDE : 0, c = ok ? ent - r * NDE : 0;
       const double ur = __shfl_sync(0xffffffffu, ue, r);
-      const double uc = __shfl_sync(0xffffffffu, ue, c);
+      const double uc = __shfl_sync(0xffffffffu, ve, c);
       if (ok) acc += ur * __ldg(&ke[ent]) * uc;
     }
     acc = warp_sum(acc);
-    if (lane == 0) out[e] = 0.5 * (scale ? scale[e] : 1.0) * acc;
+    if (lane == 0) out[e] = factor * (scale ? scale[e] : 1.0) * acc;
   }
 }
+
+static int element_form(const sktb_mesh *m, int dpn, const double *unit_ke,
+                        const int32_t *elem_class, const double *scale,
+                        const double *u, const double *v, double factor,
+                        double *out, void *stream);
 
 extern "C" int sktb_element_energy(const sktb_mesh *m, int dpn,
                                    const double *unit_ke,
                                    const int32_t *elem_class,
                                    const double *scale, const double *u,
                                    double *out, void *stream) {
+  return element_form(m, dpn, unit_ke, elem_class, scale, u, nullptr, 0.5, out,
+                      stream);
+}
+
+extern "C" int sktb_element_bilinear(const sktb_mesh *m, int dpn,
+                                     const double *unit_ke,
+                                     const int32_t *elem_class,
+                                     const double *scale, const double *u,
+                                     const double *v, double factor,
+                                     double *out, void *stream) {
+  SKTB_REQUIRE(v, "null argument");
+  return element_form(m, dpn, unit_ke, elem_class, scale, u, v, factor, out,
+                      stream);
+}
+
+static int element_form(const sktb_mesh *m, int dpn, const double *unit_ke,
+                        const int32_t *elem_class, const double *scale,
+                        const double *u, const double *v, double factor,
+                        double *out, void *stream) {
   SKTB_REQUIRE(m && unit_ke && u && out, "null argument");
   SKTB_REQUIRE(dpn == 1 || dpn == 3, "dpn must be 1 or 3");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(m->n_elem * 32, kBlock, 16);
 #define LAUNCH(D, NEN)                                                        \
   element_energy_kernel<D, NEN><<<grid, kBlock, 0, st>>>(                     \
-      m->n_elem, m->n_nodes, m->conn, elem_class, unit_ke, scale, u, out)
+      m->n_elem, m->n_nodes, m->conn, elem_class, unit_ke, scale, u, v,       \
+      factor, out)
   if (m->nen == 8 && dpn == 3)
     LAUNCH(3, 8);
   else if (m->nen == 8 && dpn == 1)
@@ -1001,6 +1030,99 @@ extern "C" int sktb_robin_explicit_local(const sktb_mesh *m, int nqp,
     robin_explicit_local_kernel<4><<<grid, kBlock, 0, st>>>(
         m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, T,
         h, T_env, p, q, out_local);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+// K18: heat-exchange objective pieces on the interface measure |grad rho_n|
+// (fea/solver_heat.py:306-324 numerator, :385-392 denominator, :395-413 adjoint
+// load).  Per element:
+//   den_e   = sum_q |g| dx
+//   num_e   = sum_q -T_env h (T_q - T_env) |g| dx                 (T != NULL)
+//   local_a = sum_q -T_env heff_q |g| N_a dx, heff_q = sum_b N_b heff_b with
+//             the NODAL values heff_b = h rho_b^p (1-rho_b)^q  (local != NULL)
+template <int NEN>
+__global__ void __launch_bounds__(kBlock)
+    heat_exchange_local_kernel(int64_t n_elem, int nqp,
+                               const int32_t *__restrict__ conn,
+                               const int32_t *__restrict__ elem_class,
+                               const double *__restrict__ Ntab,
+                               const double *__restrict__ Gtab,
+                               const double *__restrict__ dxtab,
+                               const double *__restrict__ rho_n,
+                               const double *__restrict__ T, double p,
+                               double q, double h,
+                               double T_env, double *__restrict__ den_out,
+                               double *__restrict__ num_out,
+                               double *__restrict__ local_out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < n_elem; e += stride) {
+    double r[NEN], t[NEN], hf[NEN], acc[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) {
+      const int32_t nd = conn[(int64_t)a * n_elem + e];
+      r[a] = rho_n[nd];
+      t[a] = T ? T[nd] : 0.0;
+      hf[a] = local_out ? h * pow(r[a], p) * pow(1.0 - r[a], q) : 0.0;
+      acc[a] = 0.0;
+    }
+    const int64_t cls = elem_class ? (int64_t)elem_class[e] : e;
+    double den = 0.0, num = 0.0;
+    for (int k = 0; k < nqp; ++k) {
+      const double *Nq = Ntab + (cls * nqp + k) * NEN;
+      const double *Gq = Gtab + (cls * nqp + k) * NEN * 3;
+      const double dx = dxtab[cls * nqp + k];
+      double tq = 0.0, hq = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        const double Na = __ldg(&Nq[a]);
+        tq += Na * t[a];
+        hq += Na * hf[a];
+        g0 += __ldg(&Gq[a * 3 + 0]) * r[a];
+        g1 += __ldg(&Gq[a * 3 + 1]) * r[a];
+        g2 += __ldg(&Gq[a * 3 + 2]) * r[a];
+      }
+      const double iface = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+      den += iface * dx;
+      num += -T_env * h * (tq - T_env) * iface * dx;
+      const double w = -T_env * hq * iface * dx;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) acc[a] += w * __ldg(&Nq[a]);
+    }
+    den_out[e] = den;
+    if (num_out) num_out[e] = num;
+    if (local_out) {
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) local_out[(int64_t)a * n_elem + e] = acc[a];
+    }
+  }
+}
+
+extern "C" int sktb_heat_exchange_local(const sktb_mesh *m, int nqp,
+                                        const int32_t *elem_class,
+                                        const double *N_tab,
+                                        const double *G_tab,
+                                        const double *dx_tab,
+                                        const double *rho_node,
+                                        const double *T, double p,
+                                        double q, double h,
+                                        double T_env, double *den_out,
+                                        double *num_out, double *local_out,
+                                        void *stream) {
+  SKTB_REQUIRE(m && N_tab && G_tab && dx_tab && rho_node && den_out,
+               "null argument");
+  SKTB_REQUIRE(!num_out || T, "numerator needs the temperature field");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(m->n_elem);
+  if (m->nen == 8)
+    heat_exchange_local_kernel<8><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, T,
+        p, q, h, T_env, den_out, num_out, local_out);
+  else
+    heat_exchange_local_kernel<4><<<grid, kBlock, 0, st>>>(
+        m->n_elem, nqp, m->conn, elem_class, N_tab, G_tab, dx_tab, rho_node, T,
+        p, q, h, T_env, den_out, num_out, local_out);
   SKTB_KERNEL_OK();
   return 0;
 }

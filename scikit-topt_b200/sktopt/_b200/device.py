@@ -215,6 +215,36 @@ class DeviceMesh:
         )
         return out
 
+    def element_bilinear(self, dpn, unit_ke, scale, u, v, factor=1.0, out=None):
+        """out[e] = factor * scale[e] * u_e^T Ke0 v_e (scale may be None)."""
+        if out is None:
+            out = torch.empty(self.n_elem, dtype=F64, device="cuda")
+        _lib.check(
+            self.lib.sktb_element_bilinear(
+                self.handle, dpn, _ptr(unit_ke), _ptr(self.elem_class), _ptr(scale),
+                _ptr(u), _ptr(v), float(factor), _ptr(out), _stream(),
+            )
+        )
+        return out
+
+    def heat_exchange_local(self, tables, rho_node, T, p, q, h, T_env,
+                            want_num=True, want_local=True):
+        """(den_e [n_elem], num_e [n_elem] | None, local [nen, n_elem] | None)."""
+        N, G, dx, _ = tables
+        nq = N.shape[1]
+        den = torch.empty(self.n_elem, dtype=F64, device="cuda")
+        num = torch.empty(self.n_elem, dtype=F64, device="cuda") if want_num else None
+        local = (torch.empty((self.nen, self.n_elem), dtype=F64, device="cuda")
+                 if want_local else None)
+        _lib.check(
+            self.lib.sktb_heat_exchange_local(
+                self.handle, nq, _ptr(self.elem_class), _ptr(N), _ptr(G), _ptr(dx),
+                _ptr(rho_node), _ptr(T), float(p), float(q), float(h), float(T_env),
+                _ptr(den), _ptr(num), _ptr(local), _stream(),
+            )
+        )
+        return den, num, local
+
     # -- heat: quadrature tables and Robin kernels -----------------------------
     def geom_tables(self, X: np.ndarray, W: np.ndarray):
         """(N [cls,q,a], G [cls,q,a,3], dx [cls,q]) CUDA tensors."""

@@ -17,8 +17,18 @@ Follows reference ``fea/solver_heat.py`` for ``objective="compliance"``
   sum_a g[t_a] / count[t_a] (:575-625, :928-980).
 
 The reference solves with a sparse LU; here the enforced system goes through
-the device Jacobi-PCG.  The ``heat_exchange`` / ``averaged_temp`` objectives are
-the next scope row and raise ``NotImplementedError``.
+the device Jacobi-PCG.
+
+``objective="heat_exchange"`` (:306-324, :385-446, :791-869) and
+``"averaged_temp"`` (:871-884) reuse the same operator: J = J_num / J_den on the
+interface measure |grad rho_n| (``CellBasis`` with skfem's *default* quadrature,
+not the task's), resp. J = sum(T); the adjoint systems K_e lambda = dJ/dT are
+enforced with the *same* Dirichlet values as the state (reference quirk kept:
+``solve_heat_system_multi`` is called with ``dirichlet_values_list`` :838-845),
+and ``energy_multi_load`` returns the unit-conductivity elemental integrals of
+grad T . grad lambda (:327-383, :518-549).  ``compliance_sensitivity_multi_load``
+stays the SIMP conduction term for those objectives (:962-963), exactly like
+the reference, whose optimiser always prefers it (common_density.py:1069-1082).
 """
 from __future__ import annotations
 
@@ -90,6 +100,17 @@ class _HeatDevice:
         self.emit_real = dev.to_dev(emit0)
         self.tables = dm.geom_tables(basis.X, basis.W)
         self.scale_v = None
+        self._cell_tables = None
+        self.ones_e = None
+
+    def cell_tables(self):
+        """Quadrature tables of ``skfem.CellBasis(mesh, elem)`` with the default
+        integration order (reference :793), used by the heat_exchange forms."""
+        if self._cell_tables is None:
+            from sktopt._fem.basis import Basis
+            cb = Basis(self.task.basis.mesh, self.task.basis.elem)
+            self._cell_tables = self.eng.dm.geom_tables(cb.X, cb.W)
+        return self._cell_tables
 
 
 class FEM_SimpLinearHeatConduction():
@@ -123,11 +144,9 @@ class FEM_SimpLinearHeatConduction():
     def engine(self):
         return self._device().eng
 
-    def _require_compliance(self):
-        if self.task.objective != "compliance":
-            raise NotImplementedError(
-                f"heat objective '{self.task.objective}' is not built yet "
-                "(SURVEY.md 8f); only 'compliance' runs on the GPU path")
+    def _check_objective(self):
+        if self.task.objective not in ("compliance", "heat_exchange", "averaged_temp"):
+            raise ValueError(f"Unknown objective: {self.task.objective}")
 
     def _robin_scalar(self):
         h, T_env = self.task.robin_coefficient, self.task.robin_bc_value
@@ -138,7 +157,7 @@ class FEM_SimpLinearHeatConduction():
 
     def objectives_multi_load(self, rho, p: float, u_dofs, timer=None,
                               force_scale: float = 1.0) -> np.ndarray:
-        self._require_compliance()
+        self._check_objective()
         _check_solver(self.solver_config.solver)
         st = self._device()
         eng, dm = st.eng, st.eng.dm
@@ -160,7 +179,7 @@ class FEM_SimpLinearHeatConduction():
             # virtual load = T_env * V * 1 (shape functions sum to one)
             dev.spmv(eng.row_ptr, eng.col_idx, st.V, st.ones, 1, out=st.tmp)
             dev.axpby(T_env, st.tmp, 1.0, st.emit)
-            if not self._warned_robin_compliance:
+            if self.task.objective == "compliance" and not self._warned_robin_compliance:
                 logger.warning(
                     "Heat objective='compliance' with Robin boundaries evaluates "
                     "T^T K T, which includes Dirichlet reaction work.")
@@ -171,23 +190,103 @@ class FEM_SimpLinearHeatConduction():
         eng.update_preconditioner(st.K_e)
 
         n_loads = len(st.xD)
-        J = np.empty(n_loads)
+        Ts = []
         for i in range(n_loads):
-            dev.spmv(eng.row_ptr, eng.col_idx, st.K, st.xD[i], 1, out=st.tmp)
-            dev.enforce_rhs(st.emit, st.tmp, eng.dir_mask, st.xD[i], out=eng.rhs)
-            # start from the exact Dirichlet values: their identity rows then
-            # have zero residual for the whole solve (as exact as the LU)
-            x0 = eng.solution(i)
-            dev.enforce_rhs(x0, None, eng.dir_mask, st.xD[i], out=x0)
-            T = eng.solve(eng.rhs, i, self.solver_config.rtol,
-                          self.solver_config.maxiter, vals=st.K_e)
-            dev.spmv(eng.row_ptr, eng.col_idx, st.K, T, 1, out=st.tmp)
-            J[i] = dev.dot(T, st.tmp)
-            if _is_dev(u_dofs):
-                (u_dofs[:, i] if u_dofs.ndim == 2 else u_dofs).copy_(T)
+            T = self._solve_enforced(st.emit, i, slot=i)
+            Ts.append(T)
+            self._store(u_dofs, i, T)
+
+        objective = self.task.objective
+        if objective == "compliance":
+            J = np.empty(n_loads)
+            for i, T in enumerate(Ts):
+                dev.spmv(eng.row_ptr, eng.col_idx, st.K, T, 1, out=st.tmp)
+                J[i] = dev.dot(T, st.tmp)
+            self.λ_all = -2.0 * u_dofs
+            return J
+        if objective == "heat_exchange":
+            return self._heat_exchange(st, rho_d, p, u_dofs, Ts)
+        # averaged_temp (:871-884): J = sum(T), adjoint load = ones
+        J = np.array([dev.dot(T, st.ones) for T in Ts])
+        lam = self._new_like(u_dofs)
+        for i in range(n_loads):
+            self._store(lam, i, self._solve_enforced(st.ones, i, slot=n_loads + i))
+        self.λ_all = lam
+        return J
+
+    # -- helpers of objectives_multi_load --------------------------------------
+    def _solve_enforced(self, load_vec, i: int, slot: int):
+        """K_e x = enforce(load_vec; D, x_D = Dirichlet value of load i)
+        (``solve_heat_system_multi`` :136-200); ``slot`` selects the warm-start
+        vector (state and adjoint solves keep separate ones)."""
+        st = self._device()
+        eng = st.eng
+        dev.spmv(eng.row_ptr, eng.col_idx, st.K, st.xD[i], 1, out=st.tmp)
+        dev.enforce_rhs(load_vec, st.tmp, eng.dir_mask, st.xD[i], out=eng.rhs)
+        # start from the exact Dirichlet values: their identity rows then
+        # have zero residual for the whole solve (as exact as the LU)
+        x0 = eng.solution(slot)
+        dev.enforce_rhs(x0, None, eng.dir_mask, st.xD[i], out=x0)
+        return eng.solve(eng.rhs, slot, self.solver_config.rtol,
+                         self.solver_config.maxiter, vals=st.K_e)
+
+    @staticmethod
+    def _store(dst, i: int, vec):
+        if _is_dev(dst):
+            (dst[:, i] if dst.ndim == 2 else dst).copy_(vec)
+        else:
+            dst[:, i] = vec.cpu().numpy()
+
+    @staticmethod
+    def _new_like(u_dofs):
+        return torch.zeros_like(u_dofs) if _is_dev(u_dofs) else np.zeros_like(u_dofs)
+
+    def _heat_exchange(self, st, rho_d, p, u_dofs, Ts):
+        """heat_exchange branch of objectives_multi_load (:791-869)."""
+        if self.task.robin_coefficient is None:
+            raise RuntimeError("heat_exchange objective requires Robin boundary data.")
+        eng, dm = st.eng, st.eng.dm
+        h, T_env = self._robin_scalar()
+        n_loads = len(Ts)
+        tab = st.cell_tables()
+        # st.rho_n was filled by the virtual Robin assembly above; the kernel
+        # forms h_eff nodal = h rho_n^p (1 - rho_n)^q itself (:825-826)
+        den_e, _, local = dm.heat_exchange_local(tab, st.rho_n, None, p, self.q, h, T_env,
+                                                 want_num=False, want_local=True)
+        if st.ones_e is None:
+            st.ones_e = torch.ones_like(den_e)
+        ones_e = st.ones_e
+        J_den = dev.dot(den_e, ones_e)
+        if J_den <= 1e-16:
+            self.λ_all = self._new_like(u_dofs)
+            return np.zeros(n_loads)
+        J = np.empty(n_loads)
+        for i, T in enumerate(Ts):
+            _, num_e, _ = dm.heat_exchange_local(tab, st.rho_n, T, p, self.q, h, T_env,
+                                                 want_num=True, want_local=False)
+            J[i] = dev.dot(num_e, ones_e) / J_den
+        rhs = torch.empty_like(st.tmp)
+        dev.affine(1.0 / J_den, dm.local_to_nodes(local), 0.0, None, 0.0, rhs)   # dJ/dT (:830)
+        lam = self._new_like(u_dofs)
+        lam_d = [self._solve_enforced(rhs, i, slot=n_loads + i) for i in range(n_loads)]
+        w = float(getattr(self.task, "avg_temp_weight", 0.0))
+        if w != 0.0:
+            avg = np.array([dev.dot(T, st.ones) for T in Ts])
+            lam_avg = [self._solve_enforced(st.ones, i, slot=2 * n_loads + i)
+                       for i in range(n_loads)]
+            if n_loads > 1:
+                hx_scale = max(float(np.mean(np.abs(J))), 1.0e-12)
+                avg_scale = max(float(np.mean(np.abs(avg))), 1.0e-12)
+                J = J / hx_scale + w * (avg / avg_scale)
+                mix = (1.0 / hx_scale, w / avg_scale)
             else:
-                u_dofs[:, i] = T.cpu().numpy()
-        self.λ_all = -2.0 * u_dofs
+                J = J + w * avg
+                mix = (1.0, w)
+            lam_d = [dev.affine(mix[0], l, mix[1], la, 0.0, torch.empty_like(l))
+                     for l, la in zip(lam_d, lam_avg)]
+        for i, l in enumerate(lam_d):
+            self._store(lam, i, l)
+        self.λ_all = lam
         return J
 
     def _energy_dev(self, rho_d, p, u_dofs):
@@ -206,9 +305,25 @@ class FEM_SimpLinearHeatConduction():
         return out, Ts
 
     def energy_multi_load(self, rho, p: float, u_dofs):
-        self._require_compliance()
-        out, _ = self._energy_dev(dev.to_dev(rho), p, u_dofs)
-        return out.t() if _is_dev(u_dofs) else out.t().cpu().numpy()
+        self._check_objective()
+        if self.task.objective == "compliance":
+            out, _ = self._energy_dev(dev.to_dev(rho), p, u_dofs)
+            return out.t() if _is_dev(u_dofs) else out.t().cpu().numpy()
+        # heat_exchange / averaged_temp: elemental integrals of grad T . grad lambda
+        # with unit conductivity (:327-383, :518-549, :886-917)
+        if self.λ_all is None:
+            raise RuntimeError("adjoint field λ_all is not computed.")
+        eng = self._device().eng
+        on_dev = _is_dev(u_dofs)
+        U2 = u_dofs if u_dofs.ndim == 2 else u_dofs[:, None]
+        L2 = self.λ_all if self.λ_all.ndim == 2 else self.λ_all[:, None]
+        out = torch.empty((U2.shape[1], eng.n_elem), dtype=dev.F64, device="cuda")
+        for i in range(U2.shape[1]):
+            Ti = U2[:, i].contiguous() if on_dev else dev.to_dev(np.ascontiguousarray(U2[:, i]))
+            Li = (L2[:, i].contiguous() if _is_dev(L2)
+                  else dev.to_dev(np.ascontiguousarray(L2[:, i])))
+            eng.dm.element_bilinear(1, eng.unit_ke, None, Ti, Li, 1.0, out=out[i])
+        return out.t() if on_dev else out.t().cpu().numpy()
 
     def compliance_sensitivity_multi_load(self, rho, p: float, u_dofs):
         st = self._device()

@@ -125,6 +125,30 @@ def test_heaviside_and_bisection(toy_oracle):
     assert np.all(np.isfinite(h["compliance"]))
 
 
+def test_heat_exchange_forms_known_answers():
+    """rho_n linear in x => |grad rho| = b everywhere: J_den = b V, J_num =
+    -T_env h (T0 - T_env) b V for a uniform T0, the adjoint load sums to
+    -T_env b int h_eff; grad T . grad lambda of two linear fields = (gT.gL) V."""
+    from oracle import heat as oheat
+    p, t = omesh.box_hex(2.0, 1.0, 1.0, 0.25)
+    a, b, h, T_env, T0, pw, q = 0.2, 0.3, 4e-5, 300.0, 450.0, 3.0, 4
+    rho_n = a + b * p[0]
+    vol = 2.0
+    J_num, J_den, rhs = oheat.heat_exchange_forms(p, t, rho_n, np.full(p.shape[1], T0),
+                                                  h, T_env, pw, q)
+    np.testing.assert_allclose(J_den, b * vol, rtol=1e-12)
+    np.testing.assert_allclose(J_num, -T_env * h * (T0 - T_env) * b * vol, rtol=1e-12)
+    # int of the nodal interpolant of h_eff: trapezoid in x on the uniform grid
+    xs = np.unique(p[0])
+    he = h * (a + b * xs) ** pw * (1.0 - a - b * xs) ** q
+    integral = np.sum(0.5 * (he[1:] + he[:-1]) * np.diff(xs)) * 1.0 * 1.0
+    np.testing.assert_allclose(rhs.sum(), -T_env * b * integral, rtol=1e-12)
+    gT, gL = np.array([1.0, -2.0, 0.5]), np.array([0.3, 0.1, -0.7])
+    U = oheat.grad_dot_energy(p, t, gT @ p, gL @ p, 2)
+    np.testing.assert_allclose(U.sum(), float(gT @ gL) * vol, rtol=1e-12)
+    np.testing.assert_allclose(U, float(gT @ gL) * 0.25 ** 3, rtol=1e-11)
+
+
 def test_oracle_is_deterministic(toy_oracle):
     o, pr = toy_oracle
     a = optim.run(pr, "logmoc", max_iters=3, vol_frac=0.6)
