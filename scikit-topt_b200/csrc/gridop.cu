@@ -45,18 +45,50 @@ struct GridParams {
   const uint8_t *dmask;   // per node
 };
 
+// DPN = 1, uniform coefficient: the element sums collapse to a 27-point stencil.
+// Kept split by the y-position of the contributing elements so that the y-ends
+// of a grid line (which sit in the middle of a warp) need no branch:
+//   w0[(dz+1)*3+(dx+1)][k]: elements BELOW the node in y (oy = 0), neighbour dy = k-1
+//   w1[(dz+1)*3+(dx+1)][k]: elements ABOVE (oy = 1), neighbour dy = k
+struct ScalarStencil {
+  double w0[9][2];
+  double w1[9][2];
+};
 struct sktb_gridop {
   int dpn = 3;
   GridParams<3> P3;
   GridParams<1> P1;
+  ScalarStencil W1;
   int device = 0;
   int64_t n_nodes = 0;
   bool fields_set = false;
   bool direct = false;  // untiled kernel (DPN = 3 only; default there)
   bool split = false;   // two warps per node (SKTB_GRIDOP_SPLIT=1)
   bool shfl = true;     // y-neighbours by warp shuffle (SKTB_GRIDOP_SHFL=0: all from L1)
+  bool scalar_direct = true;  // DPN = 1: untiled stencil kernel (SKTB_GRIDOP_SCALAR_TILED=1: tiled)
   size_t smem = 0;
 };
+
+static ScalarStencil make_scalar_stencil(const double *ke) {
+  ScalarStencil W;
+  for (int i = 0; i < 9; ++i) W.w0[i][0] = W.w0[i][1] = W.w1[i][0] = W.w1[i][1] = 0.0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int o = 0; o < 8; ++o) {
+          const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+          const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+          if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+          const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+          const int cb = bx + 2 * by + 4 * bz;
+          const int line = (dz + 1) * 3 + (dx + 1);
+          if (oy == 0)
+            W.w0[line][by] += ke[ca * 8 + cb];  // by = dy + 1: dy = -1 -> 0, dy = 0 -> 1
+          else
+            W.w1[line][by] += ke[ca * 8 + cb];  // by = dy: dy = 0 -> 0, dy = +1 -> 1
+        }
+  return W;
+}
 
 __device__ __forceinline__ int clampi(int v, int hi) {
   return v < 0 ? 0 : (v > hi ? hi : v);
@@ -693,6 +725,120 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// ------------------------------------- scalar stencil kernel (DPN = 1) ------
+// One thread per node, nodes of a warp consecutive along y (the same blocked
+// assignment and shuffle scheme as hexgrid_apply_shfl_kernel): each of the 9
+// neighbour lines costs one coalesced load + two shuffles.  Nodes whose eight
+// elements all exist in x and z, with no fixed node around and a uniform
+// coefficient (scale == NULL: the Helmholtz operator M + r^2 K), take the
+// 36-FMA stencil W; grid faces, the neighbourhood of fixed nodes and variable
+// coefficients take the general per-element sum (64 FMA + 8 for the scale).
+// Fixed nodes: inputs read as 0, outputs pass x through (identity rows/columns).
+template <bool DOT>
+__global__ void __launch_bounds__(kBlock, 3)
+    scalar_grid_apply_kernel(const __grid_constant__ GridParams<1> P,
+                             const __grid_constant__ ScalarStencil W, int64_t node0,
+                             int64_t n_loc, const double *__restrict__ x,
+                             double *__restrict__ y, const double *__restrict__ dotv,
+                             double *partials, unsigned int *ticket, double *dot_out,
+                             const PcgScalars *S) {
+  if (S && S->rr <= S->tol2) return;
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_total = (int64_t)npx * npy * npz;
+  double dot = 0.0;
+  const int64_t n_pad = (n_loc + 31) / 32 * 32;  // whole warps run every trip (shuffles)
+  const int64_t trips = (n_pad + kBlock - 1) / kBlock;
+  const int64_t per_cta = (trips + gridDim.x - 1) / gridDim.x;
+  const int64_t r_end = min(n_pad, (int64_t)(blockIdx.x + 1) * per_cta * kBlock);
+  for (int64_t r = (int64_t)blockIdx.x * per_cta * kBlock + threadIdx.x; r < r_end;
+       r += kBlock) {
+    const bool live = r < n_loc;
+    const int64_t n = node0 + r;
+    const int64_t nc = n < n_total ? n : n_total - 1;
+    const int iy = (int)(nc % npy);
+    const int64_t t = nc / npy;
+    const int ix = (int)(t % npx);
+    const int iz = (int)(t / npx);
+    const unsigned dm = P.dmask[nc];
+    const bool fast = !P.scale && !(dm & 8u) && ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1;
+    double a0 = 0.0, a1 = 0.0;  // fast path: elements below / above in y
+    double pe[8];               // general path: per-element sums
+#pragma unroll
+    for (int o = 0; o < 8; ++o) pe[o] = 0.0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int l = (dz + 1) * 3 + (dx + 1);
+        const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
+        const int64_t mc = (int64_t)npy * (kx + (int64_t)npx * kz) + iy;
+        double u[3];  // [dy + 1]
+        u[1] = __ldg(x + mc);
+        u[0] = __shfl_up_sync(0xffffffffu, u[1], 1);
+        u[2] = __shfl_down_sync(0xffffffffu, u[1], 1);
+        if (lane == 0 && iy > 0) u[0] = __ldg(x + mc - 1);
+        if (lane == 31 && iy < npy - 1) u[2] = __ldg(x + mc + 1);
+        // the y-ends of a line: the shuffled value belongs to another line and
+        // only ever meets a zero weight; make it a plain zero
+        if (iy == 0) u[0] = 0.0;
+        if (iy == npy - 1) u[2] = 0.0;
+        if (fast) {
+          a0 = fma(W.w0[l][0], u[0], a0);
+          a0 = fma(W.w0[l][1], u[1], a0);
+          a1 = fma(W.w1[l][0], u[1], a1);
+          a1 = fma(W.w1[l][1], u[2], a1);
+        } else {
+          if (dm & 8u) {  // a fixed node somewhere around: mask the inputs
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+              const int ky = iy + dy;
+              if (ky < 0 || ky >= npy) continue;
+              if (P.dmask[mc + dy] & 1u) u[dy + 1] = 0.0;
+            }
+          }
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+              const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+              const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+              if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+              const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+              const int cb = bx + 2 * by + 4 * bz;
+              pe[o] = fma(P.ke[ca * 8 + cb], u[dy + 1], pe[o]);
+            }
+        }
+      }
+    }
+    double a;
+    if (fast) {
+      a = (iy > 0 ? a0 : 0.0) + (iy < npy - 1 ? a1 : 0.0);
+    } else {
+      a = 0.0;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int ex = ix - 1 + (o & 1), ey = iy - 1 + ((o >> 1) & 1), ez = iz - 1 + (o >> 2);
+        const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+        const double E =
+            ok ? (P.scale ? __ldg(&P.scale[ey + (int64_t)ny * (ex + (int64_t)nx * ez)]) : 1.0)
+               : 0.0;
+        a = fma(E, pe[o], a);
+      }
+    }
+    if (live) {
+      if (dm & 1u) a = x[n];
+      y[r] = a;
+      if (DOT) dot = fma(a, dotv[r], dot);
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
 // ------------------------------------------------------------------ launch --
 template <int DPN>
 static int launch_tiled(const sktb_gridop *op, const GridParams<DPN> &P, int64_t node0,
@@ -719,6 +865,17 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
                          const double *x, double *y, const double *dotv,
                          ReduceScratch *rs, double *dot_out, const PcgScalars *S,
                          cudaStream_t st) {
+  if (op->dpn == 1 && op->scalar_direct) {
+    const int g = grid_for(n_nodes, kBlock, 3);  // 3 resident CTAs per SM (80 registers)
+    if (dotv)
+      scalar_grid_apply_kernel<true><<<g, kBlock, 0, st>>>(
+          op->P1, op->W1, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
+    else
+      scalar_grid_apply_kernel<false><<<g, kBlock, 0, st>>>(
+          op->P1, op->W1, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr, S);
+    SKTB_KERNEL_OK();
+    return 0;
+  }
   if (op->dpn == 1)
     return launch_tiled<1>(op, op->P1, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
   if (!op->direct)
@@ -850,6 +1007,9 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   } else {
     fill(op->P1, 64);
     choose_tiles<1>(op->P1, &op->smem);
+    op->W1 = make_scalar_stencil(op->P1.ke);
+    const char *env4 = getenv("SKTB_GRIDOP_SCALAR_TILED");
+    op->scalar_direct = !(env4 && env4[0] == '1');
   }
   *out = op;
   return 0;

@@ -74,6 +74,7 @@ class _HelmholtzDevice:
         self.x_fixed = dev.to_dev(fm.astype(np.float64))  # x0: 1 on fixed nodes
         # matrix-free on uniform tensor grids, assembled CSR otherwise
         self.grid = None
+        self.fd = None
         if (isinstance(mesh, MeshHex) and self.dm.elem_class is not None and self.dm.n_class == 1
                 and os.environ.get("SKTOPT_B200_MATFREE", "1") != "0"):
             from sktopt.fea._multigrid import detect_tensor_grid, vertex_bits
@@ -87,6 +88,12 @@ class _HelmholtzDevice:
                 self.flags_free = self.gop_M.dmask
                 self.flags_fixed = self.gop_M.node_flags(fm)
                 self.gop_A = None
+                # systems without fixed nodes (every adjoint solve) are solved
+                # directly by fast diagonalisation; SKTOPT_B200_HELMHOLTZ_FD=0
+                # keeps the PCG for them too
+                if os.environ.get("SKTOPT_B200_HELMHOLTZ_FD", "1") != "0":
+                    from sktopt.filters._fastdiag import FastDiagHelmholtz
+                    self.fd = FastDiagHelmholtz(axes)
         if self.grid is None:
             self.row_ptr, self.col_idx = self.dm.dof_pattern(1)
             self.M = self.dm.assemble(1, ke_m)
@@ -114,6 +121,8 @@ class _HelmholtzDevice:
                                     None, dpn=1)
             self.gop_A.set_scale(None, dmask=self.flags_free)
             self.gop_A.inv_diag(out=self.minv)
+            if self.fd is not None:
+                self.fd.set_radius(float(r))
             if self.has_fixed:
                 self.gop_A.apply(self.x_fixed, out=self.c)
                 self.gop_A.set_scale(None, dmask=self.flags_fixed)
@@ -137,6 +146,9 @@ class _HelmholtzDevice:
 
     def _solve(self, enforced: bool, rhs, x):
         minv = self.minv_fwd if enforced else self.minv
+        if self.fd is not None and not enforced:
+            self.solve_iters.append(0)                    # direct solve
+            return self.fd.solve(rhs, out=x)
         if self.grid is not None:
             self.gop_A.set_scale(None, dmask=self.flags_fixed if enforced else self.flags_free)
             self.pcg.solve_grid(self.gop_A, minv, rhs, x, rtol=self.RTOL, maxiter=self.MAXITER,

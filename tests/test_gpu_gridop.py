@@ -109,13 +109,19 @@ def test_helmholtz_filter_matrix_free_matches_assembled(gpu, monkeypatch):
     rho = rng.uniform(0.05, 1.0, mesh.nelements)
     v = -rng.uniform(0.0, 1.0, mesh.nelements)
     out = {}
-    for flag in ("1", "0"):
+    # (matrix-free?, direct fast-diagonalisation solve of the adjoint system?)
+    for flag, fd in (("1", "1"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("SKTOPT_B200_MATFREE", flag)
+        monkeypatch.setenv("SKTOPT_B200_HELMHOLTZ_FD", fd)
         f = HelmholtzFilterNodal.from_defaults(mesh, vol, radius=0.35, design_mask=design)
         st = f._device()
         assert (st.grid is not None) == (flag == "1")
-        out[flag] = (f.forward(rho), f.gradient(v), list(st.solve_iters))
-    for k in (0, 1):
-        a, b = out["1"][k], out["0"][k]
-        assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b)))
-    assert out["1"][2] == out["0"][2]          # same PCG iteration counts
+        assert (st.fd is not None) == (flag == "1" and fd == "1")
+        out[flag + fd] = (f.forward(rho), f.gradient(v), list(st.solve_iters))
+    ref = out["01"]                            # assembled CSR + PCG
+    for key in ("11", "10"):
+        for k in (0, 1):
+            a, b = out[key][k], ref[k]
+            assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b)))
+    assert out["10"][2] == ref[2]              # same PCG iteration counts
+    assert out["11"][2] == [ref[2][0], 0]      # forward: PCG (fixed nodes); adjoint: direct
