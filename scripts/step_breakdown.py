@@ -28,9 +28,14 @@ opt.timer.reset()
 opt.timer.cuda_sync = True
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-opt.optimize_steps(n)
-torch.cuda.synchronize()
+per_step = []
+for _ in range(n):
+    ts = time.perf_counter()
+    opt.optimize_steps(1)
+    torch.cuda.synchronize()
+    per_step.append(round(1e3 * (time.perf_counter() - ts), 2))
 dt = (time.perf_counter() - t0) / n
+print("per-step ms", per_step)
 st = opt.timer.stats()
 print("ms/step", dt * 1e3)
 for k, v in sorted(st.items(), key=lambda kv: -kv[1]["total"]):

@@ -165,3 +165,38 @@ def test_fused_tail_matches_per_level_launches(gpu, monkeypatch):
         a[D] = 0.0
         out[flag] = eng.mg.vcycle(dev.to_dev(a)).cpu().numpy()
     assert np.max(np.abs(out["1"] - out["0"])) <= 1e-11 * np.max(np.abs(out["0"]))
+
+
+def test_projected_start_vector(gpu, monkeypatch):
+    """Galerkin projection of the new system onto the last solutions: the same
+    converged displacement as the plain warm start, in no more PCG iterations,
+    over a sequence of slowly changing density fields."""
+    sktopt, dev = gpu
+    from oracle import fem
+    rng = np.random.default_rng(3)
+    out = {}
+    for hist in ("1", "3"):
+        monkeypatch.setenv("SKTOPT_B200_START_HIST", hist)
+        tsk = sktopt.mesh.toy_problem.toy_base(0.45)
+        f = sktopt.fea.FEM_SimpLinearElasticity(tsk, 1e-3, solver_option="cg_pyamg")
+        rho = np.full(tsk.mesh.nelements, 0.5)
+        noise = np.random.default_rng(4).uniform(-1.0, 1.0, rho.size)
+        u = np.zeros((tsk.basis.N, 1))
+        its, comp = [], []
+        for k in range(5):
+            c = f.objectives_multi_load(np.clip(rho + 0.03 * k * noise, 0.05, 1.0), 3.0, u)
+            its.append(f.engine.pcg_log[-1][0])
+            comp.append(c[0])
+            assert f.engine.pcg_log[-1][1]
+        assert f.engine.start_hist == int(hist)
+        out[hist] = (its, comp, u[:, 0].copy(), tsk, np.clip(rho + 0.03 * 4 * noise, 0.05, 1.0))
+    print("PCG iterations: warm start", out["1"][0], "projected start", out["3"][0])
+    assert np.max(np.abs(np.array(out["1"][1]) / np.array(out["3"][1]) - 1.0)) <= 1e-7
+    assert sum(out["3"][0][1:]) <= sum(out["1"][0][1:])
+    tsk, rho4 = out["3"][3], out["3"][4]
+    K = fem.assemble_stiffness(tsk.mesh.p, tsk.mesh.t, rho4, tsk.E, tsk.E * 1e-3, 3.0, tsk.nu)
+    fl = tsk.neumann_linear if isinstance(tsk.neumann_linear, list) else [tsk.neumann_linear]
+    F = np.asarray(fl[0], dtype=float).copy()
+    K_e, f_e = fem.enforce(K, F, tsk.dirichlet_dofs)
+    u_ref, _, _ = fem.solve(K_e, f_e, "spsolve")
+    assert np.max(np.abs(out["3"][2] - u_ref)) <= 1e-6 * np.abs(u_ref).max()
