@@ -40,6 +40,23 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const double *dotv, sktb::ReduceScratch *rs,
                          double *dot_out, const PcgScalars *S, cudaStream_t st);
 
+// Damped-Jacobi sweep fused into the product (multigrid smoother):
+//   y = x + omega dinv (b - A x)     (y must not alias x)
+// launch_*_jacobi pick the same kernels with this epilogue switched on.
+struct JacobiEpi {
+  const double *b = nullptr;  // null: plain product
+  const double *dinv = nullptr;
+  double omega = 0.0;
+};
+int launch_spmv_bsr3_jacobi(int64_t n_nodes, const int32_t *node_ptr,
+                            const int32_t *node_col, const double *vals,
+                            const double *x, double *y, const JacobiEpi &epi,
+                            cudaStream_t st);
+int launch_spmv_bsr3_tma_jacobi(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                                const int32_t *node_ptr, const int32_t *node_col,
+                                const double *vals, const double *x, double *y,
+                                const JacobiEpi &epi, cudaStream_t st);
+
 // below ~8k nodes the bulk-async pipeline's fixed start-up (~10 us) exceeds the
 // work and the warp-per-node kernel is faster (measured: 2.7k nodes 13 -> 7 us,
 // 16k nodes 13 vs 17 us)

@@ -16,6 +16,9 @@
 
 #include <vector>
 
+#include <cstdlib>
+#include <utility>
+
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -59,6 +62,7 @@ struct sktb_mg {
   int nu_coarse = 20;
   bool fp32_level0 = false;  // single-precision products on a matrix-free level 0
   bool fused_tail = false;   // levels <= kTailMaxNodes nodes in one cooperative kernel
+  bool fused_sweeps = true;  // Jacobi sweeps of levels >= 1 fused into the product kernel
 };
 
 extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
@@ -66,6 +70,8 @@ extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
   sktb_mg *m = new sktb_mg();
   m->device = device;
   m->lv.resize(n_levels);
+  const char *env = getenv("SKTB_MG_FUSED_SWEEPS");
+  m->fused_sweeps = !(env && env[0] == '0');
   *out = m;
   return 0;
 }
@@ -900,6 +906,28 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
                           nullptr, nullptr, nullptr, nullptr, st);
 }
 
+// One damped-Jacobi sweep x <- x + omega D^-1 (b - A x) of an assembled,
+// replicated level (k >= 1) as ONE kernel: the product writes the new iterate
+// into l.tmp through the fused epilogue, then the two buffers swap roles.
+// Returns -1 when the level has no such kernel (caller: product + update).
+static int level_sweep(MgLevel &l, const double *b, double omega, cudaStream_t st) {
+  if (l.gop || !l.vals || l.node0 != 0 || l.n_global != l.n_nodes) return -1;
+  JacobiEpi epi;
+  epi.b = b;
+  epi.dinv = l.inv_diag;
+  epi.omega = omega;
+  int rc = l.n_nodes < kTmaMinNodes
+               ? -1
+               : launch_spmv_bsr3_tma_jacobi(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
+                                             l.node_col, l.vals, l.x, l.tmp, epi, st);
+  if (rc == -1)
+    rc = launch_spmv_bsr3_jacobi(l.n_nodes, l.node_ptr, l.node_col, l.vals, l.x, l.tmp, epi,
+                                 st);
+  if (rc) return rc;
+  std::swap(l.x, l.tmp);
+  return 0;
+}
+
 // z = M^-1 r : V(1,1) cycle.  Level 0 may be row-sharded (its x is a
 // full-length vector whose ghost slots are refreshed before every SpMV, the
 // restricted residual is all-reduced); levels >= 1 are replicated.
@@ -1016,6 +1044,14 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       }
     } else {
       for (int s = 1; s < l.nu; ++s) {  // extra pre-smoothing sweeps
+        if (k > 0 && m->fused_sweeps) {
+          const int rc = level_sweep(l, b, om, st);
+          if (rc == 0) {
+            xfull = x = l.x;  // the buffers swapped
+            continue;
+          }
+          if (rc != -1) return rc;
+        }
         if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
         if (level_spmv(l, xfull, l.tmp, st)) return 1;
         mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
@@ -1066,10 +1102,23 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       continue;
     }
     for (int s = 1; s < l.nu; ++s) {  // extra post-smoothing sweeps
+      if (k > 0 && m->fused_sweeps) {
+        const int rc = level_sweep(l, b, om, st);
+        if (rc == 0) {
+          xfull = x = l.x;
+          continue;
+        }
+        if (rc != -1) return rc;
+      }
       if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
       if (level_spmv(l, xfull, l.tmp, st)) return 1;
       mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
       SKTB_COUNT(1);
+    }
+    if (k > 0 && m->fused_sweeps) {  // last post-smoothing sweep
+      const int rc = level_sweep(l, b, om, st);
+      if (rc == 0) continue;
+      if (rc != -1) return rc;
     }
     if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
     if (k == 0 && l.gop) {

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kBlock, 6)
                      const double *__restrict__ x, double *__restrict__ y,
                      const double *__restrict__ dotv, double *partials,
                      unsigned int *ticket, double *dot_out,
-                     const PcgScalars *S) {
+                     const PcgScalars *S, const JacobiEpi J) {
   if (S && S->rr <= S->tol2) return;
   constexpr int U = 8;  // 8 * 32 = 256 >= 243 values of a 27-neighbour node
   const int lane = threadIdx.x & 31;
@@ -69,6 +69,11 @@ __global__ void __launch_bounds__(kBlock, 6)
     a2 = warp_sum(a2);
     if (lane == 0) {
       const int64_t r = 3 * n;
+      if (J.b) {  // fused damped-Jacobi sweep
+        a0 = x[r] + J.omega * J.dinv[r] * (J.b[r] - a0);
+        a1 = x[r + 1] + J.omega * J.dinv[r + 1] * (J.b[r + 1] - a1);
+        a2 = x[r + 2] + J.omega * J.dinv[r + 2] * (J.b[r + 2] - a2);
+      }
       y[r] = a0;
       y[r + 1] = a1;
       y[r + 2] = a2;
@@ -90,11 +95,23 @@ int launch_spmv_bsr3(int64_t n_nodes, const int32_t *node_ptr,
   if (dotv)
     spmv_bsr3_kernel<true><<<grid, kBlock, 0, st>>>(
         n_nodes, node_ptr, node_col, vals, x, y, dotv, rs->partials, rs->ticket,
-        dot_out, S);
+        dot_out, S, JacobiEpi());
   else
     spmv_bsr3_kernel<false><<<grid, kBlock, 0, st>>>(
         n_nodes, node_ptr, node_col, vals, x, y, nullptr, nullptr, nullptr,
-        nullptr, S);
+        nullptr, S, JacobiEpi());
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+int launch_spmv_bsr3_jacobi(int64_t n_nodes, const int32_t *node_ptr,
+                            const int32_t *node_col, const double *vals,
+                            const double *x, double *y, const JacobiEpi &epi,
+                            cudaStream_t st) {
+  const int grid = grid_for(n_nodes * 32, kBlock, 6);
+  spmv_bsr3_kernel<false><<<grid, kBlock, 0, st>>>(
+      n_nodes, node_ptr, node_col, vals, x, y, nullptr, nullptr, nullptr, nullptr,
+      nullptr, epi);
   SKTB_KERNEL_OK();
   return 0;
 }

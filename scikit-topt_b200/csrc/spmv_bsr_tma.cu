@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBlock, 2)
                          const double *__restrict__ x, double *__restrict__ y,
                          const double *__restrict__ dotv, double *partials,
                          unsigned int *ticket, double *dot_out,
-                         const PcgScalars *S) {
+                         const PcgScalars *S, const JacobiEpi J) {
   if (S && S->rr <= S->tol2) return;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = (uint64_t *)(smem + (size_t)kStages * kStageBytes);
@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(kBlock, 2)
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       if (quarter == 0 && ln < nn) {
         const int64_t r = 3 * (n_a + ln) + ri;
+        if (J.b) acc = x[r] + J.omega * J.dinv[r] * (J.b[r] - acc);  // fused Jacobi sweep
         y[r] = acc;
         if (DOT) dot += acc * dotv[r];
       }
@@ -233,11 +234,11 @@ bool g_attr_set[2] = {false, false};
 }  // namespace
 
 // returns 0 on success, -1 if the layout is not eligible (caller falls back)
-int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
-                         const int32_t *node_ptr, const int32_t *node_col,
-                         const double *vals, const double *x, double *y,
-                         const double *dotv, ReduceScratch *rs, double *dot_out,
-                         const PcgScalars *S, cudaStream_t st) {
+static int launch_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                      const int32_t *node_ptr, const int32_t *node_col,
+                      const double *vals, const double *x, double *y,
+                      const double *dotv, ReduceScratch *rs, double *dot_out,
+                      const PcgScalars *S, const JacobiEpi &epi, cudaStream_t st) {
   if (max_deg > kMaxDeg || n_nodes < 8 * kTile) return -1;
   const int64_t n_tiles = (n_nodes + kTile - 1) / kTile;
   int64_t g = (int64_t)kNumSM * 2;
@@ -258,13 +259,30 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
   if (dotv)
     spmv_bsr3_tma_kernel<true><<<grid, kBlock, kSmemBytes, st>>>(
         n_nodes, n_blocks, node_ptr, node_col, vals, x, y, dotv, rs->partials,
-        rs->ticket, dot_out, S);
+        rs->ticket, dot_out, S, epi);
   else
     spmv_bsr3_tma_kernel<false><<<grid, kBlock, kSmemBytes, st>>>(
         n_nodes, n_blocks, node_ptr, node_col, vals, x, y, nullptr, nullptr,
-        nullptr, nullptr, S);
+        nullptr, nullptr, S, epi);
   SKTB_KERNEL_OK();
   return 0;
+}
+
+int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                         const int32_t *node_ptr, const int32_t *node_col,
+                         const double *vals, const double *x, double *y,
+                         const double *dotv, ReduceScratch *rs, double *dot_out,
+                         const PcgScalars *S, cudaStream_t st) {
+  return launch_tma(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y, dotv, rs,
+                    dot_out, S, JacobiEpi(), st);
+}
+
+int launch_spmv_bsr3_tma_jacobi(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                                const int32_t *node_ptr, const int32_t *node_col,
+                                const double *vals, const double *x, double *y,
+                                const JacobiEpi &epi, cudaStream_t st) {
+  return launch_tma(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y, nullptr,
+                    nullptr, nullptr, nullptr, epi, st);
 }
 
 extern "C" int sktb_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
