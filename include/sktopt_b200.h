@@ -319,6 +319,12 @@ int sktb_interpolate_modulus(int64_t n, const double *rho, double E0,
 int sktb_element_energy(const sktb_mesh *m, int dpn, const double *unit_ke,
                         const int32_t *elem_class, const double *scale,
                         const double *u, double *out, void *stream);
+/* K7 for 3-dof hexahedral meshes whose elements share ONE geometry class (tensor
+ * grids): unit_ke_h = the 24x24 unit matrix on the HOST (passed as kernel
+ * parameters); same result as sktb_element_energy up to summation order        */
+int sktb_element_energy_hex_uniform(const sktb_mesh *m, const double *unit_ke_h,
+                                    const double *scale, const double *u,
+                                    double *out, void *stream);
 /* out[e] = factor scale[e] u_e^T Ke0[class[e]] v_e : the elemental integrals of
  * grad T . grad lambda behind energy_multi_load for the heat_exchange and
  * averaged_temp objectives (fea/solver_heat.py:327-383,518-549; scale = NULL,

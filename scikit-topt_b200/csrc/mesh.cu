@@ -631,6 +631,61 @@ static int element_form(const sktb_mesh *m, int dpn, const double *unit_ke,
   return 0;
 }
 
+// K7 on meshes with ONE hexahedral geometry class (every tensor grid): one thread
+// per element, the 24x24 unit matrix as kernel parameters (constant bank, like
+// the grid operator), upper triangle only: U_e = scale_e sum_i u_i (K_ii u_i / 2
+// + sum_{j>i} K_ij u_j) = 300 FMA per element instead of a warp per element.
+struct Ke24 {
+  double k[576];
+};
+__global__ void __launch_bounds__(kBlock, 3)
+    hex_energy_uniform_kernel(const __grid_constant__ Ke24 K, int64_t n_elem,
+                              const int32_t *__restrict__ conn,
+                              const double *__restrict__ scale,
+                              const double *__restrict__ u, double *__restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < n_elem; e += stride) {
+    double ue[24];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int64_t nd = conn[(int64_t)a * n_elem + e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ue[3 * a + c] = __ldg(&u[3 * nd + c]);
+    }
+    // the element matrix annihilates translations: remove local node 0 (same
+    // cancellation guard as element_energy_kernel)
+#pragma unroll
+    for (int a = 7; a >= 0; --a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ue[3 * a + c] -= ue[c];
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      double acc = 0.5 * K.k[i * 24 + i] * ue[i];
+#pragma unroll
+      for (int j = i + 1; j < 24; ++j) acc = fma(K.k[i * 24 + j], ue[j], acc);
+      tot = fma(ue[i], acc, tot);
+    }
+    out[e] = (scale ? scale[e] : 1.0) * tot;
+  }
+}
+
+extern "C" int sktb_element_energy_hex_uniform(const sktb_mesh *m,
+                                               const double *unit_ke_h,
+                                               const double *scale,
+                                               const double *u, double *out,
+                                               void *stream) {
+  SKTB_REQUIRE(m && unit_ke_h && u && out, "null argument");
+  SKTB_REQUIRE(m->nen == 8, "hexahedral meshes only");
+  Ke24 K;
+  for (int i = 0; i < 576; ++i) K.k[i] = unit_ke_h[i];
+  hex_energy_uniform_kernel<<<grid_for(m->n_elem), kBlock, 0, (cudaStream_t)stream>>>(
+      K, m->n_elem, m->conn, scale, u, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
 // ------------------------------------------------- Helmholtz transfer (K9) --
 __global__ void __launch_bounds__(kBlock)
     e2n_kernel(int64_t n_nodes, const int32_t *__restrict__ n2e_ptr,

@@ -7,6 +7,7 @@ the hand-written kernels in ``csrc/`` through ctypes.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -207,6 +208,19 @@ class DeviceMesh:
     def element_energy(self, dpn, unit_ke, scale, u, out=None):
         if out is None:
             out = torch.empty(self.n_elem, dtype=F64, device="cuda")
+        if (dpn == 3 and self.nen == 8 and self.elem_class is not None and self.n_class == 1
+                and os.environ.get("SKTOPT_B200_ENERGY_UNIFORM", "1") != "0"):
+            # one geometry class: thread-per-element kernel, Ke0 as kernel parameters
+            key = ("ke_host", unit_ke.data_ptr())
+            if key not in self._unit_ke:
+                self._unit_ke[key] = np.ascontiguousarray(
+                    unit_ke[0].detach().cpu().numpy().reshape(576), dtype=np.float64)
+            ke_h = self._unit_ke[key]
+            _lib.check(
+                self.lib.sktb_element_energy_hex_uniform(
+                    self.handle, ke_h.ctypes.data_as(C.c_void_p), _ptr(scale), _ptr(u),
+                    _ptr(out), _stream()))
+            return out
         _lib.check(
             self.lib.sktb_element_energy(
                 self.handle, dpn, _ptr(unit_ke), _ptr(self.elem_class), _ptr(scale),

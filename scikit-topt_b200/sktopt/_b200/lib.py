@@ -85,6 +85,7 @@ SIGNATURES = {
     "sktb_pcg_solve": [C.c_void_p, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_interpolate_modulus": [i64, c_f64p, f64, f64, f64, i32, c_f64p, c_stream],
     "sktb_element_energy": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_element_energy_hex_uniform": [C.c_void_p, C.c_void_p, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_element_bilinear": [C.c_void_p, i32, c_f64p, c_i32p, c_f64p, c_f64p, c_f64p, f64, c_f64p, c_stream],
     "sktb_heat_exchange_local": [C.c_void_p, i32, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, f64, f64, f64, f64, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_dc_drho": [i64, c_f64p, c_f64p, f64, f64, f64, i32, c_f64p, c_f64p, c_stream],
