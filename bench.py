@@ -193,6 +193,15 @@ def run_b200(args):
     n_solves0 = len(eng.pcg_log)
     sampler = ClockSampler(local)
 
+    if args.profile_step:
+        # one steady-state step inside a cudaProfilerStart/Stop window:
+        #   ncu --profile-from-start off --metrics gpu__time_duration.sum ... bench.py --profile-step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        opt.optimize_steps(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+
     # ---- timed region 1 (`value`): K steps, state resident in HBM, bracketed by
     # barrier + synchronize, timed on the device with CUDA events recorded on the
     # stream every kernel of the path is launched on (torch's current stream)
@@ -280,6 +289,12 @@ def run_b200(args):
             # by the FP64 FMA pipe, not by HBM: 576 DFMA per node row block + 24
             # for the modulus scaling (DESIGN.md "grid operator").
             flops = n_loc_nodes * (576 + 24) * 2
+            gridop_traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "gridop_traffic.json")) as f:
+                    gridop_traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                gridop_traffic = None
             fp64_peak = dev.fp64_peak_tflops()
             fp64_peak_const = dev.fp64_peak_tflops(const_operand=True)
             achieved = flops / (spmv_ms * 1e-3) / 1e12 if spmv_n else None
@@ -294,7 +309,7 @@ def run_b200(args):
                 "peak_const_operand": fp64_peak_const,
                 "frac_of_const_operand_peak": (achieved / fp64_peak_const) if achieved else None,
                 "alg_flops_per_launch": flops, "avg_launch_ms": spmv_ms, "samples": spmv_n,
-                "traffic": None,
+                "traffic": gridop_traffic if world == 1 else None,
                 "hbm": {"alg_bytes_per_launch": alg_bytes,
                         "achieved_GBs": alg_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None,
                         "peak_GBs": peak, "peak_source": peak_src},
@@ -372,7 +387,8 @@ def run_b200(args):
             "config": {
                 "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
                 "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
-                "solver": ("device PCG rtol 1e-8, warm start, operator: "
+                "solver": ("device PCG rtol 1e-8, start vector = Galerkin projection on the last "
+                           "%d solutions, operator: " % eng.start_hist
                            + ("matrix-free grid stencil" if eng.matrix_free else "assembled node-block CSR")
                            + ", preconditioner: "
                            + ("geometric multigrid V-cycle (Galerkin coarse operators, damped Jacobi "
@@ -380,8 +396,10 @@ def run_b200(args):
                               % ",".join(str(v) for v in eng.mg.sweeps)
                               if eng.precond == "mg" else "Jacobi")),
                 "pcg_iters_per_step": pcg_iters,
-                "l2": ("per-step working set (u, rho, filter CSR 0.34 GB, level-1 operator 0.27 GB, "
-                       "work vectors) larger than the 126 MB L2; nothing is flushed explicitly"),
+                "l2": ("inputs larger than L2: one step streams the level-1 operator (0.27 GB) ~4x per PCG "
+                       "iteration plus ~20 work vectors of 25 MB against the 126 MB L2; nothing is "
+                       "flushed explicitly"),
+                "filter": "Helmholtz: direct fast-diagonalisation solve (adjoint) + matrix-free PCG (forward, fixed nodes)",
                 "parallelism": "single GPU" if world == 1 else (
                     f"elasticity operator row-sharded over {world} GPUs (NCCL halo exchange + "
                     f"dot all-reduce); filter/element stages replicated"),
@@ -410,13 +428,15 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh-size", type=float, default=C2_MESH_SIZE)
     ap.add_argument("--cpu-mesh-size", type=float, default=CPU_SAMPLE_MESH_SIZE)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spmv-leg", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run one extra step inside cudaProfilerStart/Stop before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -210,11 +210,14 @@ class FeaEngine:
         A start vector does not change the converged solution."""
         hist = self.u_hist.setdefault(load, [])
         m = self.start_hist
-        if m <= 1 or self.sharded or not self.warm_start:
+        if m <= 1 or not self.warm_start or (self.sharded and not self.matrix_free):
             return
         V = [x] + hist
         if dev.dot(x, x) == 0.0:               # first solve: nothing to project on
             return
+        # sharded: products and dots over the owned rows, one all-reduce of the
+        # small Gram system; the vectors are full length on every rank
+        lo, hi = self.row0, self.row0 + self.n_local
         trace = os.environ.get("SKTOPT_B200_START_TRACE") == "1"
         if trace:
             import time
@@ -222,7 +225,7 @@ class FeaEngine:
             t0 = time.perf_counter()
         while len(self._proj_tmp) < len(V):
             self._proj_tmp.append(torch.empty(self.n_dof, dtype=dev.F64, device="cuda"))
-        AV = [self.spmv(v, out=t) for v, t in zip(V, self._proj_tmp)]
+        AV = [self.spmv(v, out=t[:self.n_local]) for v, t in zip(V, self._proj_tmp)]
         if trace:
             torch.cuda.synchronize()
             t1 = time.perf_counter()
@@ -230,9 +233,13 @@ class FeaEngine:
         G = np.empty((k, k))
         c = np.empty(k)
         for i in range(k):
-            c[i] = dev.dot(V[i], rhs)
+            c[i] = dev.dot(V[i][lo:hi], rhs[lo:hi])
             for j in range(i, k):
-                G[i, j] = G[j, i] = dev.dot(V[i], AV[j])
+                G[i, j] = G[j, i] = dev.dot(V[i][lo:hi], AV[j])
+        if self.sharded:
+            pack = torch.as_tensor(np.concatenate([G.ravel(), c]), dtype=dev.F64, device="cuda")
+            pack = self.comm.allreduce_sum(pack).cpu().numpy()
+            G, c = pack[:k * k].reshape(k, k), pack[k * k:]
         # scaled, regularised solve: near-parallel history vectors must not blow up
         if trace:
             t2 = time.perf_counter()
