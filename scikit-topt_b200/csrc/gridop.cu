@@ -90,6 +90,19 @@ static ScalarStencil make_scalar_stencil(const double *ke) {
   return W;
 }
 
+// node -> (ix, iy, iz) with 32-bit unsigned arithmetic (node counts are < 2^31:
+// connectivity is int32); the 64-bit div/mod the compiler emits otherwise costs
+// ~200 instructions per node, more than the whole scalar stencil
+__device__ __forceinline__ void node_coords(int64_t n, int npx, int npy, int &ix, int &iy,
+                                            int &iz) {
+  const unsigned n32 = (unsigned)n;
+  const unsigned t = n32 / (unsigned)npy;
+  iy = (int)(n32 - t * (unsigned)npy);
+  const unsigned z = t / (unsigned)npx;
+  ix = (int)(t - z * (unsigned)npx);
+  iz = (int)z;
+}
+
 __device__ __forceinline__ int clampi(int v, int hi) {
   return v < 0 ? 0 : (v > hi ? hi : v);
 }
@@ -380,10 +393,8 @@ __global__ void __launch_bounds__(kBlock, 2)
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_loc;
        r += stride) {
     const int64_t n = node0 + r;
-    const int iy = (int)(n % npy);
-    const int64_t t = n / npy;
-    const int ix = (int)(t % npx);
-    const int iz = (int)(t / npx);
+    int ix, iy, iz;
+    node_coords(n, npx, npy, ix, iy, iz);
     const unsigned dm = P.dmask[n];
     double out[3];
     if (ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1 && !(dm & 8u))
@@ -454,10 +465,8 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int64_t n = node0 + r;
     const int64_t n_total = (int64_t)npx * npy * npz;
     const int64_t nc = n < n_total ? n : n_total - 1;
-    const int iy = (int)(nc % npy);
-    const int64_t t = nc / npy;
-    const int ix = (int)(t % npx);
-    const int iz = (int)(t / npx);
+    int ix, iy, iz;
+    node_coords(nc, npx, npy, ix, iy, iz);
     const unsigned dm = P.dmask[nc];
     T E[8];
 #pragma unroll
@@ -650,10 +659,8 @@ __global__ void __launch_bounds__(kBlock, 4)
        r += stride) {
     const bool live = r < n_loc;
     const int64_t n = node0 + (live ? r : n_loc - 1);
-    const int iy = (int)(n % npy);
-    const int64_t t = n / npy;
-    const int ix = (int)(t % npx);
-    const int iz = (int)(t / npx);
+    int ix, iy, iz;
+    node_coords(n, npx, npy, ix, iy, iz);
     const unsigned dm = P.dmask[n];
     const bool fast = ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1 && !(dm & 8u);
     double out[3];
@@ -700,10 +707,8 @@ __global__ void __launch_bounds__(kBlock)
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_loc;
        r += stride) {
     const int64_t n = node0 + r;
-    const int iy = (int)(n % npy);
-    const int64_t t = n / npy;
-    const int ix = (int)(t % npx);
-    const int iz = (int)(t / npx);
+    int ix, iy, iz;
+    node_coords(n, npx, npy, ix, iy, iz);
     double d[DPN];
 #pragma unroll
     for (int i = 0; i < DPN; ++i) d[i] = 0.0;
@@ -726,14 +731,17 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 // ------------------------------------- scalar stencil kernel (DPN = 1) ------
-// One thread per node, nodes of a warp consecutive along y (the same blocked
-// assignment and shuffle scheme as hexgrid_apply_shfl_kernel): each of the 9
-// neighbour lines costs one coalesced load + two shuffles.  Nodes whose eight
-// elements all exist in x and z, with no fixed node around and a uniform
-// coefficient (scale == NULL: the Helmholtz operator M + r^2 K), take the
-// 36-FMA stencil W; grid faces, the neighbourhood of fixed nodes and variable
-// coefficients take the general per-element sum (64 FMA + 8 for the scale).
-// Fixed nodes: inputs read as 0, outputs pass x through (identity rows/columns).
+// One thread per node, consecutive threads = consecutive nodes along y, blocked
+// assignment (a CTA walks a contiguous run of grid lines, so the neighbour
+// lines of one trip are L1 hits of the next).  Nodes whose eight elements all
+// exist in x and z, with no fixed node around and a uniform coefficient (scale
+// == NULL: the Helmholtz operator M + r^2 K), take the 36-FMA stencil W with
+// plain offset addressing: 27 coalesced loads, no shuffles, no lane
+// predicates (a first version with shuffled y-neighbours spent ~600
+// instructions per 36 FMA on lane fix-ups and convergence barriers).  Grid
+// faces, the neighbourhood of fixed nodes and variable coefficients take the
+// general per-element sum (64 FMA + 8 for the scale).  Fixed nodes: inputs read
+// as 0, outputs pass x through (identity rows/columns).
 template <bool DOT>
 __global__ void __launch_bounds__(kBlock, 3)
     scalar_grid_apply_kernel(const __grid_constant__ GridParams<1> P,
@@ -745,61 +753,53 @@ __global__ void __launch_bounds__(kBlock, 3)
   if (S && S->rr <= S->tol2) return;
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
-  const int lane = threadIdx.x & 31;
-  const int64_t n_total = (int64_t)npx * npy * npz;
+  const int plane = npx * npy;
   double dot = 0.0;
-  const int64_t n_pad = (n_loc + 31) / 32 * 32;  // whole warps run every trip (shuffles)
-  const int64_t trips = (n_pad + kBlock - 1) / kBlock;
+  const int64_t trips = (n_loc + kBlock - 1) / kBlock;
   const int64_t per_cta = (trips + gridDim.x - 1) / gridDim.x;
-  const int64_t r_end = min(n_pad, (int64_t)(blockIdx.x + 1) * per_cta * kBlock);
+  const int64_t r_end = min(n_loc, (int64_t)(blockIdx.x + 1) * per_cta * kBlock);
   for (int64_t r = (int64_t)blockIdx.x * per_cta * kBlock + threadIdx.x; r < r_end;
        r += kBlock) {
-    const bool live = r < n_loc;
     const int64_t n = node0 + r;
-    const int64_t nc = n < n_total ? n : n_total - 1;
-    const int iy = (int)(nc % npy);
-    const int64_t t = nc / npy;
-    const int ix = (int)(t % npx);
-    const int iz = (int)(t / npx);
-    const unsigned dm = P.dmask[nc];
-    const bool fast = !P.scale && !(dm & 8u) && ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1;
-    double a0 = 0.0, a1 = 0.0;  // fast path: elements below / above in y
-    double pe[8];               // general path: per-element sums
+    int ix, iy, iz;
+    node_coords(n, npx, npy, ix, iy, iz);
+    const unsigned dm = P.dmask[n];
+    double a;
+    if (!P.scale && !(dm & 8u) && ix > 0 && ix < npx - 1 && iz > 0 && iz < npz - 1) {
+      const double *xc = x + n;
+      const int dl = iy > 0 ? 1 : 0, dr = iy < npy - 1 ? 1 : 0;  // stay on the line at its ends
+      double a0 = 0.0, a1 = 0.0;  // elements below / above the node in y
 #pragma unroll
-    for (int o = 0; o < 8; ++o) pe[o] = 0.0;
+      for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int l = (dz + 1) * 3 + (dx + 1);
+          // at the y-ends of a line the missing neighbour is replaced by the node
+          // itself; it only feeds the accumulator that is dropped below
+          const double *p = xc + (dz * plane + dx * npy);
+          const double u0 = __ldg(p - dl), u1 = __ldg(p), u2 = __ldg(p + dr);
+          a0 = fma(W.w0[l][0], u0, a0);
+          a0 = fma(W.w0[l][1], u1, a0);
+          a1 = fma(W.w1[l][0], u1, a1);
+          a1 = fma(W.w1[l][1], u2, a1);
+        }
+      }
+      a = (iy > 0 ? a0 : 0.0) + (iy < npy - 1 ? a1 : 0.0);
+    } else {
+      double pe[8];  // per-element sums
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int l = (dz + 1) * 3 + (dx + 1);
-        const int kx = clampi(ix + dx, npx - 1), kz = clampi(iz + dz, npz - 1);
-        const int64_t mc = (int64_t)npy * (kx + (int64_t)npx * kz) + iy;
-        double u[3];  // [dy + 1]
-        u[1] = __ldg(x + mc);
-        u[0] = __shfl_up_sync(0xffffffffu, u[1], 1);
-        u[2] = __shfl_down_sync(0xffffffffu, u[1], 1);
-        if (lane == 0 && iy > 0) u[0] = __ldg(x + mc - 1);
-        if (lane == 31 && iy < npy - 1) u[2] = __ldg(x + mc + 1);
-        // the y-ends of a line: the shuffled value belongs to another line and
-        // only ever meets a zero weight; make it a plain zero
-        if (iy == 0) u[0] = 0.0;
-        if (iy == npy - 1) u[2] = 0.0;
-        if (fast) {
-          a0 = fma(W.w0[l][0], u[0], a0);
-          a0 = fma(W.w0[l][1], u[1], a0);
-          a1 = fma(W.w1[l][0], u[1], a1);
-          a1 = fma(W.w1[l][1], u[2], a1);
-        } else {
-          if (dm & 8u) {  // a fixed node somewhere around: mask the inputs
+      for (int o = 0; o < 8; ++o) pe[o] = 0.0;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-              const int ky = iy + dy;
-              if (ky < 0 || ky >= npy) continue;
-              if (P.dmask[mc + dy] & 1u) u[dy + 1] = 0.0;
-            }
-          }
+      for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
+            if (kx < 0 || kx >= npx || ky < 0 || ky >= npy || kz < 0 || kz >= npz) continue;
+            const int m = ky + npy * (kx + npx * kz);
+            double u = __ldg(x + m);
+            if ((dm & 8u) && (P.dmask[m] & 1u)) u = 0.0;  // fixed input
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
               const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
@@ -807,15 +807,9 @@ __global__ void __launch_bounds__(kBlock, 3)
               if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
               const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
               const int cb = bx + 2 * by + 4 * bz;
-              pe[o] = fma(P.ke[ca * 8 + cb], u[dy + 1], pe[o]);
+              pe[o] = fma(P.ke[ca * 8 + cb], u, pe[o]);
             }
-        }
-      }
-    }
-    double a;
-    if (fast) {
-      a = (iy > 0 ? a0 : 0.0) + (iy < npy - 1 ? a1 : 0.0);
-    } else {
+          }
       a = 0.0;
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
@@ -827,11 +821,9 @@ __global__ void __launch_bounds__(kBlock, 3)
         a = fma(E, pe[o], a);
       }
     }
-    if (live) {
-      if (dm & 1u) a = x[n];
-      y[r] = a;
-      if (DOT) dot = fma(a, dotv[r], dot);
-    }
+    if (dm & 1u) a = x[n];
+    y[r] = a;
+    if (DOT) dot = fma(a, dotv[r], dot);
   }
   if (DOT) {
     double v[1] = {dot};
@@ -866,7 +858,7 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
                          ReduceScratch *rs, double *dot_out, const PcgScalars *S,
                          cudaStream_t st) {
   if (op->dpn == 1 && op->scalar_direct) {
-    const int g = grid_for(n_nodes, kBlock, 3);  // 3 resident CTAs per SM (80 registers)
+    const int g = grid_for(n_nodes, kBlock, 3);
     if (dotv)
       scalar_grid_apply_kernel<true><<<g, kBlock, 0, st>>>(
           op->P1, op->W1, node0, n_nodes, x, y, dotv, rs->partials, rs->ticket, dot_out, S);
@@ -978,6 +970,10 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   op->dpn = dpn;
   op->device = device;
   op->n_nodes = (int64_t)np_h[0] * np_h[1] * np_h[2];
+  if (op->n_nodes >= ((int64_t)1 << 31) / 3) {
+    delete op;
+    SKTB_REQUIRE(false, "grid too large for 32-bit node indexing");
+  }
   // the 3-dof product is latency bound either way and measures faster straight
   // from L1 (0.100 ms vs 0.128 ms at 1M nodes); SKTB_GRIDOP_TILED=1 forces the
   // shared-memory variant, which is the only one for the scalar operator
