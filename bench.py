@@ -385,7 +385,7 @@ def run_b200(args):
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "C2: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
+                "workload": ("C2" if abs(args.mesh_size - C2_MESH_SIZE) < 1e-12 else "custom") + ": 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
                 "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
                 "solver": ("device PCG rtol 1e-8, start vector = Galerkin projection on the last "
                            "%d solutions, operator: " % eng.start_hist

@@ -112,6 +112,7 @@ class FeaEngine:
         # last START_HIST solutions of the same load (1 = plain warm start)
         self.start_hist = int(os.environ.get("SKTOPT_B200_START_HIST", "3"))
         self.u_hist = {}
+        self._hist_pool = {}
         self._proj_tmp = []
         self.pcg_log = []  # (iters, converged, relres) of every solve
 
@@ -223,8 +224,14 @@ class FeaEngine:
             import time
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-        while len(self._proj_tmp) < len(V):
+        # all work vectors (m products, m-1 history slots + 1 spare per load) are
+        # allocated at the first projection, not as the history fills up
+        while len(self._proj_tmp) < m:
             self._proj_tmp.append(torch.empty(self.n_dof, dtype=dev.F64, device="cuda"))
+        pool = self._hist_pool.setdefault(load, None)
+        if pool is None:
+            pool = self._hist_pool[load] = [torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
+                                            for _ in range(m)]
         AV = [self.spmv(v, out=t[:self.n_local]) for v, t in zip(V, self._proj_tmp)]
         if trace:
             torch.cuda.synchronize()
@@ -248,7 +255,10 @@ class FeaEngine:
         a = d * np.linalg.lstsq(Gs, d * c, rcond=1e-10)[0]
         if trace:
             t3 = time.perf_counter()
-        keep = [x.clone()] + hist[:max(m - 2, 0)]
+        spare = pool.pop()                      # a slot that is not part of the history
+        spare.copy_(x)
+        keep = [spare] + hist[:max(m - 2, 0)]
+        pool.extend(hist[max(m - 2, 0):])       # the dropped oldest solution becomes free
         if k == 1:
             dev.affine(float(a[0]), x, 0.0, None, 0.0, x)
         else:
