@@ -32,6 +32,11 @@ C2_MESH_SIZE = 0.0577          # toy_base(0.0577): 139x104x70 = 1,011,920 hex
 CPU_SAMPLE_MESH_SIZE = 0.2     # toy1_fine: 40x30x20 = 24,000 hex (largest mesh the reference defines)
 
 
+def workload_name(mesh_size: float) -> str:
+    tag = "C2" if abs(mesh_size - C2_MESH_SIZE) < 1e-12 else "custom"
+    return "%s: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % (tag, mesh_size)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -93,29 +98,28 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------- CPU legs --
+CPU_MAX_TIMED_STEPS = 3        # ~20 s each on the sample mesh: bounds the CPU legs
+CPU_MAX_WARMUP_STEPS = 1
+
+
 def cpu_oracle_step_rate(steps: int, warmup: int, mesh_size: float):
     """The oracle port of the reference path (NumPy/SciPy, scipy cg + Jacobi,
     splu Helmholtz filter) running full LogMOC iterations on a bounded sample
-    mesh.  Returns (iters/s on the sample, n_elem_sample, seconds per step)."""
+    mesh: at most CPU_MAX_WARMUP_STEPS untimed + CPU_MAX_TIMED_STEPS timed
+    iterations, whatever --steps / --warmup ask for, so that the run ends within
+    a few minutes.  Returns (iters/s on the sample, n_elem_sample, seconds per
+    step, timed steps)."""
     from oracle import mesh as omesh, optim
     o = omesh.toy_base(mesh_size)
     pr = optim.Problem(o["p"], o["t"], o["dirichlet_dofs"], o["force"], o["design"],
                        o["pinned"], o["volumes"], o["E"], o["nu"], fixed=o["fixed"])
-    total = max(1, steps + warmup)
-    tm = []
-
-    # optim.run has no per-step hook: run (warmup) and (warmup+steps) iterations
-    # of the same deterministic loop and difference the wall clock
-    def timed(n):
-        t0 = time.perf_counter()
-        optim.run(pr, "logmoc", max_iters=200, iters=n, vol_frac=0.3,
-                  solver="cg_jacobi", rtol=1e-8, cg_maxiter=20000)
-        return time.perf_counter() - t0
-    t_w = timed(warmup) if warmup > 0 else 0.0
-    t_all = timed(total)
-    dt = (t_all - t_w) / max(1, steps)
-    tm.append(dt)
-    return 1.0 / dt, int(o["t"].shape[1]), dt
+    n_warm = max(0, min(int(warmup), CPU_MAX_WARMUP_STEPS))
+    n_timed = max(1, min(int(steps), CPU_MAX_TIMED_STEPS))
+    marks = []
+    optim.run(pr, "logmoc", max_iters=200, iters=n_warm + n_timed, vol_frac=0.3,
+              solver="cg_jacobi", rtol=1e-8, cg_maxiter=20000, step_times=marks)
+    dt = (marks[-1] - marks[n_warm]) / n_timed
+    return 1.0 / dt, int(o["t"].shape[1]), dt, n_timed
 
 
 def run_reference(args):
@@ -125,10 +129,11 @@ def run_reference(args):
     if rank != 0:
         return
     n_c2 = 1011920
-    rate, n_s, dt = cpu_oracle_step_rate(args.steps, args.warmup, args.cpu_mesh_size)
+    rate, n_s, dt, n_t = cpu_oracle_step_rate(args.steps, args.warmup, args.cpu_mesh_size)
     value = rate * n_s / n_c2
     sample = (f"oracle LogMOC iteration (scipy cg+Jacobi rtol 1e-8, splu Helmholtz filter) on "
-              f"toy_base({args.cpu_mesh_size}) = {n_s} hex ({dt:.2f} s/step), scaled linearly in "
+              f"toy_base({args.cpu_mesh_size}) = {n_s} hex ({dt:.2f} s/step, mean of {n_t} timed "
+              f"steps: the CPU leg is capped at {CPU_MAX_TIMED_STEPS}), scaled linearly in "
               f"element count to {n_c2} hex (optimistic for the CPU: CG iterations also grow "
               f"with mesh size); scipy is single-threaded")
     line = {
@@ -136,7 +141,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 3D cantilever 1,011,920 hex, LogMOC, vol_frac 0.3",
+        "config": {"workload": workload_name(args.mesh_size), "n_elem": n_c2,
                    "sample_mesh_size": args.cpu_mesh_size},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": sample},
@@ -385,7 +390,7 @@ def run_b200(args):
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": ("C2" if abs(args.mesh_size - C2_MESH_SIZE) < 1e-12 else "custom") + ": 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % args.mesh_size,
+                "workload": workload_name(args.mesh_size),
                 "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
                 "solver": ("device PCG rtol 1e-8, start vector = Galerkin projection on the last "
                            "%d solutions, operator: " % eng.start_hist
@@ -413,7 +418,7 @@ def run_b200(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            rate, n_s, dt = cpu_oracle_step_rate(1, 0, args.cpu_mesh_size)
+            rate, n_s, dt, _ = cpu_oracle_step_rate(1, 0, args.cpu_mesh_size)
             line["cpu_baseline"] = {
                 "value": rate * n_s / n_elem, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": (f"oracle LogMOC iteration on toy_base({args.cpu_mesh_size}) = {n_s} hex "

@@ -124,7 +124,7 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         beta_sched=(1.0, 2.0, 3, 2.0), move_sched=(0.3, 0.1, 6), eta=None,
         rho_min=1e-2, rho_max=1.0, E_min_coeff=1e-3, beta_eta=0.5,
         solver="spsolve", rtol=1e-8, cg_maxiter=None, lambda_lower=1e-7,
-        lambda_upper=1e7, logmoc=None, iters=None, timings=None):
+        lambda_upper=1e7, logmoc=None, iters=None, timings=None, step_times=None):
     """DensityMethod._optimize_impl (common_density.py:1014-1134) with the
     default schedules of DensityMethodConfig / OC_Config / LogMOC_Config.
     Returns dict(rho, compliance[], vol_error[], rho_hist[])."""
@@ -160,6 +160,8 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
 
     n_it = max_iters if iters is None else iters
     for it in range(1, n_it + 1):
+        if step_times is not None:
+            step_times.append(time.perf_counter())      # start of every iteration
         pw = sched_step(it, max_iters, *p_sched)
         beta = sched_step(it, max_iters, beta_sched[0], beta_sched[1], beta_sched[2],
                           beta_sched[3], "accelerating")
@@ -233,6 +235,8 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         hist["compliance"].append(compliance)
         hist["vol_error"].append(float(vol_error))
         hist["rho"].append(rho[pr.design].copy())
+    if step_times is not None:
+        step_times.append(time.perf_counter())          # end of the last one
     hist["rho_final"] = rho
     hist["rho_projected"] = rho_p
     hist["energy"] = energy

@@ -219,11 +219,6 @@ class FeaEngine:
         # sharded: products and dots over the owned rows, one all-reduce of the
         # small Gram system; the vectors are full length on every rank
         lo, hi = self.row0, self.row0 + self.n_local
-        trace = os.environ.get("SKTOPT_B200_START_TRACE") == "1"
-        if trace:
-            import time
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
         # all work vectors (m products, m-1 history slots + 1 spare per load) are
         # allocated at the first projection, not as the history fills up
         while len(self._proj_tmp) < m:
@@ -233,9 +228,6 @@ class FeaEngine:
             pool = self._hist_pool[load] = [torch.empty(self.n_dof, dtype=dev.F64, device="cuda")
                                             for _ in range(m)]
         AV = [self.spmv(v, out=t[:self.n_local]) for v, t in zip(V, self._proj_tmp)]
-        if trace:
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
         k = len(V)
         G = np.empty((k, k))
         c = np.empty(k)
@@ -248,13 +240,9 @@ class FeaEngine:
             pack = self.comm.allreduce_sum(pack).cpu().numpy()
             G, c = pack[:k * k].reshape(k, k), pack[k * k:]
         # scaled, regularised solve: near-parallel history vectors must not blow up
-        if trace:
-            t2 = time.perf_counter()
         d = 1.0 / np.sqrt(np.maximum(np.diag(G), 1e-300))
         Gs = G * d[:, None] * d[None, :]
         a = d * np.linalg.lstsq(Gs, d * c, rcond=1e-10)[0]
-        if trace:
-            t3 = time.perf_counter()
         spare = pool.pop()                      # a slot that is not part of the history
         spare.copy_(x)
         keep = [spare] + hist[:max(m - 2, 0)]
@@ -266,11 +254,6 @@ class FeaEngine:
             for i in range(2, k):
                 dev.axpby(float(a[i]), V[i], 1.0, x)
         self.u_hist[load] = keep
-        if trace:
-            torch.cuda.synchronize()
-            t4 = time.perf_counter()
-            print(f"[start k={k}] products {1e3*(t1-t0):.3f} dots {1e3*(t2-t1):.3f} "
-                  f"lstsq {1e3*(t3-t2):.3f} combine {1e3*(t4-t3):.3f} ms  a={a}", flush=True)
 
     def solve(self, rhs, load: int, rtol: float, maxiter: int | None, vals=None):
         """PCG on the enforced system; ``rhs`` and the returned solution are
