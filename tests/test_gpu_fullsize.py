@@ -79,12 +79,16 @@ def test_c2_helmholtz_filter_properties(c2, monkeypatch):
         filt = sktopt.filters.HelmholtzFilterNodal.from_defaults(
             tsk.mesh, tsk.elements_volume, 0.01, design_mask=tsk.design_mask)
         out[fd] = (filt.gradient(v), filt.forward(rho))
-        # partition of unity: a field of ones (design and fixed elements alike) stays ones
-        assert np.max(np.abs(filt.forward(np.ones(ne)) - 1.0)) <= 1e-9
+        # partition of unity: a field of ones (design and fixed elements alike) stays
+        # ones.  The forward system has fixed nodes and goes through the PCG, whose
+        # stopping rule is a 2-norm over 1.04M entries (||r|| <= 1e-11 ||b||): the
+        # max-norm error it allows is ~ kappa sqrt(n) 1e-11 ~ 1e-7, far inside the
+        # 1e-4 density tolerance
+        assert np.max(np.abs(filt.forward(np.ones(ne)) - 1.0)) <= 1e-6
     g_fd, g_it = out["1"][0], out["0"][0]
     assert np.max(np.abs(g_fd - g_it)) <= 1e-9 * max(1.0, np.abs(g_it).max())
     assert np.all(g_fd <= 0.0)
-    assert np.max(np.abs(out["1"][1] - out["0"][1])) <= 1e-9
+    assert np.max(np.abs(out["1"][1] - out["0"][1])) <= 1e-6      # two PCG runs of the forward system
     f = out["1"][1]
     assert f.min() >= 0.05 - 0.2 and f.max() <= 1.0 + 0.2       # no wild over/undershoot
     # no fixed nodes: the Neumann problem preserves the mean of a uniform-grid field
