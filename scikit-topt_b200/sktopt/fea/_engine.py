@@ -240,6 +240,8 @@ class FeaEngine:
             pack = self.comm.allreduce_sum(pack).cpu().numpy()
             G, c = pack[:k * k].reshape(k, k), pack[k * k:]
         # scaled, regularised solve: near-parallel history vectors must not blow up
+        if not (np.all(np.isfinite(G)) and np.all(np.isfinite(c)) and np.all(np.diag(G) > 0.0)):
+            return                              # degenerate history: keep the plain warm start
         d = 1.0 / np.sqrt(np.maximum(np.diag(G), 1e-300))
         Gs = G * d[:, None] * d[None, :]
         a = d * np.linalg.lstsq(Gs, d * c, rcond=1e-10)[0]
