@@ -177,6 +177,18 @@ class DensityMethodBase(ABC):
         pass
 
     @abstractmethod
+    def scale(self):
+        pass
+
+    @abstractmethod
+    def unscale(self):
+        pass
+
+    @abstractmethod
+    def load_parameters(self):
+        pass
+
+    @abstractmethod
     def init_schedulers(self, export: bool = True):
         pass
 

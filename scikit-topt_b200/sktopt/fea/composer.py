@@ -129,3 +129,29 @@ def assemble_stiffness_matrix_simp(basis, rho, E0, Emin, p, nu):
 
 def assemble_stiffness_matrix_ramp(basis, rho, E0, Emin, p, nu):
     return assemble_stiffness_matrix(basis, rho, E0, Emin, p, nu, ramp_interpolation)
+
+
+# ----------------------------------------------- remaining public names -----
+def adjacency_matrix(mesh) -> list:
+    """Face neighbours of every tetrahedron as a list of lists (reference
+    ``fea/composer.py:351-371``, a dict-of-faces Python loop there; vectorised
+    here with the mesh's facet tables)."""
+    f2t = np.asarray(mesh.f2t)                     # (2, n_facets), -1 = boundary
+    both = f2t[:, (f2t >= 0).all(axis=0)]
+    adjacency = [[] for _ in range(mesh.nelements)]
+    for i, j in both.T.tolist():
+        adjacency[i].append(j)
+        adjacency[j].append(i)
+    return adjacency
+
+
+def strain_energy_skfem(basis, rho, u, E0, Emin, p, nu, elem_func=simp_interpolation):
+    """Element strain energies of one displacement field (``fea/composer.py:402-423``;
+    the same function also lives in ``fea/solver_elastic.py``, where it is built)."""
+    from sktopt.fea import solver_elastic
+    return solver_elastic.strain_energy_skfem(basis, rho, u, E0, Emin, p, nu, elem_func)
+
+
+def strain_energy_skfem_multi(basis, rho, U, E0, Emin, p, nu, elem_func=simp_interpolation):
+    from sktopt.fea import solver_elastic
+    return solver_elastic.strain_energy_skfem_multi(basis, rho, U, E0, Emin, p, nu, elem_func)

@@ -55,6 +55,51 @@ def _as_list(x):
     return x if isinstance(x, list) else [x]
 
 
+# ------------------------------------------------ function-level API --------
+def heat_energy_skfem_multi(basis, rho, T_all, k0, kmin, p,
+                            elem_func: Callable = composer.simp_interpolation):
+    """U_e = int_e 1/2 k_e |grad T|^2 for every temperature column, shape
+    (n_elements, n_loads) (reference :256-303)."""
+    dm = dev.device_mesh(basis.mesh)
+    ke0 = dm.unit_ke(KE_LAPLACE, basis.X, basis.W)
+    k = dev.interpolate_modulus(dev.to_dev(rho), k0, kmin, p, ramp=composer.is_ramp(elem_func))
+    on_dev = _is_dev(T_all)
+    T2 = T_all if T_all.ndim == 2 else T_all[:, None]
+    out = torch.empty((T2.shape[1], dm.n_elem), dtype=dev.F64, device="cuda")
+    for i in range(T2.shape[1]):
+        Ti = T2[:, i].contiguous() if on_dev else dev.to_dev(np.ascontiguousarray(T2[:, i]))
+        dm.element_energy(1, ke0, k, Ti, out=out[i])
+    res = out.t()
+    return res if on_dev else res.cpu().numpy()
+
+
+def heat_energy_skfem(basis, rho, T, k0, kmin, p,
+                      elem_func: Callable = composer.simp_interpolation):
+    return heat_energy_skfem_multi(basis, rho, T[:, None], k0, kmin, p, elem_func)[:, 0]
+
+
+def heat_exchange_grad_density_multi(basis, T_all, λ_all):
+    """Elemental integrals of grad T . grad lambda, shape (n_elements, n_loads)
+    (reference :343-383; ``avg_temp_grad_density_multi`` :536-549 is the same
+    functional)."""
+    dm = dev.device_mesh(basis.mesh)
+    ke0 = dm.unit_ke(KE_LAPLACE, basis.X, basis.W)
+    on_dev = _is_dev(T_all)
+    T2 = T_all if T_all.ndim == 2 else T_all[:, None]
+    L2 = λ_all if λ_all.ndim == 2 else λ_all[:, None]
+    out = torch.empty((T2.shape[1], dm.n_elem), dtype=dev.F64, device="cuda")
+    for i in range(T2.shape[1]):
+        Ti = T2[:, i].contiguous() if on_dev else dev.to_dev(np.ascontiguousarray(T2[:, i]))
+        Li = (L2[:, i].contiguous() if _is_dev(L2)
+              else dev.to_dev(np.ascontiguousarray(L2[:, i])))
+        dm.element_bilinear(1, ke0, None, Ti, Li, 1.0, out=out[i])
+    res = out.t()
+    return res if on_dev else res.cpu().numpy()
+
+
+avg_temp_grad_density_multi = heat_exchange_grad_density_multi
+
+
 class _HeatDevice:
     """Device buffers of one heat task (scalar CSR on the node graph)."""
 

@@ -212,3 +212,72 @@ class HelmholtzFilterNodal(BaseFilter):
         if isinstance(v_ele, torch.Tensor) and v_ele.is_cuda:
             return st.gradient(v_ele, out=out)
         return st.gradient(dev.to_dev(v_ele)).cpu().numpy()
+
+
+# ------------------------------------------------ function-level API --------
+# The reference exposes the three steps of the filter as module functions
+# (:26-56, :121-157); here they run the same device kernels as the class.
+_FUNC_STATES: dict = {}
+
+
+def _as_device(a):
+    on_dev = isinstance(a, torch.Tensor) and a.is_cuda
+    return (a if on_dev else dev.to_dev(np.ascontiguousarray(a, dtype=np.float64))), on_dev
+
+
+def _state_for(mesh, elements_volume, design_mask) -> _HelmholtzDevice:
+    vol = np.ones(mesh.nelements) if elements_volume is None \
+        else np.ascontiguousarray(elements_volume, dtype=np.float64)
+    mask = None if design_mask is None else np.ascontiguousarray(design_mask, dtype=bool)
+    key = (id(mesh), vol.tobytes(), None if mask is None else mask.tobytes())
+    ent = _FUNC_STATES.get(key)
+    if ent is None or ent[0] is not mesh:
+        if len(_FUNC_STATES) >= 4:
+            _FUNC_STATES.clear()
+        ent = (mesh, _HelmholtzDevice(mesh, vol, mask))
+        _FUNC_STATES[key] = ent
+    return ent[1]
+
+
+def node_to_element_density(mesh, rho_node):
+    """Plain mean of an element's nodal values (reference :26-27)."""
+    x, on_dev = _as_device(rho_node)
+    out = dev.device_mesh(mesh).n2e_mean(x, clamp_max0=False)
+    return out if on_dev else out.cpu().numpy()
+
+
+def element_to_node_density_averaging(mesh, elements_volume, rho_elem, design_mask=None,
+                                      weighted: bool = True,
+                                      fixed_value_for_design: float = 1.0):
+    """Volume-weighted (or plain, ``weighted=False``) nodal average of element
+    values; non-design elements contribute ``fixed_value_for_design`` (:30-56)."""
+    vol = np.asarray(elements_volume, dtype=np.float64) if weighted \
+        else np.ones(mesh.nelements)
+    st = _state_for(mesh, vol, design_mask)
+    rho, on_dev = _as_device(rho_elem)
+    out = st.dm.e2n(st.w, rho, st.design_u8, float(fixed_value_for_design), st.wsum)
+    return out if on_dev else out.cpu().numpy()
+
+
+def solve_helmholtz(case, mesh, rho_node, r_min: float, design_mask=None):
+    """Nodal solution of (M + r_min^2 K) x = M rho_node (:121-157): ``"forward"``
+    pins the nodes of non-design elements to 1; ``"gradient"`` is the plain
+    Neumann problem (the filter class calls it without a mask, :221; a mask
+    with ``"gradient"`` -- zero Dirichlet values -- is not built)."""
+    if case not in ("forward", "gradient"):
+        raise ValueError("case must be 'forward' or 'gradient'")
+    has_mask = design_mask is not None and not np.all(design_mask)
+    if case == "gradient" and has_mask:
+        raise NotImplementedError(
+            "solve_helmholtz('gradient', ..., design_mask=...) is not part of the filter path")
+    st = _state_for(mesh, None, design_mask if case == "forward" else None)
+    st.set_radius(float(r_min))
+    x_in, on_dev = _as_device(rho_node)
+    st._mass_times(x_in, st.b)
+    if case == "forward" and st.has_fixed:
+        dev.enforce_rhs(st.b, st.c, st.fixed_u8, st.x_fixed, out=st.rhs)
+        x = st._solve(True, st.rhs, st.x_fwd)
+    else:
+        x = st._solve(False, st.b, st.x_adj)
+    out = x.clone()
+    return out if on_dev else out.cpu().numpy()

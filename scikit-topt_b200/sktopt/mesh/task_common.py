@@ -221,6 +221,27 @@ class FEMDomain():
         except OSError:
             pass
 
+    def nodes_and_elements_stats(self, dst_path: str | None = None) -> dict:
+        """Nearest-neighbour distance statistics of nodes and element centres
+        (reference ``mesh/task_common.py:424-449``; the histogram figure it also
+        saves needs matplotlib and is not produced here).  Returns the numbers it
+        prints."""
+        from scipy.spatial import cKDTree
+        mesh = self.basis.mesh
+        out = {}
+        for key, title, pts in (
+                ("nodes", "=== Distance between nodes ===", mesh.p.T),
+                ("elements", "\n=== Distance between elements ===",
+                 np.mean(mesh.p[:, mesh.t], axis=1).T)):
+            d = cKDTree(pts).query(pts, k=2)[0][:, 1]
+            st = dict(min=float(np.min(d)), max=float(np.max(d)), mean=float(np.mean(d)),
+                      median=float(np.median(d)), std=float(np.std(d)))
+            print(title)
+            for name in ("min", "max", "mean", "median", "std"):
+                print(f"{name + ':':8s}{st[name]:.4f}")
+            out[key] = st
+        return out
+
     def exlude_dirichlet_from_design(self):
         self.design_elements = setdiff1d(self.design_elements, self.dirichlet_elements)
 

@@ -76,6 +76,16 @@ class LinearElasticity(FEMDomain):
     def force_elements(self):
         return self.neumann_elements
 
+    @property
+    def force_elements_all(self) -> np.ndarray:
+        """Union of the loaded elements of every load case.  (The reference
+        property, ``mesh/task_elastic.py:261-263``, forwards to an attribute
+        ``neumann_elements_all`` that ``FEMDomain`` never defines.)"""
+        ne = self.neumann_elements
+        if isinstance(ne, list):
+            return np.unique(np.concatenate([np.asarray(a).ravel() for a in ne]))
+        return np.asarray(ne)
+
     @force_elements.setter
     def force_elements(self, value):
         self.neumann_elements = value

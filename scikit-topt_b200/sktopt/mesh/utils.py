@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import numpy as np
+import scipy.sparse as sp
 
 from sktopt._fem import MeshHex, MeshTet
 
@@ -75,3 +76,42 @@ def get_adjacent_elements(mesh, element_indices):
     nodes = np.unique(mesh.t[:, element_indices])
     nb = get_elements_by_nodes(mesh, nodes)
     return sorted(set(nb.tolist()) - set(element_indices.tolist()))
+
+
+def _element_incidence(mesh) -> sp.csr_matrix:
+    """(n_nodes x n_elem) node-element incidence, one per (node, element) pair."""
+    t = np.asarray(mesh.t, dtype=np.int64)
+    nen, ne = t.shape
+    B = sp.coo_matrix((np.ones(nen * ne, dtype=np.int32),
+                       (t.ravel(), np.tile(np.arange(ne), nen))),
+                      shape=(mesh.nvertices, ne)).tocsr()
+    B.data[:] = 1                      # a degenerate element may list a node twice
+    return B
+
+
+def build_element_adjacency_matrix(mesh) -> sp.csr_matrix:
+    """uint8 CSR A with A[i, j] = 1 iff elements i and j share at least one node,
+    the diagonal included (``mesh/utils.py:139-159``, there a double Python loop;
+    here one sparse product)."""
+    B = _element_incidence(mesh)
+    A = (B.T @ B).tocsr()
+    A.sort_indices()
+    return sp.csr_matrix((np.ones(A.nnz, dtype=np.uint8), A.indices, A.indptr), shape=A.shape)
+
+
+def build_element_adjacency_matrix_fast(mesh) -> sp.csr_matrix:
+    """Same without the diagonal (``mesh/utils.py:231-254``)."""
+    A = build_element_adjacency_matrix(mesh).tolil()
+    A.setdiag(0)
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    return A
+
+
+def get_adjacent_elements_fast(adjacency, element_indices) -> np.ndarray:
+    """Sorted int32 ids of the elements adjacent to any of ``element_indices``,
+    excluding those (``mesh/utils.py:257-263``)."""
+    idx = np.asarray(element_indices, dtype=np.int64).ravel()
+    nb = np.unique(adjacency[idx].indices) if idx.size else np.array([], dtype=np.int64)
+    return np.setdiff1d(nb, idx).astype(np.int32)

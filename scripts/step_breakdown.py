@@ -36,8 +36,7 @@ for _ in range(n):
     per_step.append(round(1e3 * (time.perf_counter() - ts), 2))
 dt = (time.perf_counter() - t0) / n
 print("per-step ms", per_step)
-st = opt.timer.stats()
 print("ms/step", dt * 1e3)
-for k, v in sorted(st.items(), key=lambda kv: -kv[1]["total"]):
-    print(f"{k:60s} {v['total']/n*1e3:9.2f} ms/step  n={v['count']//n}")
+for s in opt.timer.summary():
+    print(f"{s.name:60s} {s.total/n*1e3:9.2f} ms/step  n={s.count//n}")
 print("pcg", opt.fem.engine.pcg_log[-n:], "filter iters", opt.filter._dev_state.solve_iters[-8:])

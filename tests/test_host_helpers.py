@@ -1,0 +1,96 @@
+"""CPU tests of host-side helpers that mirror reference utilities: SectionTimer
+(tools/timer.py), element adjacency (mesh/utils.py:139-263, fea/composer.py:351-371),
+task statistics and the small argparse converters."""
+import numpy as np
+import pytest
+
+
+def test_section_timer_interface():
+    import sktopt
+    from sktopt.tools.timer import SectionStats, SectionTimer
+    clock = iter(np.arange(0.0, 100.0, 1.0))
+    t = SectionTimer(clock=lambda: float(next(clock)), hierarchical=True)
+    with t.section("outer"):            # start 0
+        with t.section("inner"):        # start 1, end 2
+            pass
+        with t.section("inner"):        # start 3, end 4
+            pass
+    # outer ends at 5
+    t.add("manual", 0.25)
+
+    @t.wrap("wrapped")
+    def f(x):
+        return x + 1
+    assert f(1) == 2 and f.__name__ == "f"
+    st = {s.name: s for s in t.stats()}
+    assert isinstance(st["outer"], SectionStats)
+    assert st["outer"].total == 5.0 and st["outer"].count == 1
+    assert st["outer>inner"].total == 2.0 and st["outer>inner"].count == 2
+    assert st["outer>inner"].avg == 1.0 and st["outer>inner"].max == 1.0
+    assert st["manual"].total == 0.25 and st["wrapped"].count == 1
+    assert [s.name for s in t.summary()][0] == "outer"
+    assert [s.name for s in t.summary(sort_by="name", descending=False)][0] == "manual"
+    own = {s.name: s.total for s in t.summary_self_time()}
+    assert own["outer"] == 3.0 and own["outer>inner"] == 2.0
+    with pytest.raises(ValueError):
+        t.summary(sort_by="bogus")
+    text = t.report()
+    assert text.splitlines()[0].startswith("outer: total=5.000000s")
+    with pytest.raises(RuntimeError, match="matplotlib"):
+        t.plot_bar()
+    t.reset("manual")
+    assert "manual" not in {s.name for s in t.stats()}
+    t.reset()
+    assert t.stats() == [] and t.report() == "No timing data collected."
+    with pytest.raises(ValueError, match="No timing data"):
+        t.plot()
+    flat = sktopt.tools.SectionTimer()
+    with flat.section("a"):
+        with flat.section("b"):
+            pass
+    assert {s.name for s in flat.stats()} == {"a", "b"}
+
+
+def test_element_adjacency_matches_bruteforce():
+    import sktopt
+    from sktopt.mesh import utils
+    from sktopt.fea import composer
+    mesh = sktopt.mesh.toy_problem.create_box_hex(2.0, 1.5, 1.0, 0.5)
+    ne = mesh.nelements
+    sets = [set(mesh.t[:, e].tolist()) for e in range(ne)]
+    brute = np.array([[1 if sets[i] & sets[j] else 0 for j in range(ne)] for i in range(ne)])
+    A = utils.build_element_adjacency_matrix(mesh)
+    assert A.dtype == np.uint8 and np.array_equal(A.toarray(), brute)
+    B = utils.build_element_adjacency_matrix_fast(mesh)
+    assert np.array_equal(B.toarray(), brute - np.eye(ne, dtype=int))
+    nb = utils.get_adjacent_elements_fast(B, [0, 1])
+    expect = sorted(set(np.nonzero(brute[0] | brute[1])[0].tolist()) - {0, 1})
+    assert nb.dtype == np.int32 and nb.tolist() == expect
+    assert nb.tolist() == utils.get_adjacent_elements(mesh, [0, 1])
+    # face neighbours of tetrahedra
+    tet = sktopt.mesh.toy_problem.create_box_tet(1.0, 1.0, 1.0, 0.5)
+    adj = composer.adjacency_matrix(tet)
+    faces = [{frozenset(c) for c in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))}]
+    for e in range(tet.nelements):
+        fe = {frozenset(tet.t[list(c), e].tolist()) for c in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))}
+        expect = sorted(j for j in range(tet.nelements) if j != e and fe & {
+            frozenset(tet.t[list(c), j].tolist()) for c in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))})
+        assert sorted(adj[e]) == expect
+
+
+def test_task_statistics_and_converters(capsys):
+    import sktopt
+    from sktopt.core import misc
+    tsk = sktopt.mesh.toy_problem.toy_test()
+    st = tsk.nodes_and_elements_stats()
+    assert abs(st["nodes"]["min"] - 1.0) < 1e-12 and abs(st["elements"]["max"] - 1.0) < 1e-12
+    assert "=== Distance between nodes ===" in capsys.readouterr().out
+    assert np.array_equal(tsk.force_elements_all, np.unique(tsk.neumann_elements))
+    t2 = sktopt.mesh.toy_problem.toy2()
+    assert t2.n_tasks == 2
+    assert np.array_equal(t2.force_elements_all,
+                          np.unique(np.concatenate([np.ravel(a) for a in t2.neumann_elements])))
+    assert misc.str2bool("Yes") is True and misc.str2bool("0") is False and misc.str2bool(True) is True
+    with pytest.raises(Exception):
+        misc.str2bool("maybe")
+    assert misc.float_or_none("None") is None and misc.float_or_none("1.5") == 1.5
