@@ -322,6 +322,7 @@ class FeaEngine:
 
 
 _ENGINES: dict = {}
+_MAX_ENGINES = 16
 
 
 def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0, shard: bool = True) -> FeaEngine:
@@ -331,6 +332,10 @@ def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0, shard: bool = 
            None if d is None else (d.size, int(d.sum()) if d.size else 0))
     ent = _ENGINES.get(key)
     if ent is None or ent[0] is not basis:
+        # bounded cache: the oldest entry goes first (its owner, if any, still
+        # holds the engine; only the lookup is forgotten)
+        while len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.pop(next(iter(_ENGINES)))
         ent = (basis, FeaEngine(basis, d, kind, nu, comm=comm))
         _ENGINES[key] = ent
     return ent[1]

@@ -22,6 +22,7 @@ assembled: both are applied matrix-free by the scalar grid operator
 """
 from __future__ import annotations
 
+import hashlib
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -229,7 +230,8 @@ def _state_for(mesh, elements_volume, design_mask) -> _HelmholtzDevice:
     vol = np.ones(mesh.nelements) if elements_volume is None \
         else np.ascontiguousarray(elements_volume, dtype=np.float64)
     mask = None if design_mask is None else np.ascontiguousarray(design_mask, dtype=bool)
-    key = (id(mesh), vol.tobytes(), None if mask is None else mask.tobytes())
+    digest = lambda a: hashlib.blake2b(a.tobytes(), digest_size=16).digest()
+    key = (id(mesh), digest(vol), None if mask is None else digest(mask))
     ent = _FUNC_STATES.get(key)
     if ent is None or ent[0] is not mesh:
         if len(_FUNC_STATES) >= 4:
