@@ -94,10 +94,18 @@ def exact_matrices():
         e = sy.expand(e.subs({x: xm[0], y: xm[1], z: xm[2]}, simultaneous=True))
         return detJ * sy.integrate(e, (t, 0, 1 - r - s), (s, 0, 1 - r), (r, 0, 1))
     tetK, tetL, tetM = forms(Nt, tet_int)
+    # unit cube (the toy meshes are grids of cubes: Ke(h) = h Ke(1), Le(h) = h Le(1),
+    # Me(h) = h^3 Me(1))
+    Nc = []
+    for vx, vy, vz in HEX_VERTS:
+        Nc.append((x if vx else 1 - x) * (y if vy else 1 - y) * (z if vz else 1 - z))
+    cube_int = lambda e: sy.integrate(sy.expand(e), (x, 0, 1), (y, 0, 1), (z, 0, 1))
+    cubeK, cubeL, cubeM = forms(Nc, cube_int)
     hex_p = np.array([[float(sy.Rational(BRICK[d])) * v[d] for v in HEX_VERTS]
                       for d in range(3)])
     tet_p = np.array([[float(sy.Rational(v)) for v in row] for row in TET]).T
-    return dict(nu=float(nu), hex_p=hex_p, hex_K=hexK, hex_L=hexL, hex_M=hexM,
+    return dict(nu=float(nu), cube_K=cubeK, cube_L=cubeL, cube_M=cubeM,
+                hex_p=hex_p, hex_K=hexK, hex_L=hexL, hex_M=hexM,
                 tet_p=tet_p, tet_K=tetK, tet_L=tetL, tet_M=tetM, tet_vol=float(vol))
 
 
@@ -159,6 +167,10 @@ def oracle_regression():
 def main():
     ex = exact_matrices()
     np.savez_compressed(os.path.join(HERE, "exact_element_matrices.npz"), **ex)
+    if "--exact-only" in sys.argv:        # keep the frozen regression vectors
+        print("exact_element_matrices.npz",
+              os.path.getsize(os.path.join(HERE, "exact_element_matrices.npz")), "bytes")
+        return
     reg = oracle_regression()
     np.savez_compressed(os.path.join(HERE, "oracle_regression.npz"), **reg)
     for f in ("exact_element_matrices.npz", "oracle_regression.npz"):
