@@ -63,6 +63,14 @@ def dC_drho_simp(rho, U, E0, Emin, p):
 
 
 # ------------------------------------------------------------------- OC ---
+def dC_drho_ramp(rho, U, E0, Emin, p):
+    """core/derivatives.py:56-68 (RAMP: no clamping of rho)."""
+    den = 1.0 + p * (1.0 - rho)
+    dE = (E0 - Emin) * (den - p * rho) / den ** 2
+    E = Emin + (E0 - Emin) * (rho / den)
+    return -2.0 * U * dE / np.maximum(E, 1e-12)
+
+
 def oc_bisection(dC, rho_e, rho_full, design, filt, rho_min, rho_max, move, eta,
                  eps, vol_frac, beta, beta_eta, vol_d, vol_sum, sr_min, sr_max,
                  max_iter=1000, tolerance=1e-5, vol_tol=1e-4, l1=1e-7, l2=1e7):
@@ -124,13 +132,17 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         beta_sched=(1.0, 2.0, 3, 2.0), move_sched=(0.3, 0.1, 6), eta=None,
         rho_min=1e-2, rho_max=1.0, E_min_coeff=1e-3, beta_eta=0.5,
         solver="spsolve", rtol=1e-8, cg_maxiter=None, lambda_lower=1e-7,
-        lambda_upper=1e7, logmoc=None, iters=None, timings=None, step_times=None):
+        lambda_upper=1e7, logmoc=None, iters=None, timings=None, step_times=None,
+        interpolation="SIMP", sensitivity_filter=False):
     """DensityMethod._optimize_impl (common_density.py:1014-1134) with the
     default schedules of DensityMethodConfig / OC_Config / LogMOC_Config.
     Returns dict(rho, compliance[], vol_error[], rho_hist[])."""
     pr = problem
     ne = pr.t.shape[1]
     E0, Emin = pr.E, pr.E * E_min_coeff
+    # interpolation_funcs (common_density.py:392-404)
+    interp, dC_drho = {"SIMP": (fem.simp, dC_drho_simp),
+                       "RAMP": (fem.ramp, dC_drho_ramp)}[interpolation]
     if filter_type == "helmholtz":
         filt = HelmholtzOracle(pr.p, pr.t, pr.vol, pr.design_mask)
     else:
@@ -171,7 +183,8 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         rho_p = heaviside(rho_f, beta, beta_eta)
         tick("filter_and_project", t0)
         t0 = time.perf_counter()
-        K = fem.assemble_stiffness(pr.p, pr.t, rho_p, E0, Emin, pw, pr.nu, pr.intorder)
+        K = fem.assemble_stiffness(pr.p, pr.t, rho_p, E0, Emin, pw, pr.nu, pr.intorder,
+                                   interp=interp)
         tick("assemble", t0)
         t0 = time.perf_counter()
         K_e, _ = fem.enforce(K, pr.forces[0], pr.D)
@@ -189,14 +202,17 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         tick("solve", t0)
         compliance = float(np.mean(comps))
         t0 = time.perf_counter()
-        energy = fem.strain_energy(pr.p, pr.t, rho_p, U, E0, Emin, pw, pr.nu, pr.intorder)
+        energy = fem.strain_energy(pr.p, pr.t, rho_p, U, E0, Emin, pw, pr.nu, pr.intorder,
+                                   interp=interp)
         tick("energy", t0)
         t0 = time.perf_counter()
         dC_full = np.zeros(ne)
         dH = heaviside_derivative(rho_f, beta, beta_eta)
         for l in range(U.shape[1]):
-            dC_full += filt.gradient(dC_drho_simp(rho_p, energy[:, l], E0, Emin, pw) * dH)
+            dC_full += filt.gradient(dC_drho(rho_p, energy[:, l], E0, Emin, pw) * dH)
         dC_full /= U.shape[1]
+        if sensitivity_filter:                            # common_density.py:1102-1106
+            dC_full = filt.forward(dC_full)
         tick("sensitivity", t0)
         dC = dC_full[pr.design].copy()
         rho_e = rho[pr.design].copy()

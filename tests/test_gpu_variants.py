@@ -1,0 +1,85 @@
+"""Configuration branches of the loop: RAMP interpolation
+(fea/composer.py:25-39, core/derivatives.py:56-68), the sensitivity filter
+(common_density.py:1102-1106), the spatial filter inside the loop and the
+`scaling=True` path (common_density.py:626-641)."""
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sktopt
+    from sktopt._b200 import device as dev
+    return sktopt, dev
+
+
+def _oc(sktopt, iters, **kw):
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg = sktopt.core.OC_Config(dst_path=tmp, max_iters=iters, record_times=iters, **kw)
+        tsk = sktopt.mesh.toy_problem.toy_test()
+        p0 = tsk.mesh.p.copy()
+        opt = sktopt.core.OC_Optimizer(cfg, tsk)
+        opt.parameterize()
+        opt.optimize()
+        comp = np.asarray(opt.recorder.as_object().compliance)
+        return comp, opt._state.rho.cpu().numpy(), opt, p0
+
+
+def test_ramp_kernels_and_loop(gpu, toy_oracle):
+    sktopt, dev = gpu
+    from oracle import fem, optim
+    rng = np.random.default_rng(0)
+    rho = rng.uniform(0.0, 1.0, 4001)
+    U = rng.uniform(0.0, 5.0, 4001)
+    E = dev.interpolate_modulus(dev.to_dev(rho), 210e3, 210.0, 3.0, ramp=True).cpu().numpy()
+    assert np.max(np.abs(E - fem.ramp(rho, 210e3, 210.0, 3.0))) <= 1e-12 * 210e3
+    g = dev.dc_drho(dev.to_dev(rho), dev.to_dev(U), 210e3, 210.0, 3.0, ramp=True).cpu().numpy()
+    g_ref = optim.dC_drho_ramp(rho, U, 210e3, 210.0, 3.0)
+    assert np.max(np.abs(g - g_ref)) <= 1e-13 * np.abs(g_ref).max()
+    g2 = sktopt.core.derivatives.dC_drho_ramp(rho, U, 210e3, 210.0, 3.0)
+    assert np.max(np.abs(np.asarray(g2) - g_ref)) <= 1e-13 * np.abs(g_ref).max()
+    o, pr = toy_oracle
+    comp, rho_fin, _, _ = _oc(sktopt, 4, interpolation="RAMP")
+    ref = optim.run(pr, "oc", max_iters=4, interpolation="RAMP")
+    assert np.max(np.abs(comp - ref["compliance"]) / np.abs(ref["compliance"])) <= 1e-6
+    assert np.max(np.abs(rho_fin - ref["rho_final"])) <= 1e-4
+
+
+@pytest.mark.parametrize("sens", [
+    False,
+    pytest.param(True, marks=pytest.mark.xfail(
+        strict=False, reason="written after this round's GPU budget was spent: the spatial-filter "
+                             "loop (sens=False) ran green on a B200, this branch has not run yet")),
+])
+def test_spatial_filter_loop_and_sensitivity_filter(gpu, toy_oracle, sens):
+    """OC loop with the neighbour-weighted filter (a13 inside a1) and, on top, the
+    sensitivity filter dC <- F(dC) (common_density.py:1102-1106).  (With the
+    Helmholtz filter and fixed elements the reference's sensitivity filter pins
+    sensitivities to +1 and the OC update takes the root of a negative number:
+    NaN there as well; the spatial filter is the combination that works.)"""
+    sktopt, dev = gpu
+    from oracle import optim
+    o, pr = toy_oracle
+    const = sktopt.tools.SchedulerConfig.constant
+    comp, rho_fin, opt, _ = _oc(sktopt, 4, filter_type="spacial", sensitivity_filter=sens,
+                                filter_radius=const(target_value=1.5))
+    ref = optim.run(pr, "oc", max_iters=4, filter_type="spacial", filter_radius=1.5,
+                    sensitivity_filter=sens)
+    assert np.max(np.abs(comp - ref["compliance"]) / np.abs(ref["compliance"])) <= 1e-6
+    assert np.max(np.abs(rho_fin - ref["rho_final"])) <= 1e-4
+
+
+def test_scaling_path_runs_and_restores_the_task(gpu):
+    sktopt, dev = gpu
+    comp, rho_fin, opt, p0 = _oc(sktopt, 2, scaling=True)
+    assert comp.size == 2 and np.all(np.isfinite(comp)) and np.all(comp > 0.0)
+    assert rho_fin.min() >= 1e-2 - 1e-15 and rho_fin.max() <= 1.0 + 1e-15
+    # _finalize() unscales: the task's mesh is back to its original size
+    assert np.max(np.abs(opt.tsk.mesh.p - p0)) <= 1e-12 * np.abs(p0).max()
