@@ -1,6 +1,12 @@
-"""Filter interface (reference ``filters/base.py:9-37``).  As in the reference
-the method that applies the filter is ``forward`` (``run`` is declared there
-but never implemented or called)."""
+"""Density-filter interface shared by the Helmholtz and the neighbour-weighted
+filter (same four fields and method names as the reference's ``filters/base.py``,
+so that user code constructing or subclassing filters keeps working).
+
+The method that applies a filter is ``forward``; ``run`` is also declared by the
+reference but nothing implements or calls it -- it is kept as a
+name only.  Concrete filters accept NumPy arrays (copied to the device and back)
+or CUDA tensors (kept on the device) in ``forward`` / ``gradient``.
+"""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -9,26 +15,34 @@ from typing import Optional
 import numpy as np
 
 
-@dataclass
-class BaseFilter():
-    mesh: object
-    elements_volume: np.ndarray
-    radius: float
-    design_mask: Optional[np.ndarray] = None
+def _missing(obj, what: str):
+    owner = obj.__name__ if isinstance(obj, type) else type(obj).__name__
+    return NotImplementedError(f"{owner} does not implement {what}()")
 
-    def update_radius(self, radius: float, **args):
-        raise NotImplementedError("")
+
+@dataclass
+class BaseFilter:
+    mesh: object                                 # sktopt._fem.Mesh (skfem.Mesh in the reference)
+    elements_volume: np.ndarray                  # (n_elements,)
+    radius: float
+    design_mask: Optional[np.ndarray] = None     # bool (n_elements,), None = all design
 
     @classmethod
     def from_defaults(cls, mesh, elements_volume: np.ndarray, radius: float = 0.3,
-                      design_mask: Optional[np.ndarray] = None) -> 'BaseFilter':
-        raise NotImplementedError("")
+                      design_mask: Optional[np.ndarray] = None) -> "BaseFilter":
+        raise _missing(cls, "from_defaults")
+
+    def update_radius(self, radius: float, **args):
+        """Called by the optimiser when the radius schedule moves."""
+        raise _missing(self, "update_radius")
+
+    def forward(self, rho_element):
+        """Filtered element densities."""
+        raise _missing(self, "forward")
+
+    def gradient(self, v):
+        """Adjoint of ``forward`` applied to element sensitivities ``v``."""
+        raise _missing(self, "gradient")
 
     def run(self, rho_element: np.ndarray) -> np.ndarray:
-        raise NotImplementedError("")
-
-    def forward(self, rho_element: np.ndarray) -> np.ndarray:
-        raise NotImplementedError("")
-
-    def gradient(self, v: np.ndarray) -> np.ndarray:
-        raise NotImplementedError("")
+        raise _missing(self, "run")
