@@ -104,6 +104,26 @@ def main():
     out["pcg_solve"] = {"s": time.time() - t0, "iters": eng.pcg.last_iters,
                         "converged": eng.pcg.last_converged, "relres": eng.pcg.last_relres}
 
+    # matrix-free operator, multigrid and the uniform energy kernel (tensor grids)
+    eng2 = get_engine(tsk.basis, tsk.dirichlet_dofs, KE_ELASTIC, tsk.nu)
+    if eng2.matrix_free:
+        eng2.set_modulus(rho, tsk.E, tsk.E * 1e-3, 3.0)
+        eng2.prepare()
+        n_nodes = eng2.n_dof // 3
+        ms, best = timeit(lambda: eng2.spmv(x, out=y), reps, flush)
+        out["gridop_fp64"] = {"ms": ms, "best_ms": best,
+                              "TFLOPs": n_nodes * 1200 / ms / 1e9}
+        if eng2.mg is not None:
+            r = torch.randn(n, dtype=dev.F64, device="cuda")
+            z = torch.empty_like(r)
+            ms, best = timeit(lambda: eng2.mg.vcycle(r, z), reps, flush)
+            out["mg_vcycle"] = {"ms": ms, "best_ms": best, "levels": eng2.mg.n_levels,
+                                "sweeps": eng2.mg.sweeps}
+            ms, best = timeit(lambda: eng2.mg.setup(), max(3, reps // 4), flush)
+            out["mg_setup"] = {"ms": ms, "best_ms": best}
+        ms, best = timeit(lambda: eng2.energy(u, out=e), reps, flush)
+        out["energy_uniform"] = {"ms": ms, "best_ms": best, "alg_GBps": en_bytes / ms / 1e6}
+
     # Helmholtz filter
     filt = sktopt.filters.HelmholtzFilterNodal.from_defaults(
         tsk.mesh, tsk.elements_volume, 0.01, design_mask=tsk.design_mask)
@@ -117,6 +137,22 @@ def main():
     st = filt._dev_state
     out["helmholtz_forward"] = {"ms": (time.time() - t0) / 5 * 1e3,
                                 "pcg_iters": st.solve_iters[-5:]}
+    if st.grid is not None:
+        xn = torch.randn(st.n_nodes, dtype=dev.F64, device="cuda")
+        yn = torch.empty_like(xn)
+        ms, best = timeit(lambda: st.gop_A.apply(xn, out=yn), reps, flush)
+        out["scalar_stencil"] = {"ms": ms, "best_ms": best,
+                                 "alg_GBps": st.n_nodes * 17 / ms / 1e6}
+        if st.fd is not None:
+            ms, best = timeit(lambda: st.fd.solve(xn, out=yn), reps, flush)
+            out["helmholtz_direct_solve"] = {"ms": ms, "best_ms": best}
+        g = filt.gradient(-r)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(5):
+            filt.gradient(-r)
+        torch.cuda.synchronize()
+        out["helmholtz_gradient"] = {"ms": (time.time() - t0) / 5 * 1e3}
     print(json.dumps(out))
 
 
