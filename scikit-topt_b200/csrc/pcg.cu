@@ -414,6 +414,18 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
       s->prof_count += 1;
     }
     n_ev = 0;
+    if (launched == 0 && s->S_h->bb == 0.0) {
+      // b = 0: the solution is x = 0 whatever the start vector was (scipy's cg
+      // returns it at once); with tol2 = 0 a non-zero warm start would
+      // otherwise iterate to maxiter.  bb is the global sum: every rank agrees.
+      SKTB_CUDA_OK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+      if (info_h) {
+        info_h[0] = 0;
+        info_h[1] = 1;
+      }
+      if (relres_h) *relres_h = 0.0;
+      return 0;
+    }
     if (s->S_h->rr <= s->S_h->tol2 || launched >= maxiter) break;
     int batch = maxiter - launched;
     if (batch > check_every) batch = check_every;

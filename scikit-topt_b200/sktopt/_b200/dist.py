@@ -83,6 +83,23 @@ def default_comm():
     return _DEFAULT
 
 
+def is_io_rank() -> bool:
+    """True on the one process that owns the run directory (rank 0 of the
+    ``torch.distributed`` job, or the only process).  Every rank computes the
+    same densities and histories; only this one writes them."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank() == 0
+    return True
+
+
+def io_barrier():
+    """Other ranks wait here until the I/O rank has prepared the run directory."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def reset_default_comm():
     global _DEFAULT
     _DEFAULT = None

@@ -27,7 +27,8 @@ import torch
 import sktopt
 from sktopt import fea, filters, tools
 from sktopt._b200 import device as dev
-from sktopt.core import derivatives, misc, projection
+from sktopt._b200 import dist as bdist
+from sktopt.core import derivatives, misc, projection, visualization
 from sktopt.fea import composer
 from sktopt.fea._petsc_compat import (
     PETScOptions, normalize_petsc_options, petsc_options_for_solver,
@@ -236,16 +237,21 @@ class DensityMethod(DensityMethodBase):
         self.timer = tools.SectionTimer(hierarchical=True)
         if cfg.scaling is True:
             self.scale()
-        os.makedirs(cfg.dst_path, exist_ok=True)
-        cfg.export(cfg.dst_path)
+        # one process per GPU: every rank holds the same state, rank 0 alone owns
+        # the run directory (set-up, cfg.json, checkpoints, histories)
+        self._io = bdist.is_io_rank()
+        if self._io:
+            os.makedirs(cfg.dst_path, exist_ok=True)
+            cfg.export(cfg.dst_path)
+            if cfg.restart is not True:
+                shutil.rmtree(f"{cfg.dst_path}/mesh_rho", ignore_errors=True)
+                os.makedirs(f"{cfg.dst_path}/mesh_rho", exist_ok=True)
+                os.makedirs(f"{cfg.dst_path}/data", exist_ok=True)
+        bdist.io_barrier()
         if cfg.design_dirichlet is False:
             tsk.exlude_dirichlet_from_design()
         if cfg.restart is True:
             self.load_parameters()
-        else:
-            shutil.rmtree(f"{cfg.dst_path}/mesh_rho", ignore_errors=True)
-            os.makedirs(f"{cfg.dst_path}/mesh_rho")
-            os.makedirs(f"{cfg.dst_path}/data", exist_ok=True)
 
         interp = interpolation_funcs(cfg)[0]
         if isinstance(tsk, sktopt.mesh.LinearElasticity):
@@ -337,7 +343,7 @@ class DensityMethod(DensityMethodBase):
         else:
             self.schedulers.add("eta", cfg.eta, cfg.eta, -1, cfg.max_iters)
         self.schedulers.set_iters_max(cfg.max_iters)
-        if export:
+        if export and getattr(self, "_io", True):
             self.schedulers.export()
         self._schedulers_initialized = True
 
@@ -451,29 +457,34 @@ class DensityMethod(DensityMethodBase):
             return
         if self.cfg.scaling is True:
             self.unscale()
-        self.recorder.export_histories(fname="histories.npz")
+        if self._io:
+            self.recorder.export_histories(fname="histories.npz")
         self._completed = True
 
     def _export_iteration(self, iter_num, state, energy_mean):
         cfg = self.cfg
         self.recorder.print()
         self.recorder.export_progress()
+        # info_mesh-XXXXXXXX.vtu with the cell fields the reference writes
+        # (common_density.py:1199-1204); SKTOPT_EXPORT_VTU=0 skips it
+        if os.environ.get("SKTOPT_EXPORT_VTU", "1") != "0":
+            visualization.export_mesh_with_info(
+                self.tsk.mesh, cell_data_names=["rho_projected", "energy"],
+                cell_data_values=[state.rho_projected.cpu().numpy(),
+                                  energy_mean.cpu().numpy()],
+                filepath=cfg.vtu_path(iter_num))
         rho_design = dev.gather(state.rho, self._design_idx).cpu().numpy()
         np.savez_compressed(
             f"{cfg.dst_path}/data/{str(iter_num).zfill(6)}-rho.npz",
             rho_design_elements=rho_design)
-        if os.environ.get("SKTOPT_EXPORT_FIELDS", "0") == "1":
-            np.savez_compressed(
-                cfg.vtu_path(iter_num).replace(".vtu", ".npz"),
-                rho_projected=state.rho_projected.cpu().numpy(),
-                energy=energy_mean.cpu().numpy())
 
     # ----------------------------------------------------------------- loop
     def _optimize_impl(self, max_steps: int | None = None):
         tsk, cfg = self.tsk, self.cfg
         if not getattr(self, "_condition_exported", False):
             # the reference rewrites this file on every call; once is enough
-            tsk.export_analysis_condition_on_mesh(cfg.dst_path)
+            if self._io:
+                tsk.export_analysis_condition_on_mesh(cfg.dst_path)
             self._condition_exported = True
         if not self._ensure_state_initialized():
             return
@@ -598,7 +609,7 @@ class DensityMethod(DensityMethodBase):
                 or iter_num == iter_limit - 1
             )
             if export_now:
-                if self.export_enabled:
+                if self.export_enabled and self._io:
                     with self._timed_section("export_iteration"):
                         self._export_iteration(iter_num, st, st.energy_mean)
                 if conv_rho and conv_kkt:

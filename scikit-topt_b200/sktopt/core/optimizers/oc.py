@@ -53,7 +53,9 @@ def bisection_with_physical_volume(
     iter_num = 0
     lmid = 0.5 * (l1 + l2)
     vol_error = 0.0
+    steps = 0
     while True:
+        steps += 1
         dev.oc_candidate(dC, rho_e, lmid, eps, eta, move_limit, rho_min, rho_max,
                          scaling_rate_min, scaling_rate_max, design_elements,
                          scaling_rate, rho_design_eles, rho_full_candidate)
@@ -77,7 +79,13 @@ def bisection_with_physical_volume(
             l2 = lmid
         iter_num += 1
         lmid = 0.5 * (l1 + l2)
+    # candidate evaluations of this call (the return value keeps the reference's
+    # two-tuple); read by OC_Optimizer.rho_update for its bisection_steps log
+    bisection_with_physical_volume.last_steps = steps
     return lmid, vol_error
+
+
+bisection_with_physical_volume.last_steps = 0
 
 
 @dataclass
@@ -162,8 +170,6 @@ class OC_Optimizer(common_density.DensityMethod):
             kkt_scale = self.running_scale
 
         with self._timed_section("bisection"):
-            filt_iters0 = len(getattr(getattr(self.filter, "_dev_state", None),
-                                      "solve_iters", []))
             lmid, vol_error = bisection_with_physical_volume(
                 dC_drho_design_eles, self._rho_e_buffer, state.rho,
                 self._design_idx, self.filter, cfg.rho_min, cfg.rho_max,
@@ -176,9 +182,7 @@ class OC_Optimizer(common_density.DensityMethod):
                 max_iter=1000, tolerance=1e-5,
                 l1=cfg.lambda_lower, l2=cfg.lambda_upper,
             )
-            filt_iters1 = len(getattr(getattr(self.filter, "_dev_state", None),
-                                      "solve_iters", []))
-            self.bisection_steps.append(filt_iters1 - filt_iters0)
+            self.bisection_steps.append(bisection_with_physical_volume.last_steps)
 
         with self._timed_section("kkt"):
             res, n_int = dev.kkt_residual(

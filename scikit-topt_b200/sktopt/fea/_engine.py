@@ -13,6 +13,7 @@ element-wise stages see the full vector.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 
 import numpy as np
@@ -304,9 +305,16 @@ class FeaEngine:
         self.pcg_log.append((self.pcg.last_iters, self.pcg.last_converged,
                              self.pcg.last_relres))
         if not self.pcg.last_converged:
-            logger.warning(
-                f"PCG stopped at {self.pcg.last_iters} iterations with "
-                f"relres={self.pcg.last_relres:.3e} (rtol={rtol:g})")
+            msg = (f"PCG stopped at {self.pcg.last_iters} iterations with "
+                   f"relres={self.pcg.last_relres:.3e} (rtol={rtol:g})")
+            # the PCG also stands in for the reference's direct solvers, whose
+            # results are exact: a solve that is still far from the tolerance must
+            # not feed compliance and sensitivities silently.  (Within 100 x rtol
+            # it is logged only, like scipy's cg `info` in the reference.)
+            far = not np.isfinite(self.pcg.last_relres) or self.pcg.last_relres > 100.0 * rtol
+            if far and os.environ.get("SKTOPT_B200_STRICT_SOLVE", "1") != "0":
+                raise RuntimeError(msg)
+            logger.warning(msg)
         return x
 
     def spmv(self, x, vals=None, out=None):
@@ -328,8 +336,11 @@ _MAX_ENGINES = 16
 def get_engine(basis, dirichlet_dofs, kind: int, nu: float = 0.0, shard: bool = True) -> FeaEngine:
     d = None if dirichlet_dofs is None else np.asarray(dirichlet_dofs, dtype=np.int64)
     comm = bdist.default_comm() if shard else None
-    key = (id(basis), kind, float(nu), comm is not None,
-           None if d is None else (d.size, int(d.sum()) if d.size else 0))
+    # the Dirichlet set is part of the operator: key on a digest of the sorted
+    # index array (size + sum alone collide, e.g. {1,4} vs {2,3})
+    dkey = None if d is None else (d.size, hashlib.blake2b(
+        np.sort(d).tobytes(), digest_size=16).hexdigest())
+    key = (id(basis), kind, float(nu), comm is not None, dkey)
     ent = _ENGINES.get(key)
     if ent is None or ent[0] is not basis:
         # bounded cache: the oldest entry goes first (its owner, if any, still

@@ -107,6 +107,17 @@ class _HeatDevice:
         self.task = task
         basis = task.basis
         d_nodes = _as_list(task.dirichlet_nodes)
+        # One enforced operator serves every load case, so the load cases must fix
+        # the same nodes (their VALUES may differ).  The reference enforces per
+        # load with D_i (fea/solver_heat.py:160-175); different node sets would
+        # need one operator per load and are rejected instead of being solved with
+        # the wrong boundary rows.
+        d0 = np.unique(np.asarray(d_nodes[0], dtype=np.int64))
+        for dn in d_nodes[1:]:
+            if not np.array_equal(d0, np.unique(np.asarray(dn, dtype=np.int64))):
+                raise NotImplementedError(
+                    "heat load cases with different Dirichlet node sets are not supported: "
+                    "all load cases must fix the same nodes (values may differ)")
         # the heat operator is replicated on every rank (scalar system, small)
         self.eng = get_engine(basis, np.asarray(d_nodes[0], dtype=np.int64), KE_LAPLACE,
                               shard=False)

@@ -199,8 +199,9 @@ class FEMDomain():
         return self.neumann_nodes
 
     def export_analysis_condition_on_mesh(self, dst_path: str):
-        """The reference writes ``condition.vtu`` through meshio (absent here);
-        the same node / element colouring is stored as ``condition.npz``."""
+        """``condition.vtu`` with the node / element colouring of the reference
+        (``mesh/task_common.py:360-396``), written by the native VTU writer."""
+        from sktopt.core.visualization import export_mesh_with_info
         mesh = self.basis.mesh
         node_color = np.zeros(mesh.nvertices, dtype=int)
         if self.neumann_nodes is not None:
@@ -216,8 +217,10 @@ class FEMDomain():
         elem_color[self.fixed_elements] = 2
         elem_color[self.design_elements] = 3
         try:
-            np.savez_compressed(f"{dst_path}/condition.npz",
-                                node_color=node_color, condition=elem_color)
+            export_mesh_with_info(mesh, point_data_values=[node_color],
+                                  point_data_names=["node_color"],
+                                  cell_data_values=[elem_color], cell_data_names=["condition"],
+                                  filepath=f"{dst_path}/condition.vtu")
         except OSError:
             pass
 
@@ -250,10 +253,18 @@ class FEMDomain():
         mesh = self.basis.mesh
         scaled = type(mesh)(mesh.p * L_scale, mesh.t, mesh.boundaries, mesh.subdomains)
         self.basis = Basis(scaled, self.basis.elem, intorder=self.basis.intorder)
-        if isinstance(self.force, np.ndarray):
-            self.force *= F_scale
-        elif isinstance(self.force, list):
-            for f in self.force:
+        # Scale the load arrays in place, never through the ``force`` property:
+        # for a single-load task its getter returns neumann_linear[0] and the
+        # setter would store that ndarray back as the list itself, so n_tasks
+        # would become n_dof (the reference, mesh/task_common.py:466-476, has
+        # that defect; it is not reproduced).
+        loads = getattr(self, "neumann_linear", None)
+        if loads is None:
+            loads = self.force
+        if isinstance(loads, np.ndarray):
+            loads *= F_scale
+        elif isinstance(loads, list):
+            for f in loads:
                 f *= F_scale
         else:
             raise ValueError("should be ndarray or list of ndarray")

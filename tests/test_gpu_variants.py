@@ -52,12 +52,7 @@ def test_ramp_kernels_and_loop(gpu, toy_oracle):
     assert np.max(np.abs(rho_fin - ref["rho_final"])) <= 1e-4
 
 
-@pytest.mark.parametrize("sens", [
-    False,
-    pytest.param(True, marks=pytest.mark.xfail(
-        strict=False, reason="written after this round's GPU budget was spent: the spatial-filter "
-                             "loop (sens=False) ran green on a B200, this branch has not run yet")),
-])
+@pytest.mark.parametrize("sens", [False, True])
 def test_spatial_filter_loop_and_sensitivity_filter(gpu, toy_oracle, sens):
     """OC loop with the neighbour-weighted filter (a13 inside a1) and, on top, the
     sensitivity filter dC <- F(dC) (common_density.py:1102-1106).  (With the
@@ -74,12 +69,26 @@ def test_spatial_filter_loop_and_sensitivity_filter(gpu, toy_oracle, sens):
                     sensitivity_filter=sens)
     assert np.max(np.abs(comp - ref["compliance"]) / np.abs(ref["compliance"])) <= 1e-6
     assert np.max(np.abs(rho_fin - ref["rho_final"])) <= 1e-4
+    # counted inside the bisection loop itself, whatever filter is used
+    assert opt.bisection_steps == ref["bisection_steps"]
 
 
-def test_scaling_path_runs_and_restores_the_task(gpu):
+def test_scaling_path_runs_and_restores_the_task(gpu, toy_oracle):
     sktopt, dev = gpu
     comp, rho_fin, opt, p0 = _oc(sktopt, 2, scaling=True)
     assert comp.size == 2 and np.all(np.isfinite(comp)) and np.all(comp > 0.0)
     assert rho_fin.min() >= 1e-2 - 1e-15 and rho_fin.max() <= 1.0 + 1e-15
     # _finalize() unscales: the task's mesh is back to its original size
     assert np.max(np.abs(opt.tsk.mesh.p - p0)) <= 1e-12 * np.abs(p0).max()
+    # scale() must not turn the single load into a list of n_dof "loads"
+    assert opt.tsk.n_tasks == 1 and isinstance(opt.tsk.neumann_linear, list)
+    # the same run in the oracle on the scaled task (common_density.py:626-641:
+    # p / max extent, F / 1e5; element volumes keep their unscaled values)
+    from oracle import optim
+    o, pr = toy_oracle
+    L = np.max(np.ptp(o["p"], axis=1))
+    pr2 = optim.Problem(o["p"] / L, o["t"], o["dirichlet_dofs"], o["force"] / 1e5, o["design"],
+                        o["pinned"], o["volumes"], o["E"], o["nu"], fixed=o["fixed"])
+    ref = optim.run(pr2, "oc", max_iters=2)
+    assert np.max(np.abs(comp - ref["compliance"]) / np.abs(ref["compliance"])) <= 1e-6
+    assert np.max(np.abs(rho_fin - ref["rho_final"])) <= 1e-4

@@ -49,3 +49,52 @@ def test_histories_npz_round_trip_and_append():
         rec2.feed_data("compliance", 0.123)                   # a resumed run appends
         assert np.allclose(rec2.as_object().compliance, [1.0, 0.5, 1.0 / 3.0, 0.25, 0.123])
         assert rec2.latest("vol_error") == 0.1 * 3
+
+
+def test_vtu_writer_round_trip(tmp_path):
+    """info_mesh-*.vtu / condition.vtu (reference core/visualization.py:22-84,
+    mesh/task_common.py:360-396) without meshio: fields, connectivity in the
+    mesh's own local order and VTK cell types survive a write/read cycle."""
+    import numpy as np
+    from sktopt._fem import MeshHex, MeshTet
+    from sktopt.core.visualization import export_mesh_with_info, read_vtu
+    ax = [np.linspace(0, 1, n) for n in (4, 3, 3)]
+    rng = np.random.default_rng(0)
+    for mesh, vtk_type in ((MeshHex.init_tensor(*ax), 12), (MeshTet.init_tensor(*ax), 10)):
+        rho = rng.uniform(size=mesh.t.shape[1])
+        en = rng.uniform(size=mesh.t.shape[1])
+        col = rng.integers(0, 4, mesh.p.shape[1])
+        f = str(tmp_path / f"m{vtk_type}.vtu")
+        export_mesh_with_info(mesh, point_data_values=[col], point_data_names=["node_color"],
+                              cell_data_values=[rho, en],
+                              cell_data_names=["rho_projected", "energy"], filepath=f)
+        r = read_vtu(f)
+        assert np.array_equal(r["points"], mesh.p.T)
+        assert np.array_equal(r["connectivity"].reshape(-1, mesh.t.shape[0]), mesh.t.T)
+        assert np.all(r["types"] == vtk_type)
+        assert np.array_equal(r["offsets"], mesh.t.shape[0] * np.arange(1, mesh.t.shape[1] + 1))
+        assert np.array_equal(r["cell_data"]["rho_projected"], rho)
+        assert np.array_equal(r["cell_data"]["energy"], en)
+        assert np.array_equal(r["point_data"]["node_color"], col)
+
+
+def test_task_scale_keeps_the_load_list_and_condition_vtu(tmp_path):
+    """scale() must scale the load arrays in place, not through the
+    ``force`` property (n_tasks went from 1 to n_dof)."""
+    import numpy as np
+    import sktopt
+    from sktopt.core.visualization import read_vtu
+    tsk = sktopt.mesh.toy_problem.toy_test()
+    f0 = tsk.neumann_linear[0].copy()
+    p0 = tsk.mesh.p.copy()
+    assert tsk.n_tasks == 1
+    tsk.scale(0.125, 1e-5)
+    assert tsk.n_tasks == 1 and isinstance(tsk.neumann_linear, list)
+    assert np.allclose(tsk.neumann_linear[0], f0 * 1e-5, rtol=1e-15, atol=0)
+    assert np.allclose(tsk.mesh.p, p0 * 0.125)
+    tsk.scale(8.0, 1e5)
+    assert np.allclose(tsk.neumann_linear[0], f0, rtol=1e-14, atol=0)
+    tsk.export_analysis_condition_on_mesh(str(tmp_path))
+    r = read_vtu(str(tmp_path / "condition.vtu"))
+    assert set(np.unique(r["cell_data"]["condition"])) <= {0, 1, 2, 3}
+    assert r["point_data"]["node_color"].max() == 2
