@@ -165,6 +165,20 @@ int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes, int64_t n_blocks,
  * Coarser levels stay replicated; the restricted residual is all-reduced and
  * the level-0 smoother exchanges halos through the PCG workspace it runs in.  */
 int sktb_mg_set_level0_range(sktb_mg *m, int64_t node0, int64_t n_global);
+/* z-slab sharding of ANY level (tensor grids; SURVEY.md 8e "element-block
+ * partition"): this rank owns the whole node planes [node0, node0 + n_owned) of
+ * n_global; prev_rank / next_rank own the adjacent planes (-1: none).  The
+ * level's operator arrays then hold the owned rows only (global columns), its
+ * iterate is a full-length vector whose ghost planes are exchanged before every
+ * product; restriction / prolongation between two sharded levels exchange one
+ * plane of the residual / the coarse iterate.  plane_nodes = 0: replicated.
+ * Call before sktb_mg_set_level / sktb_mg_set_level0_grid of that level.       */
+int sktb_mg_set_level_slab(sktb_mg *m, int level, int64_t node0, int64_t n_global,
+                           int64_t plane_nodes, int prev_rank, int next_rank);
+/* y[owned rows] = A_level x_full (ghost planes refreshed first; dist = the PCG
+ * workspace that carries the communicator, NULL on one GPU)                    */
+int sktb_mg_level_apply(sktb_mg *m, int level, sktb_pcg *dist, double *x_full,
+                        double *y_own, void *stream);
 /* transfer between level (fine) and level+1 (coarse).  Nodes per axis (x,y,z)
  * of both grids (node = iy + npy*ix + npy*npx*iz); per-axis interpolation
  * tables on the device, concatenated [x|y|z]: fine index i takes coarse
@@ -186,6 +200,14 @@ int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
                        const double *fine_ke, const double *unit,
                        const int32_t *cls, const double *scale, double *out,
                        void *stream);
+/* the same for the coarse elements [e_lo, e_hi) only (slab-sharded set-up):
+ * out holds them from e_lo on, fine_ke holds the fine elements from fine_base  */
+int sktb_elem_restrict_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
+                             int64_t fine_base, const int32_t *child,
+                             const uint8_t *ptype, const double *Qtab,
+                             const double *fine_ke, const double *unit,
+                             const int32_t *cls, const double *scale, double *out,
+                             void *stream);
 /* ---- matrix-free operators for uniform hexahedral tensor grids --------------
  * Replace the assembled matrix inside the solvers where the reference hands
  * scipy/pyamg an assembled one (elasticity: fea/solver_elastic.py:94-104,
@@ -243,6 +265,10 @@ int sktb_mg_set_level0_grid(sktb_mg *m, const sktb_gridop *op, int64_t n_nodes,
 int sktb_elem_combine(int64_t n_coarse, const int32_t *child,
                       const uint8_t *ptype, const double *T, const int32_t *cls,
                       const double *scale, double *out, void *stream);
+int sktb_elem_combine_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
+                            const int32_t *child, const uint8_t *ptype,
+                            const double *T, const int32_t *cls, const double *scale,
+                            double *out, void *stream);
 /* PCG preconditioned by the V-cycle (level 0 may be row-sharded)               */
 int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg, const int32_t *node_ptr,
                            const int32_t *node_col, int64_t n_blocks,
@@ -295,6 +321,11 @@ int sktb_comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts_h,
  * indices received from it (ghost slots of the full-length direction vector).
  * sktb_pcg_solve then takes local row_ptr/vals/inv_diag/b/x and global col_idx;
  * dot products are all-reduced in the stream (2 all-reduces per iteration).    */
+/* z-slab halo of a row-sharded PCG on a tensor grid: whole planes of plane_dofs
+ * entries exchanged with prev_rank / next_rank (-1: none) straight from / into
+ * the full-length vectors, instead of the packed index lists                   */
+int sktb_pcg_set_slab_halo(sktb_pcg *s, int64_t plane_dofs, int prev_rank,
+                           int next_rank);
 int sktb_pcg_create_dist(sktb_pcg **out, sktb_comm *comm, int64_t n_global,
                          int64_t row0, int64_t n_local, int n_peers,
                          const int32_t *peers_h, const int64_t *send_off_h,

@@ -37,7 +37,11 @@ class HelmholtzOracle:
     The reference re-assembles and calls spsolve per application; the oracle
     factorises once per radius (same linear systems)."""
 
-    def __init__(self, p, t, volumes, design_mask=None):
+    def __init__(self, p, t, volumes, design_mask=None, solver="splu", cg_rtol=1e-12):
+        """``solver='cg'``: the same linear systems solved by scipy cg + Jacobi at
+        ``cg_rtol`` instead of a sparse LU (for meshes where the 3-D factorisation
+        does not fit: the CPU baseline at BASELINE's full sizes)."""
+        self.solver, self.cg_rtol = solver, cg_rtol
         self.p, self.t, self.vol = p, t, volumes
         self.mask = None if design_mask is None else np.asarray(design_mask, bool)
         io = fem.default_intorder(t.shape[0])
@@ -54,6 +58,16 @@ class HelmholtzOracle:
     def set_radius(self, r):
         if r == self.radius:
             return
+        if self.solver == "cg":
+            A = (self.M + (r ** 2) * self.K).tocsr()
+            self.A = A
+            self.lu_full = _CgSolve(A, self.cg_rtol)
+            if self.fixed.size:
+                Af = A[self.free]
+                self.A_free_fixed = Af[:, self.fixed].tocsr()
+                self.lu_free = _CgSolve(Af[:, self.free].tocsr(), self.cg_rtol)
+            self.radius = r
+            return
         self.A = (self.M + (r ** 2) * self.K).tocsc()
         self.lu_full = spla.splu(self.A)
         if self.fixed.size:
@@ -66,7 +80,9 @@ class HelmholtzOracle:
         if self.fixed.size:
             x = np.zeros(self.p.shape[1])
             x[self.fixed] = 1.0
-            rhs = b[self.free] - (self.A[self.free][:, self.fixed] @ x[self.fixed])
+            Aff = (self.A_free_fixed if self.solver == "cg"
+                   else self.A[self.free][:, self.fixed])
+            rhs = b[self.free] - (Aff @ x[self.fixed])
             x[self.free] = self.lu_free.solve(rhs)
         else:
             x = self.lu_full.solve(b)
@@ -76,6 +92,28 @@ class HelmholtzOracle:
         v_n = element_to_node(self.t, self.vol, v_elem, self.mask, 0.0)
         x = self.lu_full.solve(self.M @ v_n)
         return np.minimum(node_to_element(self.t, x), 0.0)
+
+
+class _CgSolve:
+    """``.solve(b)`` by scipy cg + Jacobi (stands in for ``splu(A).solve``)."""
+
+    def __init__(self, A, rtol):
+        self.A, self.rtol = A, rtol
+        d = 1.0 / A.diagonal()
+        self.M = spla.LinearOperator(A.shape, matvec=lambda x: d * x)
+        self.iters = []
+
+    def solve(self, b):
+        n = [0]
+
+        def cb(_):
+            n[0] += 1
+        x, info = spla.cg(self.A, b, M=self.M, rtol=self.rtol, atol=0.0, maxiter=5000,
+                          callback=cb)
+        if info != 0:
+            raise RuntimeError("Helmholtz cg did not converge")
+        self.iters.append(n[0])
+        return x
 
 
 class SpatialOracle:

@@ -133,10 +133,18 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         rho_min=1e-2, rho_max=1.0, E_min_coeff=1e-3, beta_eta=0.5,
         solver="spsolve", rtol=1e-8, cg_maxiter=None, lambda_lower=1e-7,
         lambda_upper=1e7, logmoc=None, iters=None, timings=None, step_times=None,
-        interpolation="SIMP", sensitivity_filter=False):
+        interpolation="SIMP", sensitivity_filter=False, backend=None,
+        filter_solver="splu", time_budget=None):
     """DensityMethod._optimize_impl (common_density.py:1014-1134) with the
     default schedules of DensityMethodConfig / OC_Config / LogMOC_Config.
-    Returns dict(rho, compliance[], vol_error[], rho_hist[])."""
+    Returns dict(rho, compliance[], vol_error[], rho_hist[]).
+
+    ``backend`` (``oracle.cport.CBackend``): assembly + enforce, the Jacobi-PCG
+    and the element energies run through the C / OpenMP port (same algorithms on
+    all host cores: the CPU baseline at BASELINE's full sizes); ``filter_solver=
+    'cg'`` solves the Helmholtz systems by cg instead of a sparse LU.
+    ``time_budget`` (seconds): stop after the first iteration that ends later
+    than this (timed runs on hosts of unknown speed; at least one iteration)."""
     pr = problem
     ne = pr.t.shape[1]
     E0, Emin = pr.E, pr.E * E_min_coeff
@@ -144,7 +152,7 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
     interp, dC_drho = {"SIMP": (fem.simp, dC_drho_simp),
                        "RAMP": (fem.ramp, dC_drho_ramp)}[interpolation]
     if filter_type == "helmholtz":
-        filt = HelmholtzOracle(pr.p, pr.t, pr.vol, pr.design_mask)
+        filt = HelmholtzOracle(pr.p, pr.t, pr.vol, pr.design_mask, solver=filter_solver)
     else:
         filt = SpatialOracle(pr.p, pr.t, pr.design_mask)
     filt.set_radius(filter_radius)
@@ -171,6 +179,7 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         tm[name] = tm.get(name, 0.0) + time.perf_counter() - t0
 
     n_it = max_iters if iters is None else iters
+    t_start = time.perf_counter()
     for it in range(1, n_it + 1):
         if step_times is not None:
             step_times.append(time.perf_counter())      # start of every iteration
@@ -183,18 +192,26 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         rho_p = heaviside(rho_f, beta, beta_eta)
         tick("filter_and_project", t0)
         t0 = time.perf_counter()
-        K = fem.assemble_stiffness(pr.p, pr.t, rho_p, E0, Emin, pw, pr.nu, pr.intorder,
-                                   interp=interp)
+        if backend is not None:
+            # homogeneous Dirichlet data: enforce is folded into the assembly
+            K_e = backend.assemble(interp(rho_p, E0, Emin, pw), enforce=True)
+        else:
+            K = fem.assemble_stiffness(pr.p, pr.t, rho_p, E0, Emin, pw, pr.nu, pr.intorder,
+                                       interp=interp)
         tick("assemble", t0)
         t0 = time.perf_counter()
-        K_e, _ = fem.enforce(K, pr.forces[0], pr.D)
+        if backend is None:
+            K_e, _ = fem.enforce(K, pr.forces[0], pr.D)
         tick("enforce_bc", t0)
         t0 = time.perf_counter()
         comps, U = [], []
         for f in pr.forces:
             F_e = np.array(f, dtype=float)
             F_e[pr.D] = 0.0
-            u, _, nit = fem.solve(K_e, F_e, solver, rtol, cg_maxiter)
+            if backend is not None:
+                u, nit, _ = backend.pcg(F_e, rtol, cg_maxiter)
+            else:
+                u, _, nit = fem.solve(K_e, F_e, solver, rtol, cg_maxiter)
             hist["cg_iters"].append(nit)
             comps.append(float(F_e @ u))
             U.append(u)
@@ -202,8 +219,12 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         tick("solve", t0)
         compliance = float(np.mean(comps))
         t0 = time.perf_counter()
-        energy = fem.strain_energy(pr.p, pr.t, rho_p, U, E0, Emin, pw, pr.nu, pr.intorder,
-                                   interp=interp)
+        if backend is not None:
+            sc = interp(rho_p, E0, Emin, pw)
+            energy = np.column_stack([backend.energy(sc, U[:, l]) for l in range(U.shape[1])])
+        else:
+            energy = fem.strain_energy(pr.p, pr.t, rho_p, U, E0, Emin, pw, pr.nu, pr.intorder,
+                                       interp=interp)
         tick("energy", t0)
         t0 = time.perf_counter()
         dC_full = np.zeros(ne)
@@ -251,6 +272,8 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         hist["compliance"].append(compliance)
         hist["vol_error"].append(float(vol_error))
         hist["rho"].append(rho[pr.design].copy())
+        if time_budget is not None and time.perf_counter() - t_start > time_budget:
+            break
     if step_times is not None:
         step_times.append(time.perf_counter())          # end of the last one
     hist["rho_final"] = rho

@@ -1,8 +1,16 @@
-// NCCL communicator wrapper (see comm.cuh).  Only the handful of NCCL entry
-// points the sharded PCG needs are bound; enum values are NCCL 2.x ABI.
+// Communicator: NCCL transport (product path) and a host shared-memory
+// transport for several ranks on one GPU (see comm.cuh).  Only the handful of
+// NCCL entry points the sharded solver needs are bound; enum values are the
+// NCCL 2.x ABI.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "comm.cuh"
 #include "common.cuh"
@@ -21,6 +29,7 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int);
   int (*CommDestroy)(NcclComm);
   int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t);
   int (*Broadcast)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
   int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t);
@@ -52,6 +61,7 @@ int load_api() {
   BIND(CommInitRank, "ncclCommInitRank");
   BIND(CommDestroy, "ncclCommDestroy");
   BIND(AllReduce, "ncclAllReduce");
+  BIND(AllGather, "ncclAllGather");
   BIND(Broadcast, "ncclBroadcast");
   BIND(Send, "ncclSend");
   BIND(Recv, "ncclRecv");
@@ -74,6 +84,164 @@ int load_api() {
 
 }  // namespace
 
+// ------------------------------------------------------- shared-memory path --
+// Segment: [header | slot 0 | slot 1 | ... ]; a slot is a rank's outbox: a
+// directory of (peer, offset, count) records followed by fp64 payload.
+struct ShmHeader {
+  std::atomic<uint32_t> count;
+  std::atomic<uint32_t> gen;
+  std::atomic<uint32_t> attached;
+};
+struct ShmDirEntry {
+  int64_t peer, off, cnt;
+};
+constexpr int kShmMaxDir = 64;
+struct ShmSlotHead {
+  int64_t n_dir;
+  ShmDirEntry dir[kShmMaxDir];
+};
+
+struct sktb_shm {
+  char name[64];
+  int fd = -1;
+  size_t bytes = 0, slot_bytes = 0;
+  char *base = nullptr;
+  int rank = 0, world = 1;
+  std::vector<double> host;
+  ShmHeader *head() const { return (ShmHeader *)base; }
+  ShmSlotHead *slot(int r) const { return (ShmSlotHead *)(base + 4096 + (size_t)r * slot_bytes); }
+  double *payload(int r) const { return (double *)((char *)slot(r) + sizeof(ShmSlotHead)); }
+  int64_t capacity() const { return (int64_t)((slot_bytes - sizeof(ShmSlotHead)) / sizeof(double)); }
+  void barrier() {
+    ShmHeader *h = head();
+    const uint32_t g = h->gen.load(std::memory_order_acquire);
+    if (h->count.fetch_add(1, std::memory_order_acq_rel) + 1 == (uint32_t)world) {
+      h->count.store(0, std::memory_order_relaxed);
+      h->gen.fetch_add(1, std::memory_order_release);
+    } else {
+      while (h->gen.load(std::memory_order_acquire) == g) sched_yield();
+    }
+  }
+};
+
+static int shm_open_segment(sktb_comm *c, const char *id128) {
+  sktb_shm *s = new sktb_shm();
+  s->rank = c->rank;
+  s->world = c->world;
+  snprintf(s->name, sizeof(s->name), "/sktb_%.40s", id128 + 4);
+  const char *mb = getenv("SKTB_SHM_SLOT_MB");
+  s->slot_bytes = (size_t)(mb ? atoi(mb) : 64) << 20;
+  s->bytes = 4096 + s->slot_bytes * (size_t)c->world;
+  s->fd = shm_open(s->name, O_CREAT | O_RDWR, 0600);
+  if (s->fd < 0) {
+    sktb::set_error("shm_open failed");
+    return 1;
+  }
+  if (ftruncate(s->fd, (off_t)s->bytes) != 0) {
+    sktb::set_error("ftruncate of the shared segment failed");
+    return 1;
+  }
+  s->base = (char *)mmap(nullptr, s->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, s->fd, 0);
+  if (s->base == MAP_FAILED) {
+    sktb::set_error("mmap of the shared segment failed");
+    return 1;
+  }
+  // a fresh segment is zero-filled: count = gen = attached = 0
+  ShmHeader *h = s->head();
+  h->attached.fetch_add(1);
+  while (h->attached.load() < (uint32_t)c->world) sched_yield();
+  c->shm = s;
+  s->barrier();
+  if (c->rank == 0) shm_unlink(s->name);  // everyone is mapped: drop the name
+  return 0;
+}
+
+static int shm_allreduce(sktb_shm *s, const double *src, double *dst, int64_t count,
+                         cudaStream_t st) {
+  SKTB_CUDA_OK(cudaStreamSynchronize(st));
+  const int64_t cap = s->capacity();
+  for (int64_t c0 = 0; c0 < count; c0 += cap) {
+    const int64_t n = count - c0 < cap ? count - c0 : cap;
+    SKTB_CUDA_OK(cudaMemcpy(s->payload(s->rank), src + c0, sizeof(double) * n,
+                            cudaMemcpyDeviceToHost));
+    s->barrier();
+    s->host.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      double a = 0.0;
+      for (int r = 0; r < s->world; ++r) a += s->payload(r)[i];  // rank order: deterministic
+      s->host[(size_t)i] = a;
+    }
+    s->barrier();
+    SKTB_CUDA_OK(cudaMemcpy(dst + c0, s->host.data(), sizeof(double) * n,
+                            cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+static int shm_p2p(sktb_shm *s, int n_ops, const sktb::P2POp *ops, cudaStream_t st) {
+  SKTB_CUDA_OK(cudaStreamSynchronize(st));
+  SKTB_REQUIRE(n_ops <= kShmMaxDir, "too many peers for the shm transport");
+  ShmSlotHead *mine = s->slot(s->rank);
+  int64_t off = 0;
+  mine->n_dir = n_ops;
+  for (int i = 0; i < n_ops; ++i) {
+    SKTB_REQUIRE(off + ops[i].n_send <= s->capacity(),
+                 "halo larger than the shm slot (raise SKTB_SHM_SLOT_MB)");
+    mine->dir[i] = {ops[i].peer, off, ops[i].n_send};
+    if (ops[i].n_send > 0)
+      SKTB_CUDA_OK(cudaMemcpy(s->payload(s->rank) + off, ops[i].send,
+                              sizeof(double) * ops[i].n_send, cudaMemcpyDeviceToHost));
+    off += ops[i].n_send;
+  }
+  s->barrier();
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].n_recv <= 0) continue;
+    const ShmSlotHead *theirs = s->slot(ops[i].peer);
+    bool found = false;
+    int seen = 0;  // the k-th op towards a peer pairs with the peer's k-th op towards us
+    int want = 0;
+    for (int j = 0; j < i; ++j)
+      if (ops[j].peer == ops[i].peer) ++want;
+    for (int64_t k = 0; k < theirs->n_dir; ++k) {
+      if (theirs->dir[k].peer != s->rank) continue;
+      if (seen++ != want) continue;
+      SKTB_REQUIRE(theirs->dir[k].cnt == ops[i].n_recv, "shm exchange: size mismatch");
+      SKTB_CUDA_OK(cudaMemcpy(ops[i].recv, s->payload(ops[i].peer) + theirs->dir[k].off,
+                              sizeof(double) * ops[i].n_recv, cudaMemcpyHostToDevice));
+      found = true;
+      break;
+    }
+    SKTB_REQUIRE(found, "shm exchange: peer did not post a matching send");
+  }
+  s->barrier();
+  return 0;
+}
+
+static int shm_allgatherv(sktb_shm *s, double *buf, const int64_t *counts,
+                          const int64_t *displs, cudaStream_t st) {
+  SKTB_CUDA_OK(cudaStreamSynchronize(st));
+  const int64_t cap = s->capacity();
+  int64_t maxc = 0;
+  for (int r = 0; r < s->world; ++r) maxc = counts[r] > maxc ? counts[r] : maxc;
+  for (int64_t c0 = 0; c0 < maxc; c0 += cap) {
+    const int64_t mine = counts[s->rank] - c0;
+    if (mine > 0)
+      SKTB_CUDA_OK(cudaMemcpy(s->payload(s->rank), buf + displs[s->rank] + c0,
+                              sizeof(double) * (mine < cap ? mine : cap),
+                              cudaMemcpyDeviceToHost));
+    s->barrier();
+    for (int r = 0; r < s->world; ++r) {
+      const int64_t n = counts[r] - c0;
+      if (r == s->rank || n <= 0) continue;
+      SKTB_CUDA_OK(cudaMemcpy(buf + displs[r] + c0, s->payload(r),
+                              sizeof(double) * (n < cap ? n : cap), cudaMemcpyHostToDevice));
+    }
+    s->barrier();
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------- C ABI --
 extern "C" int sktb_comm_unique_id(void *id128_h) {
   SKTB_REQUIRE(id128_h, "null argument");
   if (load_api()) return 1;
@@ -85,12 +253,17 @@ extern "C" int sktb_comm_create(sktb_comm **out, const void *id128_h, int rank,
                                 int world, int device) {
   SKTB_REQUIRE(out && id128_h && world >= 1 && rank >= 0 && rank < world,
                "bad argument");
-  if (load_api()) return 1;
   SKTB_CUDA_OK(cudaSetDevice(device));
   sktb_comm *c = new sktb_comm();
   c->rank = rank;
   c->world = world;
   c->device = device;
+  if (memcmp(id128_h, "SHM:", 4) == 0) {
+    if (shm_open_segment(c, (const char *)id128_h)) return 1;
+    *out = c;
+    return 0;
+  }
+  if (load_api()) return 1;
   NcclUniqueId id;
   memcpy(&id, id128_h, sizeof(id));
   NcclComm comm = nullptr;
@@ -103,6 +276,11 @@ extern "C" int sktb_comm_create(sktb_comm **out, const void *id128_h, int rank,
 extern "C" void sktb_comm_destroy(sktb_comm *c) {
   if (!c) return;
   if (c->nccl && g_api.ok) g_api.CommDestroy((NcclComm)c->nccl);
+  if (c->shm) {
+    munmap(c->shm->base, c->shm->bytes);
+    close(c->shm->fd);
+    delete c->shm;
+  }
   delete c;
 }
 
@@ -127,31 +305,50 @@ namespace sktb {
 
 int comm_allreduce_sum(sktb_comm *c, const double *src, double *dst,
                        int64_t count, cudaStream_t st) {
+  if (c->shm) return shm_allreduce(c->shm, src, dst, count, st);
   NCCL_OK(g_api.AllReduce(src, dst, (size_t)count, kNcclFloat64, kNcclSum,
                           (NcclComm)c->nccl, st));
+  return 0;
+}
+
+int comm_p2p(sktb_comm *c, int n_ops, const P2POp *ops, cudaStream_t st) {
+  if (n_ops <= 0) return 0;
+  if (c->shm) return shm_p2p(c->shm, n_ops, ops, st);
+  NCCL_OK(g_api.GroupStart());
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].n_send > 0)
+      NCCL_OK(g_api.Send(ops[i].send, (size_t)ops[i].n_send, kNcclFloat64,
+                         ops[i].peer, (NcclComm)c->nccl, st));
+    if (ops[i].n_recv > 0)
+      NCCL_OK(g_api.Recv(ops[i].recv, (size_t)ops[i].n_recv, kNcclFloat64,
+                         ops[i].peer, (NcclComm)c->nccl, st));
+  }
+  NCCL_OK(g_api.GroupEnd());
   return 0;
 }
 
 int comm_exchange(sktb_comm *c, int n_peers, const int *peers,
                   const double *sendbuf, const int64_t *send_off,
                   double *recvbuf, const int64_t *recv_off, cudaStream_t st) {
-  NCCL_OK(g_api.GroupStart());
-  for (int i = 0; i < n_peers; ++i) {
-    const int64_t ns = send_off[i + 1] - send_off[i];
-    const int64_t nr = recv_off[i + 1] - recv_off[i];
-    if (ns > 0)
-      NCCL_OK(g_api.Send(sendbuf + send_off[i], (size_t)ns, kNcclFloat64,
-                         peers[i], (NcclComm)c->nccl, st));
-    if (nr > 0)
-      NCCL_OK(g_api.Recv(recvbuf + recv_off[i], (size_t)nr, kNcclFloat64,
-                         peers[i], (NcclComm)c->nccl, st));
-  }
-  NCCL_OK(g_api.GroupEnd());
-  return 0;
+  std::vector<P2POp> ops((size_t)n_peers);
+  for (int i = 0; i < n_peers; ++i)
+    ops[(size_t)i] = {peers[i], sendbuf + send_off[i], send_off[i + 1] - send_off[i],
+                      recvbuf + recv_off[i], recv_off[i + 1] - recv_off[i]};
+  return comm_p2p(c, n_peers, ops.data(), st);
 }
 
 int comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts,
                     const int64_t *displs, cudaStream_t st) {
+  if (c->shm) return shm_allgatherv(c->shm, buf, counts, displs, st);
+  // equal slices at their natural displacements: one ncclAllGather in place
+  bool uniform = true;
+  for (int r = 0; r < c->world; ++r)
+    if (counts[r] != counts[0] || displs[r] != (int64_t)r * counts[0]) uniform = false;
+  if (uniform && counts[0] > 0) {
+    NCCL_OK(g_api.AllGather(buf + displs[c->rank], buf, (size_t)counts[0], kNcclFloat64,
+                            (NcclComm)c->nccl, st));
+    return 0;
+  }
   NCCL_OK(g_api.GroupStart());
   for (int r = 0; r < c->world; ++r)
     if (counts[r] > 0)

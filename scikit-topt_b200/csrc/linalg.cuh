@@ -47,6 +47,9 @@ struct JacobiEpi {
   const double *b = nullptr;  // null: plain product
   const double *dinv = nullptr;
   double omega = 0.0;
+  // rows of x that correspond to the local rows (row-sharded level: x is the
+  // full-length vector, xo = x + first owned row); null: xo = x
+  const double *xo = nullptr;
 };
 int launch_spmv_bsr3_jacobi(int64_t n_nodes, const int32_t *node_ptr,
                             const int32_t *node_col, const double *vals,
@@ -84,6 +87,13 @@ struct sktb_pcg;
 int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
               sktb_pcg *dist = nullptr);
 // row-sharded helpers implemented by the PCG workspace (pcg.cu)
+struct sktb_comm;
 bool pcg_is_dist(const sktb_pcg *s);
+sktb_comm *pcg_comm(const sktb_pcg *s);
 int pcg_halo_exchange(sktb_pcg *s, double *full_vec, cudaStream_t st);
 int pcg_allreduce_vec(sktb_pcg *s, double *buf, int64_t n, cudaStream_t st);
+// Ghost planes of a z-slab-sharded full-length vector: this rank owns the
+// entries [own0, own0 + n_own); `plane` entries are sent to / received from the
+// previous and the next rank (-1: none), straight from / into the vector.
+int slab_halo_exchange(sktb_comm *c, double *v, int64_t own0, int64_t n_own,
+                       int64_t plane, int prev, int next, cudaStream_t st);

@@ -41,6 +41,12 @@ struct MgLevel {
   // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
   // the operator is not sharded); x is always full length (n_global nodes)
   int64_t node0 = 0, n_global = 0;
+  // z-slab sharding of this level (level 0 and the large assembled levels):
+  // whole node planes per rank, ghost planes exchanged with prev / next
+  bool sharded = false;
+  int64_t plane = 0;         // nodes per z-plane
+  int prev = -1, next = -1;  // neighbour ranks (-1: none)
+  double *res = nullptr;     // full-length residual for a sharded -> sharded restriction (owned)
   double omega = 0.0;  // damping of this level's Jacobi smoother (0: use the global one)
   int nu = 1;          // pre- and post-smoothing sweeps on this level
   bool cheb = false;   // Chebyshev polynomial smoother of degree nu instead of nu Jacobi sweeps
@@ -86,6 +92,7 @@ extern "C" void sktb_mg_destroy(sktb_mg *m) {
     cudaFree(l.dense_inv);
     cudaFree(l.d);
     cudaFree(l.x2);
+    cudaFree(l.res);
   }
   delete m;
 }
@@ -153,6 +160,7 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   SKTB_CUDA_OK(cudaSetDevice(m->device));
   MgLevel &l = m->lv[level];
   if (l.n_global < n_nodes) l.n_global = n_nodes;
+  if (!l.sharded && level > 0) l.node0 = 0;
   if (l.n_nodes != n_nodes || !l.x) {
     cudaFree(l.x);
     cudaFree(l.b);
@@ -163,8 +171,13 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
     cudaFree(l.x2);
     l.x2 = nullptr;
-    if (level > 0 && n_nodes <= kTailMaxNodes)
+    if (level > 0 && l.sharded) {
+      // second full-length iterate of the fused Jacobi sweeps
+      SKTB_CUDA_OK(cudaMalloc(&l.x2, sizeof(double) * 3 * l.n_global));
+      SKTB_CUDA_OK(cudaMemset(l.x2, 0, sizeof(double) * 3 * l.n_global));
+    } else if (level > 0 && n_nodes <= kTailMaxNodes) {
       SKTB_CUDA_OK(cudaMalloc(&l.x2, sizeof(double) * 3 * n_nodes));
+    }
   }
   l.n_nodes = n_nodes;
   l.gop = nullptr;
@@ -220,6 +233,33 @@ extern "C" int sktb_mg_set_level0_range(sktb_mg *m, int64_t node0,
   return 0;
 }
 
+// z-slab sharding of one level: this rank owns the nodes [node0, node0 +
+// n_owned) (whole planes of `plane_nodes` nodes) of n_global; prev / next are
+// the ranks owning the adjacent planes (-1: none).  Call before
+// sktb_mg_set_level / sktb_mg_set_level0_grid of that level.  plane_nodes = 0
+// marks the level as replicated again.
+extern "C" int sktb_mg_set_level_slab(sktb_mg *m, int level, int64_t node0,
+                                      int64_t n_global, int64_t plane_nodes,
+                                      int prev_rank, int next_rank) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size() && node0 >= 0 && n_global > 0 &&
+                   plane_nodes >= 0,
+               "bad argument");
+  MgLevel &l = m->lv[level];
+  if (l.n_global != n_global || l.sharded != (plane_nodes > 0)) {
+    cudaFree(l.x);
+    l.x = nullptr;
+    cudaFree(l.res);
+    l.res = nullptr;
+  }
+  l.node0 = node0;
+  l.n_global = n_global;
+  l.sharded = plane_nodes > 0;
+  l.plane = plane_nodes;
+  l.prev = prev_rank;
+  l.next = next_rank;
+  return 0;
+}
+
 extern "C" int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_np_h,
                                     const int32_t *coarse_np_h,
                                     const int32_t *ax_c0, const int32_t *ax_c1,
@@ -263,8 +303,10 @@ __global__ void __launch_bounds__(192)
                          const double *__restrict__ unit,
                          const int32_t *__restrict__ cls,
                          const double *__restrict__ scale,
-                         double *__restrict__ out) {
-  const int64_t E = blockIdx.x;
+                         double *__restrict__ out, int64_t e_lo, int64_t fine_base) {
+  // coarse elements [e_lo, e_lo + gridDim.x); out holds them from e_lo on,
+  // fine_ke holds the fine elements from fine_base on (slab-sharded set-up)
+  const int64_t E = e_lo + blockIdx.x;
   const int type = ptype[E];
   __shared__ int32_t ch[8];
   __shared__ double Q[8][64];     // Q[c][a * 8 + A]: weight of parent vertex A in child vertex a
@@ -281,7 +323,7 @@ __global__ void __launch_bounds__(192)
     const double *src;
     double sc = 1.0;
     if (fine_ke) {
-      src = fine_ke + (int64_t)ce * 576;
+      src = fine_ke + ((int64_t)ce - fine_base) * 576;
     } else {
       src = unit + (int64_t)(cls ? cls[ce] : 0) * 576;
       sc = scale[ce];
@@ -318,7 +360,7 @@ __global__ void __launch_bounds__(192)
     __syncthreads();
   }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) out[E * 576 + threadIdx.x + 192 * k] = acc[k];
+  for (int k = 0; k < 3; ++k) out[(E - e_lo) * 576 + threadIdx.x + 192 * k] = acc[k];
 }
 
 // Level 0 -> 1 fast path: children are scale[e] * Ke0[class], so the Galerkin
@@ -330,7 +372,7 @@ __global__ void __launch_bounds__(192)
                         const double *__restrict__ T,
                         const int32_t *__restrict__ cls,
                         const double *__restrict__ scale,
-                        double *__restrict__ out) {
+                        double *__restrict__ out, int64_t e_lo, int64_t e_hi) {
   // persistent CTAs, one coarse element per trip, three entries per thread; the
   // tables of the common case (class 0, full 2x2x2 parent) live in registers
   double t0[8][3];
@@ -341,7 +383,7 @@ __global__ void __launch_bounds__(192)
   __shared__ double s_sc[2][8];
   __shared__ int s_tab[2][8];  // table index (cls * 8 + type) * 8 + c, -1 = no child
   int buf = 0;
-  for (int64_t E = blockIdx.x; E < n_coarse; E += gridDim.x, buf ^= 1) {
+  for (int64_t E = e_lo + blockIdx.x; E < e_hi; E += gridDim.x, buf ^= 1) {
     if (threadIdx.x < 8) {
       const int c = threadIdx.x;
       const int32_t ce = child[(int64_t)c * n_coarse + E];
@@ -365,19 +407,42 @@ __global__ void __launch_bounds__(192)
       }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[E * 576 + threadIdx.x + 192 * k] = acc[k];
+    for (int k = 0; k < 3; ++k) out[(E - e_lo) * 576 + threadIdx.x + 192 * k] = acc[k];
   }
+}
+
+extern "C" int sktb_elem_combine_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
+                                       const int32_t *child, const uint8_t *ptype,
+                                       const double *T, const int32_t *cls,
+                                       const double *scale, double *out, void *stream) {
+  SKTB_REQUIRE(child && ptype && T && scale && out && n_coarse > 0, "null argument");
+  SKTB_REQUIRE(0 <= e_lo && e_lo < e_hi && e_hi <= n_coarse, "bad element range");
+  const int64_t cap = (int64_t)kNumSM * 10, ne = e_hi - e_lo;
+  elem_combine_kernel<<<(unsigned)(ne < cap ? ne : cap), 192, 0, (cudaStream_t)stream>>>(
+      n_coarse, child, ptype, T, cls, scale, out, e_lo, e_hi);
+  SKTB_KERNEL_OK();
+  return 0;
 }
 
 extern "C" int sktb_elem_combine(int64_t n_coarse, const int32_t *child,
                                  const uint8_t *ptype, const double *T,
                                  const int32_t *cls, const double *scale,
                                  double *out, void *stream) {
-  SKTB_REQUIRE(child && ptype && T && scale && out && n_coarse > 0, "null argument");
-  const int64_t cap = (int64_t)kNumSM * 10;
-  elem_combine_kernel<<<(unsigned)(n_coarse < cap ? n_coarse : cap), 192, 0,
-                        (cudaStream_t)stream>>>(n_coarse, child, ptype, T, cls,
-                                                scale, out);
+  return sktb_elem_combine_range(n_coarse, 0, n_coarse, child, ptype, T, cls, scale, out,
+                                 stream);
+}
+
+extern "C" int sktb_elem_restrict_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
+                                        int64_t fine_base, const int32_t *child,
+                                        const uint8_t *ptype, const double *Qtab,
+                                        const double *fine_ke, const double *unit,
+                                        const int32_t *cls, const double *scale,
+                                        double *out, void *stream) {
+  SKTB_REQUIRE(child && ptype && Qtab && out && n_coarse > 0, "null argument");
+  SKTB_REQUIRE(fine_ke || (unit && scale), "need fine element matrices or (unit, scale)");
+  SKTB_REQUIRE(0 <= e_lo && e_lo < e_hi && e_hi <= n_coarse, "bad element range");
+  elem_restrict_kernel<<<(unsigned)(e_hi - e_lo), 192, 0, (cudaStream_t)stream>>>(
+      n_coarse, child, ptype, Qtab, fine_ke, unit, cls, scale, out, e_lo, fine_base);
   SKTB_KERNEL_OK();
   return 0;
 }
@@ -387,12 +452,8 @@ extern "C" int sktb_elem_restrict(int64_t n_coarse, const int32_t *child,
                                   const double *fine_ke, const double *unit,
                                   const int32_t *cls, const double *scale,
                                   double *out, void *stream) {
-  SKTB_REQUIRE(child && ptype && Qtab && out && n_coarse > 0, "null argument");
-  SKTB_REQUIRE(fine_ke || (unit && scale), "need fine element matrices or (unit, scale)");
-  elem_restrict_kernel<<<(unsigned)n_coarse, 192, 0, (cudaStream_t)stream>>>(
-      n_coarse, child, ptype, Qtab, fine_ke, unit, cls, scale, out);
-  SKTB_KERNEL_OK();
-  return 0;
+  return sktb_elem_restrict_range(n_coarse, 0, n_coarse, 0, child, ptype, Qtab, fine_ke, unit,
+                                  cls, scale, out, stream);
 }
 
 // ------------------------------------------------------------ level kernels --
@@ -431,10 +492,13 @@ __global__ void __launch_bounds__(kBlock)
                               const double *__restrict__ bf,
                               const double *__restrict__ Axf,
                               const uint8_t *__restrict__ mask_c,
-                              double *__restrict__ bc, int64_t f_lo, int64_t f_hi) {
-  const int64_t nc = (int64_t)cnx * cny * cnz;
+                              double *__restrict__ bc, int64_t f_lo, int64_t f_hi,
+                              int64_t c_lo, int64_t c_hi, int64_t c_base) {
+  // coarse nodes [c_lo, c_hi) are produced, written at bc[3 (I - c_base)];
+  // bf / Axf hold the fine rows [f_lo, f_hi) (Axf may be null: bf is a residual)
   const int tot = cnx + cny + cnz;
-  GS(I, nc) {
+  GS(Ii, c_hi - c_lo) {
+    const int64_t I = c_lo + Ii;
     const int iy = (int)(I % cny);
     const int ix = (int)((I / cny) % cnx);
     const int iz = (int)(I / ((int64_t)cny * cnx));
@@ -454,17 +518,30 @@ __global__ void __launch_bounds__(kBlock)
           const int64_t fn = (int64_t)fy + (int64_t)fny * fx + (int64_t)fny * fnx * fz;
           if (fn < f_lo || fn >= f_hi) continue;  // another rank's fine node
           const int64_t f = 3 * (fn - f_lo);      // bf / Axf hold the owned rows
-          a0 += w * (bf[f] - Axf[f]);
-          a1 += w * (bf[f + 1] - Axf[f + 1]);
-          a2 += w * (bf[f + 2] - Axf[f + 2]);
+          if (Axf) {
+            a0 += w * (bf[f] - Axf[f]);
+            a1 += w * (bf[f + 1] - Axf[f + 1]);
+            a2 += w * (bf[f + 2] - Axf[f + 2]);
+          } else {
+            a0 += w * bf[f];
+            a1 += w * bf[f + 1];
+            a2 += w * bf[f + 2];
+          }
         }
       }
     }
-    const int64_t o = 3 * I;
-    bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
-    bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
-    bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+    const int64_t o = 3 * I, q = 3 * (I - c_base);
+    bc[q] = (mask_c && mask_c[o]) ? 0.0 : a0;
+    bc[q + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+    bc[q + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
   }
+}
+
+// r[own rows of the full-length vector] = b - Ax (b, Ax: owned rows)
+__global__ void __launch_bounds__(kBlock)
+    mg_residual_kernel(int64_t n, const double *__restrict__ b,
+                       const double *__restrict__ Ax, double *__restrict__ r) {
+  GS(i, n) r[i] = b[i] - Ax[i];
 }
 
 // b_c = mask_c * P^T (b_f - Ax_f) ; one WARP per coarse node, one lane per
@@ -476,13 +553,13 @@ __global__ void __launch_bounds__(kBlock)
                        const double *__restrict__ bf,
                        const double *__restrict__ Axf,
                        const uint8_t *__restrict__ mask_c,
-                       double *__restrict__ bc, int64_t f_lo, int64_t f_hi) {
-  const int64_t nc = (int64_t)cnx * cny * cnz;
+                       double *__restrict__ bc, int64_t f_lo, int64_t f_hi,
+                       int64_t c_lo, int64_t c_hi, int64_t c_base) {
   const int tot = cnx + cny + cnz;
   const int lane = threadIdx.x & 31;
   const int sy = lane % 3, sx = (lane / 3) % 3, sz = lane / 9;  // lanes >= 27 idle
   const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
-  for (int64_t I = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); I < nc;
+  for (int64_t I = c_lo + (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); I < c_hi;
        I += wstride) {
     const int iy = (int)(I % cny);
     const int ix = (int)((I / cny) % cnx);
@@ -498,9 +575,9 @@ __global__ void __launch_bounds__(kBlock)
           const double w = axT_w[sz * tot + cnx + cny + iz] * axT_w[sx * tot + ix] *
                            axT_w[sy * tot + cnx + iy];
           const int64_t f = 3 * (fn - f_lo);    // bf / Axf hold the owned rows
-          a0 = w * (bf[f] - Axf[f]);
-          a1 = w * (bf[f + 1] - Axf[f + 1]);
-          a2 = w * (bf[f + 2] - Axf[f + 2]);
+          a0 = w * (Axf ? bf[f] - Axf[f] : bf[f]);
+          a1 = w * (Axf ? bf[f + 1] - Axf[f + 1] : bf[f + 1]);
+          a2 = w * (Axf ? bf[f + 2] - Axf[f + 2] : bf[f + 2]);
         }
       }
     }
@@ -508,10 +585,10 @@ __global__ void __launch_bounds__(kBlock)
     a1 = warp_sum(a1);
     a2 = warp_sum(a2);
     if (lane == 0) {
-      const int64_t o = 3 * I;
-      bc[o] = (mask_c && mask_c[o]) ? 0.0 : a0;
-      bc[o + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
-      bc[o + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+      const int64_t o = 3 * I, q = 3 * (I - c_base);
+      bc[q] = (mask_c && mask_c[o]) ? 0.0 : a0;
+      bc[q + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+      bc[q + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
     }
   }
 }
@@ -906,31 +983,39 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
                           nullptr, nullptr, nullptr, nullptr, st);
 }
 
-// One damped-Jacobi sweep x <- x + omega D^-1 (b - A x) of an assembled,
-// replicated level (k >= 1) as ONE kernel: the product writes the new iterate
-// into l.tmp through the fused epilogue, then the two buffers swap roles.
+// One damped-Jacobi sweep x <- x + omega D^-1 (b - A x) of an assembled level
+// (k >= 1) as ONE kernel: the product writes the new iterate into the level's
+// second buffer through the fused epilogue, then the two buffers swap roles
+// (replicated level: x <-> tmp; z-slab-sharded level: the two full-length
+// iterates x <-> x2, ghost planes refreshed by the caller before the sweep).
 // Returns -1 when the level has no such kernel (caller: product + update).
 static int level_sweep(MgLevel &l, const double *b, double omega, cudaStream_t st) {
-  if (l.gop || !l.vals || l.node0 != 0 || l.n_global != l.n_nodes) return -1;
+  if (l.gop || !l.vals) return -1;
+  if (!l.sharded && (l.node0 != 0 || l.n_global != l.n_nodes)) return -1;
+  if (l.sharded && !l.x2) return -1;
   JacobiEpi epi;
   epi.b = b;
   epi.dinv = l.inv_diag;
   epi.omega = omega;
+  double *y = l.tmp;
+  if (l.sharded) {
+    epi.xo = l.x + 3 * l.node0;
+    y = l.x2 + 3 * l.node0;
+  }
   int rc = l.n_nodes < kTmaMinNodes
                ? -1
                : launch_spmv_bsr3_tma_jacobi(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
-                                             l.node_col, l.vals, l.x, l.tmp, epi, st);
+                                             l.node_col, l.vals, l.x, y, epi, st);
   if (rc == -1)
-    rc = launch_spmv_bsr3_jacobi(l.n_nodes, l.node_ptr, l.node_col, l.vals, l.x, l.tmp, epi,
-                                 st);
+    rc = launch_spmv_bsr3_jacobi(l.n_nodes, l.node_ptr, l.node_col, l.vals, l.x, y, epi, st);
   if (rc) return rc;
-  std::swap(l.x, l.tmp);
+  if (l.sharded)
+    std::swap(l.x, l.x2);
+  else
+    std::swap(l.x, l.tmp);
   return 0;
 }
 
-// z = M^-1 r : V(1,1) cycle.  Level 0 may be row-sharded (its x is a
-// full-length vector whose ghost slots are refreshed before every SpMV, the
-// restricted residual is all-reduced); levels >= 1 are replicated.
 // first level of the fused tail (L: none)
 static int tail_start(const sktb_mg *m) {
   const int L = (int)m->lv.size();
@@ -938,7 +1023,9 @@ static int tail_start(const sktb_mg *m) {
   int k0 = L;
   for (int k = L - 1; k >= 1; --k) {
     const MgLevel &l = m->lv[k];
-    if (l.n_nodes > kTailMaxNodes || !l.x2 || !l.vals || l.cheb || L - k > kTailMaxLevels) break;
+    if (l.n_nodes > kTailMaxNodes || !l.x2 || !l.vals || l.cheb || l.sharded ||
+        L - k > kTailMaxLevels)
+      break;
     k0 = k;
   }
   return k0;
@@ -983,13 +1070,67 @@ static int launch_tail(sktb_mg *m, int k0, cudaStream_t st) {
   return 0;
 }
 
+// ghost planes of a sharded level's full-length vector (no-op when replicated)
+static int level_halo(const MgLevel &l, double *vfull, sktb_pcg *dist, cudaStream_t st) {
+  if (!dist || !pcg_is_dist(dist)) return 0;
+  if (l.sharded && l.plane > 0)
+    return slab_halo_exchange(pcg_comm(dist), vfull, 3 * l.node0, 3 * l.n_nodes, 3 * l.plane,
+                              l.prev, l.next, st);
+  if (l.node0 != 0 || l.n_global != l.n_nodes)  // index-list halo of the PCG (level 0)
+    return pcg_halo_exchange(dist, vfull, st);
+  return 0;
+}
+
+// b_c = mask_c P^T (b_f - A x_f) for the coarse level c of fine level l
+static int level_restrict(MgLevel &l, MgLevel &c, const double *b, sktb_pcg *dist,
+                          cudaStream_t st) {
+  const bool part = l.node0 != 0 || l.n_global != l.n_nodes;  // fine rows are a slab
+  const double *bf = b, *Axf = l.tmp;
+  int64_t f_lo = part ? l.node0 : 0, f_hi = part ? l.node0 + l.n_nodes : l.n_nodes;
+  int64_t c_lo = 0, c_hi = c.n_nodes, c_base = 0;
+  if (c.sharded) {
+    // sharded -> sharded: the owned coarse rows need the fine residual on one
+    // ghost plane each side: r = b - Ax into the full-length buffer, exchange
+    if (!l.res) {
+      SKTB_CUDA_OK(cudaMalloc(&l.res, sizeof(double) * 3 * l.n_global));
+      SKTB_CUDA_OK(cudaMemset(l.res, 0, sizeof(double) * 3 * l.n_global));
+    }
+    mg_residual_kernel<<<grid_for(3 * l.n_nodes), kBlock, 0, st>>>(
+        3 * l.n_nodes, b, l.tmp, l.res + 3 * l.node0);
+    SKTB_COUNT(1);
+    if (level_halo(l, l.res, dist, st)) return 1;
+    bf = l.res;
+    Axf = nullptr;
+    f_lo = 0;
+    f_hi = l.n_global;
+    c_lo = c.node0;
+    c_hi = c.node0 + c.n_nodes;
+    c_base = c.node0;
+  }
+  const int64_t nc = c_hi - c_lo;
+  if (nc > 20000)
+    mg_restrict_thread_kernel<<<grid_for(nc), kBlock, 0, st>>>(
+        l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f, l.axT_w, bf, Axf,
+        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base);
+  else
+    mg_restrict_kernel<<<grid_for(nc * 32, kBlock, 16), kBlock, 0, st>>>(
+        l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f, l.axT_w, bf, Axf,
+        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base);
+  SKTB_COUNT(1);
+  // sharded fine level, replicated coarse level: every rank summed its own fine
+  // rows into the whole coarse vector
+  if (part && !c.sharded && dist && pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st)) return 1;
+  return 0;
+}
+
+// z = M^-1 r : V cycle.  Level 0 and the large assembled levels may be z-slab
+// sharded (their x is a full-length vector whose ghost planes are refreshed
+// before every product); the remaining coarse levels are replicated.
 int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
               sktb_pcg *dist) {
   const int L = (int)m->lv.size();
   const int k_tail = tail_start(m);
-  const bool sharded = dist && pcg_is_dist(dist);
   MgLevel &l0 = m->lv[0];
-  const int64_t f_lo = l0.node0, f_hi = l0.node0 + l0.n_nodes;
   // downward sweep
   for (int k = 0; k < L; ++k) {
     if (k == k_tail) {
@@ -999,80 +1140,60 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     MgLevel &l = m->lv[k];
     const int64_t n = 3 * l.n_nodes;
     const double *b = (k == 0) ? r : l.b;
-    double *xfull = l.x;                                  // gather source of the SpMV
-    double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;       // owned rows
     const int g = grid_for(n);
     const double om = l.omega > 0.0 ? l.omega : m->omega;
+#define XOWN (l.x + 3 * l.node0)
     if (k == L - 1 && k > 0 && l.dense_n == n) {
       mg_dense_apply_kernel<<<(int)((n + kBlock / 32 - 1) / (kBlock / 32)), kBlock, 0, st>>>(
-          (int)n, l.dense_inv, b, x);
+          (int)n, l.dense_inv, b, XOWN);
       SKTB_COUNT(1);
       break;
     }
-    if (l.cheb && k > 0 && k < L - 1) {
+    if (l.cheb && k > 0 && k < L - 1 && !l.sharded) {
       // Chebyshev pre-smoothing of degree nu from a zero initial guess
       mg_cheby_kernel<<<g, kBlock, 0, st>>>(n, 0.0, l.cheb_c2[0], l.inv_diag, b, nullptr, 1,
-                                           l.d, x);
+                                           l.d, l.x);
       SKTB_COUNT(1);
       for (int s = 1; s < l.nu; ++s) {
-        if (level_spmv(l, xfull, l.tmp, st)) return 1;
+        if (level_spmv(l, l.x, l.tmp, st)) return 1;
         mg_cheby_kernel<<<g, kBlock, 0, st>>>(n, l.cheb_c1[s], l.cheb_c2[s], l.inv_diag, b,
-                                             l.tmp, 0, l.d, x);
+                                             l.tmp, 0, l.d, l.x);
         SKTB_COUNT(1);
       }
-      if (level_spmv(l, xfull, l.tmp, st)) return 1;
-      MgLevel &c = m->lv[k + 1];
-      mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
-          l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
-          l.axT_w, b, l.tmp, c.mask, c.b, 0, l.n_nodes);
-      SKTB_COUNT(1);
+      if (level_spmv(l, l.x, l.tmp, st)) return 1;
+      if (level_restrict(l, m->lv[k + 1], b, dist, st)) return 1;
       continue;
     }
-    mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, x);
+    mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, XOWN);
     SKTB_COUNT(1);
     if (k == L - 1 && k > 0 && l.n_nodes <= 4096) {
       // (jacobi0 above is redone inside; harmless and keeps the code uniform)
       mg_coarse_solve_kernel<<<1, 1024, 0, st>>>((int)l.n_nodes, l.node_ptr,
                                                  l.node_col, l.vals, l.inv_diag,
-                                                 b, om, m->nu_coarse, x, l.tmp);
+                                                 b, om, m->nu_coarse, l.x, l.tmp);
       SKTB_COUNT(1);
     } else if (k == L - 1) {
       for (int s = 0; s < m->nu_coarse; ++s) {
-        if (level_spmv(l, xfull, l.tmp, st)) return 1;
-        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+        if (level_halo(l, l.x, dist, st)) return 1;
+        if (level_spmv(l, l.x, l.tmp, st)) return 1;
+        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, XOWN);
         SKTB_COUNT(1);
       }
     } else {
       for (int s = 1; s < l.nu; ++s) {  // extra pre-smoothing sweeps
+        if (level_halo(l, l.x, dist, st)) return 1;
         if (k > 0 && m->fused_sweeps) {
           const int rc = level_sweep(l, b, om, st);
-          if (rc == 0) {
-            xfull = x = l.x;  // the buffers swapped
-            continue;
-          }
+          if (rc == 0) continue;
           if (rc != -1) return rc;
         }
-        if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
-        if (level_spmv(l, xfull, l.tmp, st)) return 1;
-        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+        if (level_spmv(l, l.x, l.tmp, st)) return 1;
+        mg_jacobi_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, XOWN);
         SKTB_COUNT(1);
       }
-      if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
-      if (level_spmv(l, xfull, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
-      MgLevel &c = m->lv[k + 1];
-      const int64_t lo = (k == 0) ? f_lo : 0;
-      const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
-      if (c.n_nodes > 20000)
-        mg_restrict_thread_kernel<<<grid_for(c.n_nodes), kBlock, 0, st>>>(
-            l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
-            l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
-      else
-        mg_restrict_kernel<<<grid_for(c.n_nodes * 32, kBlock, 16), kBlock, 0, st>>>(
-            l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f,
-            l.axT_w, b, l.tmp, c.mask, c.b, lo, hi);
-      SKTB_COUNT(1);
-      if (k == 0 && sharded && pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st))
-        return 1;
+      if (level_halo(l, l.x, dist, st)) return 1;
+      if (level_spmv(l, l.x, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
+      if (level_restrict(l, m->lv[k + 1], b, dist, st)) return 1;
     }
   }
   // upward sweep
@@ -1082,48 +1203,43 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     MgLevel &c = m->lv[k + 1];
     const int64_t n = 3 * l.n_nodes;
     const double *b = (k == 0) ? r : l.b;
-    double *xfull = l.x;
-    double *x = (k == 0) ? l.x + 3 * l.node0 : l.x;
-    const int64_t lo = (k == 0) ? f_lo : 0;
-    const int64_t hi = (k == 0) ? f_hi : l.n_nodes;
+    const int64_t lo = l.node0, hi = l.node0 + l.n_nodes;
     const double om = l.omega > 0.0 ? l.omega : m->omega;
+    if (level_halo(c, c.x, dist, st)) return 1;  // ghost planes of a sharded coarse level
     mg_prolong_kernel<<<grid_for(hi - lo), kBlock, 0, st>>>(
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.ax_c0,
-        l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, xfull, lo, hi);
+        l.ax_c1, l.ax_w0, l.ax_w1, c.x, l.mask, l.x, lo, hi);
     SKTB_COUNT(1);
-    if (l.cheb && k > 0) {
+    if (l.cheb && k > 0 && !l.sharded) {
       for (int s = 0; s < l.nu; ++s) {
-        if (level_spmv(l, xfull, l.tmp, st)) return 1;
+        if (level_spmv(l, l.x, l.tmp, st)) return 1;
         mg_cheby_kernel<<<grid_for(n), kBlock, 0, st>>>(n, s ? l.cheb_c1[s] : 0.0,
                                                        l.cheb_c2[s], l.inv_diag, b, l.tmp, 0,
-                                                       l.d, x);
+                                                       l.d, l.x);
         SKTB_COUNT(1);
       }
       continue;
     }
     for (int s = 1; s < l.nu; ++s) {  // extra post-smoothing sweeps
+      if (level_halo(l, l.x, dist, st)) return 1;
       if (k > 0 && m->fused_sweeps) {
         const int rc = level_sweep(l, b, om, st);
-        if (rc == 0) {
-          xfull = x = l.x;
-          continue;
-        }
+        if (rc == 0) continue;
         if (rc != -1) return rc;
       }
-      if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
-      if (level_spmv(l, xfull, l.tmp, st)) return 1;
-      mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+      if (level_spmv(l, l.x, l.tmp, st)) return 1;
+      mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, XOWN);
       SKTB_COUNT(1);
     }
+    if (level_halo(l, l.x, dist, st)) return 1;
     if (k > 0 && m->fused_sweeps) {  // last post-smoothing sweep
       const int rc = level_sweep(l, b, om, st);
       if (rc == 0) continue;
       if (rc != -1) return rc;
     }
-    if (k == 0 && sharded && pcg_halo_exchange(dist, xfull, st)) return 1;
     if (k == 0 && l.gop) {
       // fused post-smoothing straight into z: z = x + om D^-1 (r - A x)
-      int rc = launch_hexgrid_apply_ex(l.gop, l.node0, l.n_nodes, xfull, z, m->fp32_level0,
+      int rc = launch_hexgrid_apply_ex(l.gop, l.node0, l.n_nodes, l.x, z, m->fp32_level0,
                                        b, l.inv_diag, om, st);
       if (rc == 0) {
         z_done = true;
@@ -1131,10 +1247,11 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       }
       if (rc != -1) return rc;
     }
-    if (level_spmv(l, xfull, l.tmp, st)) return 1;
-    mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, x);
+    if (level_spmv(l, l.x, l.tmp, st)) return 1;
+    mg_jacobi_kernel<<<grid_for(n), kBlock, 0, st>>>(n, om, l.inv_diag, b, l.tmp, XOWN);
     SKTB_COUNT(1);
   }
+#undef XOWN
   if (!z_done)
     SKTB_CUDA_OK(cudaMemcpyAsync(z, l0.x + 3 * l0.node0, sizeof(double) * 3 * l0.n_nodes,
                                  cudaMemcpyDeviceToDevice, st));
@@ -1146,4 +1263,17 @@ extern "C" int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stre
   SKTB_REQUIRE(m && r && z, "null argument");
   for (auto &l : m->lv) SKTB_REQUIRE(l.node_ptr || l.gop, "multigrid level not set");
   return mg_vcycle(m, r, z, (cudaStream_t)stream, nullptr);
+}
+
+// y[owned rows] = A_level x for a full-length x (ghost planes of a sharded
+// level are refreshed first; `dist` may be null on one GPU).  Used by the
+// host-driven power iteration that sets the per-level damping.
+extern "C" int sktb_mg_level_apply(sktb_mg *m, int level, sktb_pcg *dist, double *x_full,
+                                   double *y_own, void *stream) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size() && x_full && y_own, "bad argument");
+  MgLevel &l = m->lv[level];
+  SKTB_REQUIRE(l.node_ptr || l.gop, "multigrid level not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (level_halo(l, x_full, dist, st)) return 1;
+  return level_spmv(l, x_full, y_own, st);
 }

@@ -38,6 +38,11 @@ struct sktb_pcg {
   std::vector<int64_t> send_off, recv_off;
   int32_t *send_idx = nullptr, *recv_idx = nullptr;  // device, global indices
   double *sendbuf = nullptr, *recvbuf = nullptr;
+  // z-slab halo (tensor grids): whole node planes, exchanged straight from /
+  // into the full-length vector with the previous / next rank; replaces the
+  // index lists above when plane > 0
+  int64_t slab_plane = 0;
+  int slab_prev = -1, slab_next = -1;
   // in-situ SpMV timing
   int prof_every = 0;
   static constexpr int kMaxProf = 64;
@@ -271,8 +276,34 @@ __global__ void __launch_bounds__(kBlock)
   for (; i < n; i += stride) p[idx[i]] = buf[i];
 }
 
+int slab_halo_exchange(sktb_comm *c, double *v, int64_t own0, int64_t n_own,
+                       int64_t plane, int prev, int next, cudaStream_t st) {
+  if (!c || plane <= 0) return 0;
+  P2POp ops[2];
+  int n = 0;
+  if (prev >= 0) ops[n++] = {prev, v + own0, plane, v + own0 - plane, plane};
+  if (next >= 0)
+    ops[n++] = {next, v + own0 + n_own - plane, plane, v + own0 + n_own, plane};
+  return comm_p2p(c, n, ops, st);
+}
+
+extern "C" int sktb_pcg_set_slab_halo(sktb_pcg *s, int64_t plane_dofs, int prev_rank,
+                                      int next_rank) {
+  SKTB_REQUIRE(s && s->comm && plane_dofs > 0 && plane_dofs <= s->n, "bad argument");
+  SKTB_REQUIRE(prev_rank < 0 || s->row0 >= plane_dofs, "no room for the lower ghost plane");
+  SKTB_REQUIRE(next_rank < 0 || s->row0 + s->n + plane_dofs <= s->n_global,
+               "no room for the upper ghost plane");
+  s->slab_plane = plane_dofs;
+  s->slab_prev = prev_rank;
+  s->slab_next = next_rank;
+  return 0;
+}
+
 // ghost entries of the full-length vector v <- owners' values
 static int halo_exchange(sktb_pcg *s, double *v, cudaStream_t st) {
+  if (s->comm && s->slab_plane > 0)
+    return slab_halo_exchange(s->comm, v, s->row0, s->n, s->slab_plane, s->slab_prev,
+                              s->slab_next, st);
   const int np = (int)s->peers.size();
   if (!s->comm || np == 0) return 0;
   const int64_t ns = s->send_off[np], nr = s->recv_off[np];
@@ -293,6 +324,7 @@ static int halo_exchange(sktb_pcg *s, double *v, cudaStream_t st) {
 }
 
 bool pcg_is_dist(const sktb_pcg *s) { return s && s->comm != nullptr; }
+sktb_comm *pcg_comm(const sktb_pcg *s) { return s ? s->comm : nullptr; }
 int pcg_halo_exchange(sktb_pcg *s, double *full_vec, cudaStream_t st) {
   return halo_exchange(s, full_vec, st);
 }
@@ -443,14 +475,16 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
       pcg_update_kernel<<<vgrid, kBlock, 0, st>>>(n, p_own, s->q, inv_diag, x,
                                                  s->r, s->z, s->partials,
                                                  s->ticket, s->Sloc, s->S);
-      if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
       if (mg) {
+        // one all-reduce for (r.z, ||r||^2) after the V-cycle instead of one on
+        // each side of it: until then the kernels of the V-cycle see the previous
+        // ||r||^2, so at worst the converging iteration runs one idle V-cycle
         if (mg_vcycle(mg, s->r, s->z, st, s)) return 1;
         pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 0, s->partials,
                                                s->ticket, s->Sloc, s->S);
         SKTB_COUNT(1);
-        if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 1, st)) return 1;
       }
+      if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
       pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, p_own, s->ticket,
                                                     s->S);
       SKTB_COUNT(2);

@@ -70,9 +70,10 @@ __global__ void __launch_bounds__(kBlock, 6)
     if (lane == 0) {
       const int64_t r = 3 * n;
       if (J.b) {  // fused damped-Jacobi sweep
-        a0 = x[r] + J.omega * J.dinv[r] * (J.b[r] - a0);
-        a1 = x[r + 1] + J.omega * J.dinv[r + 1] * (J.b[r + 1] - a1);
-        a2 = x[r + 2] + J.omega * J.dinv[r + 2] * (J.b[r + 2] - a2);
+        const double *xo = J.xo ? J.xo : x;
+        a0 = xo[r] + J.omega * J.dinv[r] * (J.b[r] - a0);
+        a1 = xo[r + 1] + J.omega * J.dinv[r + 1] * (J.b[r + 1] - a1);
+        a2 = xo[r + 2] + J.omega * J.dinv[r + 2] * (J.b[r + 2] - a2);
       }
       y[r] = a0;
       y[r + 1] = a1;

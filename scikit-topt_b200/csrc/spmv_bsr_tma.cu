@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kBlock, 2)
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       if (quarter == 0 && ln < nn) {
         const int64_t r = 3 * (n_a + ln) + ri;
-        if (J.b) acc = x[r] + J.omega * J.dinv[r] * (J.b[r] - acc);  // fused Jacobi sweep
+        if (J.b)  // fused Jacobi sweep
+          acc = (J.xo ? J.xo : x)[r] + J.omega * J.dinv[r] * (J.b[r] - acc);
         y[r] = acc;
         if (DOT) dot += acc * dotv[r];
       }

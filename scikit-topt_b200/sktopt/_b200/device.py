@@ -160,10 +160,19 @@ class DeviceMesh:
             self._graph_h = self.node_graph()
         return self._graph_h
 
-    def assemble_rows(self, dpn, n0, n1, unit_ke, scale=None, dir_mask=None, out=None):
+    def assemble_rows(self, dpn, n0, n1, unit_ke, scale=None, dir_mask=None, out=None,
+                      per_element=False, ke_base: int = 0):
+        """Rows of the nodes [n0, n1).  ``per_element=True``: ``unit_ke`` holds one
+        matrix per element, starting with element ``ke_base`` (a slab of the
+        element range: only the elements touching the rows are read)."""
+        nde = dpn * self.nen
+        ke_ptr = _ptr(unit_ke)
+        if per_element and ke_base:
+            ke_ptr = C.c_void_p(unit_ke.data_ptr() - int(ke_base) * nde * nde * 8)
         _lib.check(
             self.lib.sktb_assemble_rows(
-                self.handle, dpn, int(n0), int(n1), _ptr(unit_ke), _ptr(self.elem_class),
+                self.handle, dpn, int(n0), int(n1), ke_ptr,
+                None if per_element else _ptr(self.elem_class),
                 _ptr(scale), _ptr(dir_mask), _ptr(out), _stream(),
             )
         )
@@ -473,6 +482,11 @@ class PcgSolver:
             except Exception:
                 pass
             self.handle = None
+
+    def set_slab_halo(self, plane_dofs: int, prev_rank: int, next_rank: int):
+        """z-slab halo: whole planes exchanged with the previous / next rank."""
+        _lib.check(self.lib.sktb_pcg_set_slab_halo(self.handle, int(plane_dofs),
+                                                   int(prev_rank), int(next_rank)))
 
     def set_profile(self, every_n: int):
         _lib.check(self.lib.sktb_pcg_set_profile(self.handle, int(every_n)))

@@ -62,10 +62,27 @@ class Comm:
         return buf
 
 
-def make_unique_id() -> bytes:
+def make_unique_id(transport: str = "nccl") -> bytes:
+    """128-byte communicator id: an ncclUniqueId, or ``SHM:<random>`` for the
+    host shared-memory transport (several ranks on ONE GPU: correctness runs of
+    the sharded paths on a one-GPU box; ``csrc/comm.cuh``)."""
+    if transport == "shm":
+        import secrets
+        return (b"SHM:" + secrets.token_hex(16).encode()).ljust(128, b"\0")
     buf = C.create_string_buffer(128)
     _lib.check(_lib.load().sktb_comm_unique_id(C.cast(buf, C.c_void_p)))
     return buf.raw
+
+
+def transport() -> str:
+    """``SKTOPT_B200_COMM`` = nccl | shm; default: shm when the torch.distributed
+    job itself runs on gloo (ranks sharing a GPU), else nccl."""
+    import os
+    import torch.distributed as dist
+    want = os.environ.get("SKTOPT_B200_COMM", "auto").lower()
+    if want in ("nccl", "shm"):
+        return want
+    return "shm" if dist.get_backend() == "gloo" else "nccl"
 
 
 def default_comm():
@@ -77,7 +94,7 @@ def default_comm():
         return None
     if _DEFAULT is None:
         rank, world = dist.get_rank(), dist.get_world_size()
-        box = [make_unique_id() if rank == 0 else None]
+        box = [make_unique_id(transport()) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         _DEFAULT = Comm(rank, world, torch.cuda.current_device(), box[0])
     return _DEFAULT
@@ -119,6 +136,12 @@ def partition_nodes(node_ptr: np.ndarray, world: int) -> np.ndarray:
         cuts.append(k)
     cuts.append(n_nodes)
     return np.asarray(cuts, dtype=np.int64)
+
+
+def partition_planes(n_planes: int, world: int) -> np.ndarray:
+    """Contiguous ranges of whole z-planes, as even as possible.  Returns the
+    world+1 plane boundaries."""
+    return np.round(np.linspace(0, n_planes, world + 1)).astype(np.int64)
 
 
 def build_halo(node_ptr: np.ndarray, node_col: np.ndarray, cuts: np.ndarray,

@@ -49,6 +49,11 @@ SIGNATURES = {
     "sktb_mg_set_level_omega": [C.c_void_p, i32, f64],
     "sktb_pcg_lambda_max_bsr3": [C.c_void_p, c_i32p, c_i32p, i64, i32, c_f64p, c_f64p, i32, C.c_void_p, c_stream],
     "sktb_mg_set_level0_range": [C.c_void_p, i64, i64],
+    "sktb_mg_set_level_slab": [C.c_void_p, i32, i64, i64, i64, i32, i32],
+    "sktb_mg_level_apply": [C.c_void_p, i32, C.c_void_p, c_f64p, c_f64p, c_stream],
+    "sktb_elem_restrict_range": [i64, i64, i64, i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_elem_combine_range": [i64, i64, i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_pcg_set_slab_halo": [C.c_void_p, i64, i32, i32],
     "sktb_mg_set_transfer": [C.c_void_p, i32, C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
     "sktb_mg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
     "sktb_gridop_create": [C.POINTER(C.c_void_p), i32, C.c_void_p, C.c_void_p, i32],

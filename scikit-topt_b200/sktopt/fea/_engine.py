@@ -52,10 +52,35 @@ class FeaEngine:
         self.dir_mask = dev.to_dev(mask, dev.U8)
         self.has_dirichlet = bool(mask.any())
         self.comm = comm
+        axes = None
+        if dm.elem_class is not None and dm.nen == 8:
+            from sktopt.fea._multigrid import detect_tensor_grid, vertex_bits
+            axes = detect_tensor_grid(basis.mesh)
+        self.axes = axes
+        self.plane_cuts = None      # z-plane cuts of a slab-sharded tensor grid
+        self.slab = None
         if comm is None:
             self.node0, self.node1 = 0, dm.n_nodes
             self.pcg = dev.PcgSolver(self.n_dof)
             self.cuts = None
+        elif axes is not None and axes[2].size >= 2 * comm.world:
+            # tensor grid: whole z-planes per rank (element blocks =
+            # slabs along the slowest axis).  The halo is one node plane each side,
+            # sent straight from / into the full-length vectors; the multigrid
+            # levels follow the same cuts.
+            npz, plane = int(axes[2].size), int(axes[0].size * axes[1].size)
+            self.plane_cuts = bdist.partition_planes(npz, comm.world)
+            self.cuts = self.plane_cuts * plane
+            r = comm.rank
+            self.node0, self.node1 = int(self.cuts[r]), int(self.cuts[r + 1])
+            empty = (np.zeros(0, np.int32), np.zeros(1, np.int64), np.zeros(0, np.int32),
+                     np.zeros(1, np.int64), np.zeros(0, np.int32))
+            self.pcg = dev.PcgSolver(dpn * (self.node1 - self.node0), comm=comm,
+                                     n_global=self.n_dof, row0=dpn * self.node0, halo=empty)
+            self.slab = dict(plane=plane, prev=r - 1 if r > 0 else -1,
+                             next=r + 1 if r < comm.world - 1 else -1)
+            self.pcg.set_slab_halo(dpn * plane, self.slab["prev"], self.slab["next"])
+            self.halo_dofs = dpn * plane * ((r > 0) + (r < comm.world - 1))
         else:
             rp_h, ci_h = dm.node_graph_cached()
             self.cuts = bdist.partition_nodes(rp_h, comm.world)
@@ -73,10 +98,8 @@ class FeaEngine:
         # matrix-free operator: uniform hexahedral tensor grid (one geometry
         # class), elasticity.  SKTOPT_B200_MATFREE=0 keeps the assembled SpMV.
         self.gridop = None
-        axes = None
-        if dpn == 3 and dm.elem_class is not None:
-            from sktopt.fea._multigrid import detect_tensor_grid, vertex_bits
-            axes = detect_tensor_grid(basis.mesh)
+        if dpn != 3:
+            axes = None
         if (axes is not None and dm.n_class == 1
                 and os.environ.get("SKTOPT_B200_MATFREE", "1") != "0"):
             self.gridop = dev.GridOp([a.size for a in axes],

@@ -190,6 +190,7 @@ class Multigrid:
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
+        self._plan_sharding()
         for l in range(1, self.n_levels):
             cxs, cys, czs = coords[l]
             mesh_c = MeshHex.init_tensor(cxs, cys, czs)
@@ -200,6 +201,16 @@ class Multigrid:
             fine_cells = tuple(c.size - 1 for c in coords[l - 1])
             coarse_cells = tuple(c.size - 1 for c in coords[l])
             child, ptype = child_tables(fine_cells, coarse_cells)
+            sh = self.shard[l]
+            if sh is not None:
+                # owned rows only (global columns); element matrices of the slab
+                n0, n1 = sh["node0"], sh["node1"]
+                s_, e_ = int(rp_h[n0]), int(rp_h[n1])
+                rp_loc, ci_loc = rp_h[n0:n1 + 1] - s_, ci_h[s_:e_]
+                n_ke = sh["elem1"] - sh["elem0"]
+            else:
+                rp_loc, ci_loc, n0, n1 = rp_h, ci_h, 0, dm.n_nodes
+                n_ke = dm.n_elem
             # Dirichlet mask: a coarse dof is fixed iff the coincident fine dof is
             fm = [coarse_index_map(n) for n in fine_cells]
             npx_f, npy_f = fine_cells[0] + 1, fine_cells[1] + 1
@@ -208,13 +219,13 @@ class Multigrid:
             fnode = (fm[1][Iy] + npy_f * fm[0][Ix] + npy_f * npx_f * fm[2][Iz]).ravel()
             mask_c = mask_f.reshape(-1, 3)[fnode].ravel().copy()
             lvl = dict(
-                dm=dm, n_nodes=dm.n_nodes, n_elem=dm.n_elem,
-                node_ptr=dev.to_dev(rp_h, dev.I32), node_col=dev.to_dev(ci_h, dev.I32),
-                max_deg=int(np.diff(rp_h).max()),
-                vals=torch.empty(9 * ci_h.size, dtype=dev.F64, device="cuda"),
-                inv_diag=torch.empty(3 * dm.n_nodes, dtype=dev.F64, device="cuda"),
+                dm=dm, n_nodes=dm.n_nodes, n_elem=dm.n_elem, node0=n0, node1=n1,
+                node_ptr=dev.to_dev(rp_loc, dev.I32), node_col=dev.to_dev(ci_loc, dev.I32),
+                max_deg=int(np.diff(rp_loc).max()),
+                vals=torch.empty(9 * ci_loc.size, dtype=dev.F64, device="cuda"),
+                inv_diag=torch.empty(3 * (n1 - n0), dtype=dev.F64, device="cuda"),
                 mask=dev.to_dev(mask_c, dev.U8),
-                ke=torch.empty((dm.n_elem, 576), dtype=dev.F64, device="cuda"),
+                ke=torch.empty((n_ke, 576), dtype=dev.F64, device="cuda"),
                 child=dev.to_dev(child, dev.I32), ptype=dev.to_dev(ptype, dev.U8),
             )
             self.levels.append(lvl)
@@ -258,6 +269,64 @@ class Multigrid:
                         T[k, ty_, ch] = Qv.T @ ke0[k] @ Qv
             self.T01 = dev.to_dev(T.ravel())
 
+    # ------------------------------------------------------------ sharding --
+    SHARD_MIN_NODES = 300000
+
+    def _plan_sharding(self):
+        """z-slab ownership of every level.  Level 0 follows the
+        engine's node range; a coarse plane belongs to the rank that owns the
+        coincident fine plane.  Assembled levels with at least
+        ``SKTOPT_B200_MG_SHARD_MIN`` nodes (and >= 2 planes on every rank) are
+        sharded: a rank stores the rows of its planes and computes the Galerkin
+        element matrices of its slab only.  The first replicated level gets its
+        element matrices from slab-wise products that are all-gathered."""
+        eng = self.eng
+        L = self.n_levels
+        self.shard = [None] * L
+        self.first_replicated = 1
+        self.gather_plan = None
+        comm = eng.comm
+        if comm is None or getattr(eng, "plane_cuts", None) is None:
+            return
+        world, rank = comm.world, comm.rank
+        shard_min = int(os.environ.get("SKTOPT_B200_MG_SHARD_MIN", self.SHARD_MIN_NODES))
+        zc = [np.asarray(eng.plane_cuts, dtype=np.int64)]   # plane cuts per level
+        for l in range(1, L):
+            nz_f = self.coords[l - 1][2].size - 1
+            fmap = coarse_index_map(nz_f)                    # fine plane of coarse plane
+            owner = np.searchsorted(zc[-1], fmap, side="right") - 1
+            zc.append(np.searchsorted(owner, np.arange(world + 1), side="left").astype(np.int64))
+        self.plane_cuts = zc
+        last = 0
+        for l in range(1, L - 1):
+            xs, ys, zs = self.coords[l]
+            if xs.size * ys.size * zs.size < shard_min or np.diff(zc[l]).min() < 2:
+                break
+            last = l
+        self.first_replicated = last + 1
+        if last == 0:
+            return
+        # element planes whose matrices this rank needs, from the coarsest
+        # sharded level upwards; the first replicated level is split evenly for
+        # the all-gather of its element matrices
+        lr = self.first_replicated
+        cz_lr = self.coords[lr][2].size - 1
+        a = np.round(np.linspace(0, cz_lr, world + 1)).astype(np.int64)
+        plane_e = lambda l: (self.coords[l][0].size - 1) * (self.coords[l][1].size - 1)
+        self.gather_plan = dict(level=lr, cuts=a, plane_elems=plane_e(lr))
+        need_lo, need_hi = int(a[rank]), int(a[rank + 1])
+        for l in range(last, 0, -1):
+            cz = self.coords[l][2].size - 1
+            z0, z1 = int(zc[l][rank]), int(zc[l][rank + 1])
+            lo = min(max(z0 - 1, 0), 2 * need_lo) if need_hi > need_lo else max(z0 - 1, 0)
+            hi = max(min(z1, cz), min(2 * need_hi, cz)) if need_hi > need_lo else min(z1, cz)
+            npl = self.coords[l][0].size * self.coords[l][1].size
+            self.shard[l] = dict(node0=z0 * npl, node1=z1 * npl, plane=npl,
+                                 prev=rank - 1 if rank > 0 else -1,
+                                 next=rank + 1 if rank < world - 1 else -1,
+                                 elem0=lo * plane_e(l), elem1=hi * plane_e(l))
+            need_lo, need_hi = lo, hi
+
     def __del__(self):
         h = getattr(self, "handle", None)
         if h is not None and h.value:
@@ -288,6 +357,8 @@ class Multigrid:
                 dev._stream()))
             return float(out.value)
         lv = self.levels[l]
+        if self.shard[l] is not None:
+            return self._lambda_max_sharded(l, iters)
         n = 3 * lv["n_nodes"]
         g = torch.Generator(device="cuda")
         g.manual_seed(1234)
@@ -301,6 +372,70 @@ class Multigrid:
             lam = dev.dot(v, w)
             v, w = w, v
         return float(lam)
+
+    def _lambda_max_sharded(self, l: int, iters: int) -> float:
+        """Power iteration on a z-slab-sharded level: products over the owned rows
+        (ghost planes exchanged inside ``sktb_mg_level_apply``), dots all-reduced.
+        The start vector is a function of the global index, so every rank count
+        gives the same estimate."""
+        lv, sh, eng = self.levels[l], self.shard[l], self.eng
+        n_glob = 3 * lv["n_nodes"]
+        lo, hi = 3 * sh["node0"], 3 * sh["node1"]
+        idx = torch.arange(n_glob, dtype=torch.int64, device="cuda")
+        v = ((idx * 2654435761) % 1048573).to(dev.F64) / 1048573.0 - 0.5
+        w = torch.empty(hi - lo, dtype=dev.F64, device="cuda")
+        pack = torch.empty(1, dtype=dev.F64, device="cuda")
+
+        def gdot(a, b):
+            pack[0] = dev.dot(a, b)
+            return float(eng.comm.allreduce_sum(pack)[0])
+        lam = 1.0
+        for _ in range(iters):
+            own = v[lo:hi]
+            own /= float(np.sqrt(gdot(own, own)))
+            _lib.check(self.lib.sktb_mg_level_apply(self.handle, l, eng.pcg.handle, dev._ptr(v),
+                                                    dev._ptr(w), dev._stream()))
+            dev.hadamard(1.0, w, lv["inv_diag"], w)
+            lam = gdot(own, w)
+            own.copy_(w)
+        return float(lam)
+
+    def _galerkin_level(self, l: int, st):
+        """Element matrices of level ``l`` for the element range this rank needs."""
+        eng, lib, lv = self.eng, self.lib, self.levels[l]
+        sh = self.shard[l]
+        gp = self.gather_plan
+        ke_out = lv["ke"]
+        if sh is not None:
+            e_lo, e_hi = sh["elem0"], sh["elem1"]
+        elif gp is not None and gp["level"] == l:
+            r = eng.comm.rank
+            e_lo, e_hi = (int(gp["cuts"][r]) * gp["plane_elems"],
+                          int(gp["cuts"][r + 1]) * gp["plane_elems"])
+            ke_out = lv["ke"][e_lo:]           # written at its global position
+        else:
+            e_lo, e_hi = 0, lv["n_elem"]
+        if e_hi > e_lo:
+            if l == 1 and self.T01 is not None:
+                _lib.check(lib.sktb_elem_combine_range(
+                    lv["n_elem"], e_lo, e_hi, dev._ptr(lv["child"]), dev._ptr(lv["ptype"]),
+                    dev._ptr(self.T01), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
+                    dev._ptr(ke_out), st))
+            elif l == 1:
+                _lib.check(lib.sktb_elem_restrict_range(
+                    lv["n_elem"], e_lo, e_hi, 0, dev._ptr(lv["child"]), dev._ptr(lv["ptype"]),
+                    dev._ptr(self.Qtab), None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class),
+                    dev._ptr(eng.scale), dev._ptr(ke_out), st))
+            else:
+                fsh = self.shard[l - 1]
+                _lib.check(lib.sktb_elem_restrict_range(
+                    lv["n_elem"], e_lo, e_hi, 0 if fsh is None else fsh["elem0"],
+                    dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
+                    dev._ptr(self.levels[l - 1]["ke"]), None, None, None, dev._ptr(ke_out), st))
+        if sh is None and gp is not None and gp["level"] == l:
+            # slab-wise products -> whole level on every rank
+            cnt = np.diff(gp["cuts"]) * gp["plane_elems"] * 576
+            eng.comm.allgatherv(lv["ke"].view(-1), cnt, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
 
     def setup(self):
         """Galerkin coarse operators for the engine's current modulus field;
@@ -319,28 +454,32 @@ class Multigrid:
                 self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()),
                 int(eng.max_deg), dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc),
                 dev._ptr(eng.vals), dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        sh0 = getattr(eng, "slab", None)
+        if sh0 is not None:
+            _lib.check(lib.sktb_mg_set_level_slab(
+                self.handle, 0, int(eng.node0), int(eng.dm.n_nodes), int(sh0["plane"]),
+                int(sh0["prev"]), int(sh0["next"])))
         for l in range(1, self.n_levels):
             lv = self.levels[l]
-            if l == 1 and self.T01 is not None:
-                _lib.check(lib.sktb_elem_combine(
-                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.T01),
-                    dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale), dev._ptr(lv["ke"]), st))
-            elif l == 1:
-                _lib.check(lib.sktb_elem_restrict(
-                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
-                    None, dev._ptr(eng.unit_ke), dev._ptr(eng.dm.elem_class), dev._ptr(eng.scale),
-                    dev._ptr(lv["ke"]), st))
+            sh = self.shard[l]
+            self._galerkin_level(l, st)
+            if sh is not None:
+                lv["dm"].assemble_rows(3, sh["node0"], sh["node1"], lv["ke"], scale=None,
+                                       dir_mask=lv["mask"], out=lv["vals"], per_element=True,
+                                       ke_base=sh["elem0"])
+                dev.bsr3_inv_diag(lv["node_ptr"], lv["node_col"], lv["vals"], out=lv["inv_diag"],
+                                  node0=sh["node0"])
+                _lib.check(lib.sktb_mg_set_level_slab(
+                    self.handle, l, sh["node0"], lv["n_nodes"], sh["plane"], sh["prev"],
+                    sh["next"]))
             else:
-                _lib.check(lib.sktb_elem_restrict(
-                    lv["n_elem"], dev._ptr(lv["child"]), dev._ptr(lv["ptype"]), dev._ptr(self.Qtab),
-                    dev._ptr(self.levels[l - 1]["ke"]), None, None, None, dev._ptr(lv["ke"]), st))
-            lv["dm"].assemble(3, lv["ke"], scale=None, dir_mask=lv["mask"], out=lv["vals"],
-                              per_element=True)
-            dev.bsr3_inv_diag(lv["node_ptr"], lv["node_col"], lv["vals"], out=lv["inv_diag"])
+                lv["dm"].assemble(3, lv["ke"], scale=None, dir_mask=lv["mask"], out=lv["vals"],
+                                  per_element=True)
+                dev.bsr3_inv_diag(lv["node_ptr"], lv["node_col"], lv["vals"], out=lv["inv_diag"])
             _lib.check(lib.sktb_mg_set_level(
-                self.handle, l, lv["n_nodes"], int(lv["node_col"].numel()), lv["max_deg"],
-                dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
-                dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+                self.handle, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()),
+                lv["max_deg"], dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]),
+                dev._ptr(lv["vals"]), dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
         _lib.check(lib.sktb_mg_factor_coarsest(self.handle, st))
         if self.omega_auto and self.setup_count == 0:
             # per-level damping: omega_l * lambda_max_l ~ 1.75, inside the

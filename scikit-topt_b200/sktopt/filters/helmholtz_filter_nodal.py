@@ -31,6 +31,7 @@ import numpy as np
 import torch
 
 from sktopt._b200 import device as dev
+from sktopt._b200 import dist as bdist
 from sktopt._fem import Basis, ElementHex1, ElementTetP1, MeshHex, MeshTet
 from sktopt.filters.base import BaseFilter
 
@@ -109,7 +110,33 @@ class _HelmholtzDevice:
         self.rhs = torch.empty(n, dtype=dev.F64, device="cuda")
         self.x_fwd = torch.zeros(n, dtype=dev.F64, device="cuda")
         self.x_adj = torch.zeros(n, dtype=dev.F64, device="cuda")
-        self.pcg = dev.PcgSolver(n)
+        # several GPUs (one process each): the grid systems are solved by a
+        # z-slab-sharded PCG (halo planes + dot all-reduces, csrc/pcg.cu), every
+        # rank then holds the whole filtered field again (all-gather), so the
+        # cheap element <-> node gathers stay replicated and all ranks see
+        # bit-identical densities.  The direct (fast-diagonalisation) solve is a
+        # replicated stage and is only kept on one GPU.
+        self.comm = None
+        self.lo, self.hi = 0, n
+        comm = bdist.default_comm()
+        if (comm is not None and self.grid is not None
+                and self.grid["np_axes"][2] >= 2 * comm.world
+                and os.environ.get("SKTOPT_B200_FILTER_SHARD", "1") != "0"):
+            npx, npy, npz = (int(v) for v in self.grid["np_axes"])
+            plane = npx * npy
+            cuts = bdist.partition_planes(npz, comm.world) * plane
+            r = comm.rank
+            self.comm, self.cuts = comm, cuts
+            self.lo, self.hi = int(cuts[r]), int(cuts[r + 1])
+            empty = (np.zeros(0, np.int32), np.zeros(1, np.int64), np.zeros(0, np.int32),
+                     np.zeros(1, np.int64), np.zeros(0, np.int32))
+            self.pcg = dev.PcgSolver(self.hi - self.lo, comm=comm, n_global=n, row0=self.lo,
+                                     halo=empty)
+            self.pcg.set_slab_halo(plane, r - 1 if r > 0 else -1,
+                                   r + 1 if r < comm.world - 1 else -1)
+            self.fd = None
+        else:
+            self.pcg = dev.PcgSolver(n)
         self.radius = None
         self.solve_iters = []
 
@@ -152,8 +179,11 @@ class _HelmholtzDevice:
             return self.fd.solve(rhs, out=x)
         if self.grid is not None:
             self.gop_A.set_scale(None, dmask=self.flags_fixed if enforced else self.flags_free)
-            self.pcg.solve_grid(self.gop_A, minv, rhs, x, rtol=self.RTOL, maxiter=self.MAXITER,
-                                use_x0=True, check_every=8)
+            lo, hi = self.lo, self.hi
+            self.pcg.solve_grid(self.gop_A, minv[lo:hi], rhs[lo:hi], x[lo:hi], rtol=self.RTOL,
+                                maxiter=self.MAXITER, use_x0=True, check_every=8)
+            if self.comm is not None:
+                self.comm.allgatherv(x, np.diff(self.cuts), self.cuts[:-1])
         else:
             A = self.A_fwd if enforced else self.A
             self.pcg.solve(self.row_ptr, self.col_idx, A, minv, rhs, x, dpn_hint=1,
