@@ -445,6 +445,11 @@ class Multigrid:
         st = dev._stream()
         lib = self.lib
         _lib.check(lib.sktb_mg_set_level0_range(self.handle, int(eng.node0), int(eng.dm.n_nodes)))
+        sh0 = getattr(eng, "slab", None)
+        if sh0 is not None:
+            _lib.check(lib.sktb_mg_set_level_slab(
+                self.handle, 0, int(eng.node0), int(eng.dm.n_nodes), int(sh0["plane"]),
+                int(sh0["prev"]), int(sh0["next"])))
         if eng.matrix_free:
             _lib.check(lib.sktb_mg_set_level0_grid(
                 self.handle, eng.gridop.handle, int(eng.node1 - eng.node0),
@@ -454,11 +459,6 @@ class Multigrid:
                 self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()),
                 int(eng.max_deg), dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc),
                 dev._ptr(eng.vals), dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
-        sh0 = getattr(eng, "slab", None)
-        if sh0 is not None:
-            _lib.check(lib.sktb_mg_set_level_slab(
-                self.handle, 0, int(eng.node0), int(eng.dm.n_nodes), int(sh0["plane"]),
-                int(sh0["prev"]), int(sh0["next"])))
         for l in range(1, self.n_levels):
             lv = self.levels[l]
             sh = self.shard[l]
