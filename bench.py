@@ -29,11 +29,13 @@ import numpy as np  # noqa: E402
 METRIC = "optimizer iters/sec on 1M-elem 3D cantilever; PCG SpMV HBM GB/s vs peak"
 UNIT = "iters/s"
 C2_MESH_SIZE = 0.0577          # toy_base(0.0577): 139x104x70 = 1,011,920 hex
-CPU_SAMPLE_MESH_SIZE = 0.2     # toy1_fine: 40x30x20 = 24,000 hex (largest mesh the reference defines)
+C5_MESH_SIZE = 0.0288          # toy_base(0.0288): 278x209x139 = 8,076,178 hex (BASELINE configs[4])
 
 
 def workload_name(mesh_size: float) -> str:
-    tag = "C2" if abs(mesh_size - C2_MESH_SIZE) < 1e-12 else "custom"
+    tag = ("C2" if abs(mesh_size - C2_MESH_SIZE) < 1e-12 else
+           "C5" if abs(mesh_size - C5_MESH_SIZE) < 1e-12 else
+           "C1" if abs(mesh_size - C1_MESH_SIZE) < 1e-12 else "custom")
     return "%s: 3D cantilever toy_base(%g), LogMOC, vol_frac 0.3" % (tag, mesh_size)
 
 
@@ -98,61 +100,138 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------- CPU legs --
-CPU_MAX_TIMED_STEPS = 3        # ~20 s each on the sample mesh: bounds the CPU legs
-CPU_MAX_WARMUP_STEPS = 1
+# The CPU side is the oracle's restatement of the reference path with its heavy
+# stages in C / OpenMP (oracle/cport: assembly, scipy-cg-semantics Jacobi PCG,
+# element energies) so that it runs the SAME mesh as the GPU arm on all host
+# cores -- nothing is extrapolated from a smaller mesh.  The Helmholtz systems
+# are solved by scipy cg (a sparse LU of a 1M-node 3-D system does not fit).
+C1_MESH_SIZE = 0.155           # toy_base(0.155): 52 x 39 x 26 = 52,728 hex (BASELINE configs[0])
+CPU_C2_BUDGET_S = 150.0        # stop starting new C2 steps after this long (>= 1 step always)
+CPU_C2_MAX_STEPS = 2
+C1_STEPS, C1_WARMUP = 3, 1
 
 
-def cpu_oracle_step_rate(steps: int, warmup: int, mesh_size: float):
-    """The oracle port of the reference path (NumPy/SciPy, scipy cg + Jacobi,
-    splu Helmholtz filter) running full LogMOC iterations on a bounded sample
-    mesh: at most CPU_MAX_WARMUP_STEPS untimed + CPU_MAX_TIMED_STEPS timed
-    iterations, whatever --steps / --warmup ask for, so that the run ends within
-    a few minutes.  Returns (iters/s on the sample, n_elem_sample, seconds per
-    step, timed steps)."""
-    from oracle import mesh as omesh, optim
+def cpu_port_run(mesh_size, method, max_iters, n_warm, n_timed, vol_frac, budget_s=None):
+    """Full optimiser iterations of the CPU port on toy_base(mesh_size).
+    Returns a dict with the measured seconds per step (mean over the timed
+    steps actually run), the step count, CG iterations and the thread count."""
+    from oracle import cport, mesh as omesh, optim
+    t0 = time.perf_counter()
     o = omesh.toy_base(mesh_size)
     pr = optim.Problem(o["p"], o["t"], o["dirichlet_dofs"], o["force"], o["design"],
                        o["pinned"], o["volumes"], o["E"], o["nu"], fixed=o["fixed"])
-    n_warm = max(0, min(int(warmup), CPU_MAX_WARMUP_STEPS))
-    n_timed = max(1, min(int(steps), CPU_MAX_TIMED_STEPS))
-    marks = []
-    optim.run(pr, "logmoc", max_iters=200, iters=n_warm + n_timed, vol_frac=0.3,
-              solver="cg_jacobi", rtol=1e-8, cg_maxiter=20000, step_times=marks)
-    dt = (marks[-1] - marks[n_warm]) / n_timed
-    return 1.0 / dt, int(o["t"].shape[1]), dt, n_timed
+    be = cport.CBackend(o["p"], o["t"], 3, cport.unit_elasticity_ke(o["p"], o["t"], o["nu"]),
+                        o["dirichlet_dofs"])
+    mats = cport.scalar_matrices(o["p"], o["t"])
+    setup_s = time.perf_counter() - t0
+    marks, tm = [], {}
+    res = optim.run(pr, method, max_iters=max_iters, iters=n_warm + n_timed, vol_frac=vol_frac,
+                    solver="cg_jacobi", rtol=1e-8, cg_maxiter=200000, backend=be,
+                    filter_solver="cg", filter_matrices=mats, step_times=marks, timings=tm,
+                    time_budget=budget_s)
+    done = len(marks) - 1
+    warm = min(n_warm, max(done - 1, 0))
+    timed = done - warm
+    dt = (marks[-1] - marks[warm]) / timed
+    return dict(s_per_step=dt, steps_timed=timed, warmup=warm, n_elem=int(o["t"].shape[1]),
+                cg_iters=[int(v) for v in res["cg_iters"]], threads=cport.num_threads(),
+                setup_s=setup_s, sections={k: round(v, 3) for k, v in tm.items()},
+                compliance=[float(v) for v in res["compliance"]])
+
+
+def cpu_sample_text(r, what):
+    return (f"{what}: {r['steps_timed']} timed step(s) after {r['warmup']} warm-up, "
+            f"{r['s_per_step']:.2f} s/step measured on this mesh (no extrapolation); oracle port "
+            f"with assembly / Jacobi-PCG (scipy cg semantics, rtol 1e-8, x0 = 0, "
+            f"{r['cg_iters'][-1]} iterations in the last solve) / element energies in C + OpenMP "
+            f"on {r['threads']} threads, Helmholtz filter by scipy cg, rest NumPy")
+
+
+def same_config_c1_cpu():
+    r = cpu_port_run(C1_MESH_SIZE, "oc", 50, C1_WARMUP, C1_STEPS, 0.8)
+    return {"cpu_ms_per_step": 1e3 * r["s_per_step"], "cpu_steps_timed": r["steps_timed"],
+            "cpu_threads": r["threads"], "cpu_cg_iters": r["cg_iters"],
+            "cpu_compliance": r["compliance"]}
+
+
+def bench_config(mesh_size, n_elem=None, n_dof=None):
+    """The `config` object, identical in both arms."""
+    return {"workload": workload_name(mesh_size), "mesh_size": mesh_size,
+            "method": "LogMOC, vol_frac 0.3, Helmholtz filter, 200-iteration schedules, "
+                      "rtol 1e-8, fp64",
+            "same_config_c1": "C1: toy_base(0.155) = 52,728 hex, OC defaults, 50-iteration "
+                              "schedules; %d timed steps after %d warm-up in both arms"
+                              % (C1_STEPS, C1_WARMUP)}
 
 
 def run_reference(args):
-    """--impl reference: the oracle port on the host cores (the reference itself
-    cannot be imported here: scikit-fem / pyamg are not installed)."""
+    """--impl reference: the reference path on the host cores.  The reference
+    itself cannot be imported (scikit-fem / pyamg are not installed, no network:
+    no baseline/_ref), so this is the oracle port (`kind: port`) -- on the SAME
+    mesh as the GPU arm, for as many steps as fit the time budget (at least one;
+    `steps` reports the steps actually timed, `steps_requested` the flag)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_c2 = 1011920
-    rate, n_s, dt, n_t = cpu_oracle_step_rate(args.steps, args.warmup, args.cpu_mesh_size)
-    value = rate * n_s / n_c2
-    sample = (f"oracle LogMOC iteration (scipy cg+Jacobi rtol 1e-8, splu Helmholtz filter) on "
-              f"toy_base({args.cpu_mesh_size}) = {n_s} hex ({dt:.2f} s/step, mean of {n_t} timed "
-              f"steps: the CPU leg is capped at {CPU_MAX_TIMED_STEPS}), scaled linearly in "
-              f"element count to {n_c2} hex (optimistic for the CPU: CG iterations also grow "
-              f"with mesh size); scipy is single-threaded")
+    n_timed = max(1, min(int(args.steps), CPU_C2_MAX_STEPS))
+    r = cpu_port_run(args.mesh_size, "logmoc", 200, 0, n_timed, 0.3, budget_s=CPU_C2_BUDGET_S)
+    value = 1.0 / r["s_per_step"]
+    sample = cpu_sample_text(r, workload_name(args.mesh_size))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+        "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": r["warmup"],
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * r["s_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.mesh_size), "n_elem": n_c2,
-                   "sample_mesh_size": args.cpu_mesh_size},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+        "config": bench_config(args.mesh_size),
+        "details": {"n_elem": r["n_elem"], "cg_iters_per_step": r["cg_iters"],
+                    "setup_s": r["setup_s"], "sections_s": r["sections"],
+                    "compliance": r["compliance"], "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_c1:
+        line["same_config_c1"] = same_config_c1_cpu()
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------- GPU arm --
+def _make_optimizer(sktopt, mesh_size, method="logmoc", max_iters=200):
+    tsk = sktopt.mesh.toy_problem.toy_base(mesh_size)
+    tmp = tempfile.mkdtemp(prefix="sktopt_bench_")
+    if method == "logmoc":
+        cfg = sktopt.core.LogMOC_Config(
+            dst_path=tmp, max_iters=max_iters, record_times=max(1, max_iters // 10),
+            vol_frac=sktopt.tools.SchedulerConfig.constant(target_value=0.3),
+            solver_option="cg_pyamg")
+        opt = sktopt.core.LogMOC_Optimizer(cfg, tsk)
+    else:
+        cfg = sktopt.core.OC_Config(dst_path=tmp, max_iters=max_iters, record_times=max_iters,
+                                    solver_option="cg_pyamg")
+        opt = sktopt.core.OC_Optimizer(cfg, tsk)
+    opt.parameterize()
+    opt.export_enabled = False
+    return opt
+
+
+def _timed_steps(torch, opt, steps, barrier):
+    """(seconds by CUDA events on the launch stream, wall seconds) of `steps`
+    optimiser iterations, barrier + synchronize on both sides."""
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        opt.optimize_steps(1)
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - w0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -172,16 +251,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    tsk = sktopt.mesh.toy_problem.toy_base(args.mesh_size)
-    tmp = tempfile.mkdtemp(prefix="sktopt_bench_")
-    cfg = sktopt.core.LogMOC_Config(
-        dst_path=tmp, max_iters=200, record_times=20,
-        vol_frac=sktopt.tools.SchedulerConfig.constant(target_value=0.3),
-        solver_option="cg_pyamg",
-    )
-    opt = sktopt.core.LogMOC_Optimizer(cfg, tsk)
-    opt.parameterize()
-    opt.export_enabled = False
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    opt = _make_optimizer(sktopt, args.mesh_size)
     eng = opt.fem.engine
     n_elem, n_dof, nnz = eng.n_elem, eng.n_dof, eng.nnz
 
@@ -210,21 +286,12 @@ def run_b200(args):
     # ---- timed region 1 (`value`): K steps, state resident in HBM, bracketed by
     # barrier + synchronize, timed on the device with CUDA events recorded on the
     # stream every kernel of the path is launched on (torch's current stream)
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
         sampler.start()
     launches0 = dev.launch_count()
-    w0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        opt.optimize_steps(1)
-    ev1.record()
-    barrier()
-    t_wall = time.perf_counter() - w0
+    t_step, t_wall = _timed_steps(torch, opt, args.steps, barrier)
     launches = dev.launch_count() - launches0
-    t_step = ev0.elapsed_time(ev1) * 1e-3
     spmv_ms_sum, spmv_n = eng.pcg.get_profile()
     pcg_iters = [l[0] for l in eng.pcg_log[n_solves0:]]
     eng.pcg.set_profile(0)
@@ -232,6 +299,8 @@ def run_b200(args):
     # ---- timed region 2 (`e2e`): the same K steps through the public API with
     # HOST buffers: H2D of rho from pinned memory, one optimiser step, D2H of the
     # new rho and the compliance, every step inside the timed region
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
     rho_h.copy_(st.rho)
     comp_last = None
     barrier()
@@ -250,14 +319,33 @@ def run_b200(args):
     t_e2e = max(ev0.elapsed_time(ev1) * 1e-3, t_e2e_wall)
     clocks = sampler.stop() if rank == 0 else None
 
-    times = torch.tensor([t_step, t_e2e, t_wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_step, t_e2e, t_wall = float(times[0]), float(times[1]), float(times[2])
-    # N > 1: the SAME workload, its elasticity operator row-sharded over the N
-    # GPUs (strong scaling); element-wise stages and the filter are replicated
+    t_step, t_e2e, t_wall = max_over_ranks([t_step, t_e2e, t_wall])
+    # N > 1: the SAME workload, z-slab-sharded over the N GPUs (strong scaling)
     value = args.steps / t_step
     e2e = args.steps / t_e2e
+
+    # ---- late stage (the hard regime): the same run continued to iteration
+    # `--late-iter` of its 200-iteration schedule (p = 3, beta = 2, a 0/1
+    # topology with modulus contrast 1e3), then K more timed steps
+    late = None
+    if args.late_iter > 0:
+        done = int(getattr(opt, "_iter_next", 1)) - 1
+        if args.late_iter > done:
+            opt.optimize_steps(args.late_iter - done)
+        n0 = len(eng.pcg_log)
+        t_l, _ = _timed_steps(torch, opt, args.late_steps, barrier)
+        (t_l,) = max_over_ranks([t_l])
+        its = [l[0] for l in eng.pcg_log[n0:]]
+        rp = st.rho_projected
+        late = {"first_iteration": args.late_iter + 1, "steps": args.late_steps,
+                "ms_per_step": 1e3 * t_l / args.late_steps,
+                "iters_per_s": args.late_steps / t_l, "pcg_iters_per_step": its,
+                "pcg_converged": bool(all(l[1] for l in eng.pcg_log[n0:])),
+                "p": float(opt.schedulers.values_as_list(
+                    args.late_iter + 1, ["p"], export_log=False, precision=6)[0]),
+                "rho_projected_below_0.1": float((rp < 0.1).double().mean()),
+                "rho_projected_above_0.9": float((rp > 0.9).double().mean()),
+                "compliance": float(st.compliance)}
 
     # ---- assembled-operator SpMV leg (north_star's "PCG SpMV HBM GB/s vs
     # peak"): K(rho) of the SAME mesh and the current density assembled by the
@@ -283,6 +371,67 @@ def run_b200(args):
         ts = sorted(a.elapsed_time(b) for a, b in evs)
         spmv_leg = {"mean_ms": float(np.mean(ts)), "median_ms": ts[len(ts) // 2], "reps": reps}
         del xs, ys
+        eng._pattern = None                      # free the 3 GB assembled operator again
+        torch.cuda.empty_cache()
+
+    details = {
+        "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
+        "solver": ("device PCG rtol 1e-8, start vector = Galerkin projection on the last "
+                   "%d solutions, operator: " % eng.start_hist
+                   + ("matrix-free grid stencil" if eng.matrix_free else "assembled node-block CSR")
+                   + ", preconditioner: "
+                   + ("geometric multigrid V-cycle (Galerkin coarse operators, damped Jacobi "
+                      "sweeps per level %s, exact dense coarsest solve, fp32 level-0 products)"
+                      % ",".join(str(v) for v in eng.mg.sweeps)
+                      if eng.precond == "mg" else "Jacobi")),
+        "pcg_iters_per_step": pcg_iters,
+        "l2": ("inputs larger than L2: one step streams the level-1 operator (0.27 GB) ~4x per PCG "
+               "iteration plus ~20 work vectors of 25 MB against the 126 MB L2; nothing is "
+               "flushed explicitly"),
+        "filter": ("Helmholtz: direct fast-diagonalisation solve (adjoint) + matrix-free PCG "
+                   "(forward, fixed nodes)" if world == 1 else
+                   "Helmholtz: z-slab-sharded matrix-free PCG, filtered field all-gathered"),
+        "parallelism": "single GPU" if world == 1 else (
+            f"z-slab sharding over {world} GPUs: matrix-free level 0, multigrid levels "
+            f"{[l for l, sh in enumerate(eng.mg.shard) if sh is not None] if eng.mg else []} "
+            f"and the Helmholtz filter PCG sharded (NCCL plane exchange + dot all-reduces); "
+            f"element-wise stages replicated"),
+        "rows_per_rank": int(eng.n_local), "halo_dofs": int(getattr(eng, "halo_dofs", 0)),
+        "last_compliance": comp_last,
+    }
+
+    # ---- same-config pair on C1 (52,728 hex, OC): a configuration BOTH arms
+    # complete, fully measured on both sides
+    c1 = None
+    if world == 1 and not args.no_c1:
+        o1 = _make_optimizer(sktopt, C1_MESH_SIZE, "oc", 50)
+        o1.optimize_steps(C1_WARMUP)
+        t1, _ = _timed_steps(torch, o1, C1_STEPS, barrier)
+        c1 = {"gpu_ms_per_step": 1e3 * t1 / C1_STEPS, "gpu_steps_timed": C1_STEPS,
+              "gpu_compliance": [float(v) for v in
+                                 np.asarray(o1.recorder.as_object().compliance)],
+              "gpu_bisection_steps": list(o1.bisection_steps),
+              "gpu_pcg_iters": [l[0] for l in o1.fem.engine.pcg_log]}
+        del o1
+
+    # ---- C5 (8.08M hex) under N > 1: the configuration the multi-GPU target is
+    # quoted on, a few steps next to the strong-scaling headline
+    c5 = None
+    if world > 1 and args.c5_steps > 0:
+        del opt, st
+        torch.cuda.empty_cache()
+        o5 = _make_optimizer(sktopt, C5_MESH_SIZE)
+        o5.optimize_steps(2)
+        n5 = len(o5.fem.engine.pcg_log)
+        t5, _ = _timed_steps(torch, o5, args.c5_steps, barrier)
+        (t5,) = max_over_ranks([t5])
+        e5 = o5.fem.engine
+        c5 = {"workload": workload_name(C5_MESH_SIZE), "n_elem": e5.n_elem, "n_dof": e5.n_dof,
+              "steps": args.c5_steps, "ms_per_step": 1e3 * t5 / args.c5_steps,
+              "iters_per_s": args.c5_steps / t5,
+              "pcg_iters_per_step": [l[0] for l in e5.pcg_log[n5:]],
+              "sharded_mg_levels": [l for l, sh in enumerate(e5.mg.shard) if sh is not None],
+              "compliance": float(o5._state.compliance)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -306,10 +455,10 @@ def run_b200(args):
             alg_bytes = n_loc_nodes * (24 + 24 + 24 + 1) + n_elem * 8
             roofline = {
                 "bound": "fp64",
-                "kernel": "hexgrid_apply_shfl_kernel<double,0,true> (matrix-free q = K(rho) p + p.q; the V-cycle runs two more per PCG iteration in fp32)",
+                "kernel": "hexgrid_apply kernel, fp64 + dot variant (matrix-free q = K(rho) p + p.q; the V-cycle runs two more per PCG iteration in fp32)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp64_peak) if achieved else None,
-                "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe); "
+                "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe, profiles/r2_fp64_probe.md); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "peak_const_operand": fp64_peak_const,
                 "frac_of_const_operand_peak": (achieved / fp64_peak_const) if achieved else None,
@@ -329,27 +478,13 @@ def run_b200(args):
             # SURVEY.md 8(d), for the rows this rank owns
             spmv_bytes = nnz * 12 + int(eng.n_local) * 12 + n_dof * 8
             achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_n else None
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-            if os.path.exists(tpath):
-                try:
-                    with open(tpath) as f:
-                        traffic = json.load(f).get("dram_bytes_per_launch")
-                except Exception:
-                    traffic = None
             roofline = {
                 "bound": "hbm", "kernel": "spmv_bsr3_tma_kernel<true> (PCG q=Ap + p.q, node-block columns, cp.async.bulk ring)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
                 "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
                 "peak_source": peak_src, "alg_bytes_per_launch": spmv_bytes,
-                "avg_launch_ms": spmv_ms, "samples": spmv_n,
-                "traffic": traffic if world == 1 else None,
-                "format_bytes_per_launch": nnz * 8 + (nnz // 9) * 4 + (int(eng.n_local) // 3) * 4
-                + int(eng.n_local) * 8 + n_dof * 8,
-                "note": "achieved uses SURVEY 8(d) CSR bytes (12 B/nnz); the kernel reads one int32 "
-                        "column per 3x3 block (8.44 B/nnz), so a value above the copy roofline is "
-                        "format compression, see traffic",
+                "avg_launch_ms": spmv_ms, "samples": spmv_n, "traffic": None,
             }
         if spmv_leg is not None:
             b_alg = nnz * 12 + n_dof * 12 + n_dof * 8          # SURVEY 8(d), CSR accounting
@@ -389,42 +524,32 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args.mesh_size),
-                "n_elem": n_elem, "n_dof": n_dof, "nnz": nnz,
-                "solver": ("device PCG rtol 1e-8, start vector = Galerkin projection on the last "
-                           "%d solutions, operator: " % eng.start_hist
-                           + ("matrix-free grid stencil" if eng.matrix_free else "assembled node-block CSR")
-                           + ", preconditioner: "
-                           + ("geometric multigrid V-cycle (Galerkin coarse operators, damped Jacobi "
-                              "sweeps per level %s, exact dense coarsest solve, fp32 level-0 products)"
-                              % ",".join(str(v) for v in eng.mg.sweeps)
-                              if eng.precond == "mg" else "Jacobi")),
-                "pcg_iters_per_step": pcg_iters,
-                "l2": ("inputs larger than L2: one step streams the level-1 operator (0.27 GB) ~4x per PCG "
-                       "iteration plus ~20 work vectors of 25 MB against the 126 MB L2; nothing is "
-                       "flushed explicitly"),
-                "filter": "Helmholtz: direct fast-diagonalisation solve (adjoint) + matrix-free PCG (forward, fixed nodes)",
-                "parallelism": "single GPU" if world == 1 else (
-                    f"elasticity operator row-sharded over {world} GPUs (NCCL halo exchange + "
-                    f"dot all-reduce); filter/element stages replicated"),
-                "rows_per_rank": int(eng.n_local), "halo_dofs": int(getattr(eng, "halo_dofs", 0)),
-                "last_compliance": comp_last,
-            },
+            "config": bench_config(args.mesh_size),
+            "details": details,
             "roofline": roofline,
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": n_elem * 8, "d2h_bytes_per_step": n_elem * 8 + 8},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if late is not None:
+            line["late_stage"] = late
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1 and not args.no_cpu:
-            rate, n_s, dt, _ = cpu_oracle_step_rate(1, 0, args.cpu_mesh_size)
+            # the true C2 workload on the host cores: ONE full step, measured
+            r = cpu_port_run(args.mesh_size, "logmoc", 200, 0, 1, 0.3)
             line["cpu_baseline"] = {
-                "value": rate * n_s / n_elem, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": (f"oracle LogMOC iteration on toy_base({args.cpu_mesh_size}) = {n_s} hex "
-                           f"({dt:.2f} s/step, scipy cg+Jacobi, splu filter), scaled linearly in "
-                           f"element count to {n_elem} hex (optimistic for the CPU)"),
-            }
+                "value": 1.0 / r["s_per_step"], "unit": UNIT, "cores": r["threads"],
+                "kind": "port", "sample": cpu_sample_text(r, workload_name(args.mesh_size)),
+                "sections_s": r["sections"], "host_cores": os.cpu_count()}
+            if c1 is not None:
+                c1.update(same_config_c1_cpu())
+                c1["speedup"] = c1["cpu_ms_per_step"] / c1["gpu_ms_per_step"]
+                gc, cc = np.asarray(c1["gpu_compliance"]), np.asarray(c1["cpu_compliance"])
+                c1["compliance_max_rel_diff"] = float(np.max(np.abs(gc - cc) / np.abs(cc)))
+        if c1 is not None:
+            line["same_config_c1"] = c1
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -437,9 +562,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh-size", type=float, default=C2_MESH_SIZE)
-    ap.add_argument("--cpu-mesh-size", type=float, default=CPU_SAMPLE_MESH_SIZE)
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-c1", action="store_true", help="skip the C1 same-config pair")
     ap.add_argument("--no-spmv-leg", action="store_true")
+    ap.add_argument("--late-iter", type=int, default=150,
+                    help="continue the run to this optimiser iteration and time --late-steps "
+                         "more there (0: skip)")
+    ap.add_argument("--late-steps", type=int, default=10)
+    ap.add_argument("--c5-steps", type=int, default=5,
+                    help="under --gpus N > 1: timed steps of the 8.08M-element C5 run (0: skip)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one extra step inside cudaProfilerStart/Stop before the timed region")
     args = ap.parse_args()

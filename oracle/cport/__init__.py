@@ -162,3 +162,21 @@ def unit_elasticity_ke(p, t, nu, intorder=2):
         out[s:s + 20000] = fem.elasticity_ke(p, sel[:, s:s + 20000], lam[s:s + 20000],
                                              mu[s:s + 20000], intorder)
     return out
+
+
+def scalar_matrices(p, t):
+    """(M, K) of the Helmholtz filter (mass and Laplace matrices of the scalar
+    P1/Q1 basis with skfem's default quadrature, filters/helmholtz_filter_nodal.py
+    :128,136-145) assembled by the C port; copies, so both stay valid."""
+    io = fem.default_intorder(t.shape[0])
+    x = p[:, t]
+    d = x - x[:, :1, :]
+    uniform = bool(np.all(np.abs(d - d[:, :, :1]) <= 1e-12 * np.abs(d).max()))
+    sel = t[:, :1] if uniform else t
+    out = []
+    for kind in ("mass", "laplace"):
+        Ke = np.concatenate([fem.scalar_ke(p, sel[:, s:s + 100000], io, kind)
+                             for s in range(0, sel.shape[1], 100000)])
+        be = CBackend(p, t, 1, Ke)
+        out.append(be.assemble(None, enforce=False).copy())
+    return tuple(out)

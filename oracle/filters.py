@@ -37,7 +37,8 @@ class HelmholtzOracle:
     The reference re-assembles and calls spsolve per application; the oracle
     factorises once per radius (same linear systems)."""
 
-    def __init__(self, p, t, volumes, design_mask=None, solver="splu", cg_rtol=1e-12):
+    def __init__(self, p, t, volumes, design_mask=None, solver="splu", cg_rtol=1e-12,
+                 matrices=None):
         """``solver='cg'``: the same linear systems solved by scipy cg + Jacobi at
         ``cg_rtol`` instead of a sparse LU (for meshes where the 3-D factorisation
         does not fit: the CPU baseline at BASELINE's full sizes)."""
@@ -45,8 +46,11 @@ class HelmholtzOracle:
         self.p, self.t, self.vol = p, t, volumes
         self.mask = None if design_mask is None else np.asarray(design_mask, bool)
         io = fem.default_intorder(t.shape[0])
-        self.M = fem.assemble_scalar(p, t, None, io, "mass")
-        self.K = fem.assemble_scalar(p, t, None, io, "laplace")
+        if matrices is not None:      # (M, K) assembled elsewhere (oracle.cport at full size)
+            self.M, self.K = matrices
+        else:
+            self.M = fem.assemble_scalar(p, t, None, io, "mass")
+            self.K = fem.assemble_scalar(p, t, None, io, "laplace")
         n = p.shape[1]
         if self.mask is None:
             self.fixed = np.array([], dtype=np.int64)

@@ -134,7 +134,7 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
         solver="spsolve", rtol=1e-8, cg_maxiter=None, lambda_lower=1e-7,
         lambda_upper=1e7, logmoc=None, iters=None, timings=None, step_times=None,
         interpolation="SIMP", sensitivity_filter=False, backend=None,
-        filter_solver="splu", time_budget=None):
+        filter_solver="splu", time_budget=None, filter_matrices=None):
     """DensityMethod._optimize_impl (common_density.py:1014-1134) with the
     default schedules of DensityMethodConfig / OC_Config / LogMOC_Config.
     Returns dict(rho, compliance[], vol_error[], rho_hist[]).
@@ -152,7 +152,8 @@ def run(problem: Problem, method="oc", max_iters=5, filter_type="helmholtz",
     interp, dC_drho = {"SIMP": (fem.simp, dC_drho_simp),
                        "RAMP": (fem.ramp, dC_drho_ramp)}[interpolation]
     if filter_type == "helmholtz":
-        filt = HelmholtzOracle(pr.p, pr.t, pr.vol, pr.design_mask, solver=filter_solver)
+        filt = HelmholtzOracle(pr.p, pr.t, pr.vol, pr.design_mask, solver=filter_solver,
+                               matrices=filter_matrices)
     else:
         filt = SpatialOracle(pr.p, pr.t, pr.design_mask)
     filt.set_radius(filter_radius)

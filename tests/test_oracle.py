@@ -264,3 +264,40 @@ def test_toy2_and_config_defaults():
     assert lm.eta == 0.6 and lm.lambda_lower == -1e7 and lm.mu_p == 5.0
     with pytest.raises(RuntimeError):
         sktopt.core.OC_Config(solver_option="petsc")
+
+
+def test_c_port_matches_the_numpy_oracle():
+    """oracle/cport (C / OpenMP: the CPU baseline at full size) against the
+    NumPy / SciPy restatement: same pattern, K to 1e-14, the same PCG iterates,
+    element energies to 1e-12, and a 3-iteration LogMOC loop to 1e-10."""
+    from oracle import cport, fem, mesh as omesh, optim
+    o = omesh.toy_base(0.8)
+    be = cport.CBackend(o["p"], o["t"], 3, cport.unit_elasticity_ke(o["p"], o["t"], o["nu"]),
+                        o["dirichlet_dofs"])
+    rho = np.random.default_rng(0).uniform(0.1, 1.0, o["t"].shape[1])
+    E = fem.simp(rho, 210e3, 210.0, 3.0)
+    K1 = be.assemble(E)
+    K = fem.assemble_stiffness(o["p"], o["t"], rho, 210e3, 210.0, 3.0, 0.3)
+    K2, _ = fem.enforce(K, o["force"], o["dirichlet_dofs"])
+    assert np.array_equal(K1.indptr, K2.indptr) and np.array_equal(K1.indices, K2.indices)
+    assert np.abs(K1.data - K2.data).max() <= 1e-14 * np.abs(K2.data).max()
+    F = o["force"].copy()
+    F[o["dirichlet_dofs"]] = 0.0
+    u1, it1, rel = be.pcg(F, 1e-8)
+    u2, _, it2 = fem.solve(K2, F, "cg_jacobi", 1e-8)
+    assert abs(it1 - it2) <= 1 and rel <= 1e-8
+    assert np.abs(u1 - u2).max() <= 1e-7 * np.abs(u2).max()
+    e1 = be.energy(E, u2)
+    e2 = fem.strain_energy(o["p"], o["t"], rho, u2, 210e3, 210.0, 3.0, 0.3)[:, 0]
+    assert np.abs(e1 - e2).max() <= 1e-12 * np.abs(e2).max()
+    M, Ks = cport.scalar_matrices(o["p"], o["t"])
+    M2 = fem.assemble_scalar(o["p"], o["t"], None, 6, "mass")
+    assert abs(M - M2).max() <= 1e-14 * abs(M2).max()
+    pr = optim.Problem(o["p"], o["t"], o["dirichlet_dofs"], o["force"], o["design"],
+                       o["pinned"], o["volumes"], o["E"], o["nu"], fixed=o["fixed"])
+    a = optim.run(pr, "logmoc", max_iters=200, iters=3, vol_frac=0.3, solver="cg_jacobi")
+    b = optim.run(pr, "logmoc", max_iters=200, iters=3, vol_frac=0.3, solver="cg_jacobi",
+                  backend=be, filter_solver="cg", filter_matrices=(M, Ks))
+    ca, cb = np.array(a["compliance"]), np.array(b["compliance"])
+    assert np.abs(ca - cb).max() <= 1e-10 * np.abs(ca).max()
+    assert np.abs(a["rho_final"] - b["rho_final"]).max() <= 1e-9
