@@ -114,14 +114,20 @@ class _HelmholtzDevice:
         # z-slab-sharded PCG (halo planes + dot all-reduces, csrc/pcg.cu), every
         # rank then holds the whole filtered field again (all-gather), so the
         # cheap element <-> node gathers stay replicated and all ranks see
-        # bit-identical densities.  The direct (fast-diagonalisation) solve is a
-        # replicated stage and is only kept on one GPU.
+        # bit-identical densities.  Systems without fixed nodes keep the direct
+        # (fast-diagonalisation) solve, replicated on every rank.
         self.comm = None
         self.lo, self.hi = 0, n
         comm = bdist.default_comm()
+        # a sharded solve pays ~3 collectives per PCG iteration: only worth it when
+        # a rank's slab is large (SKTOPT_B200_FILTER_SHARD_MIN nodes per rank,
+        # default 750k: C5 on up to 8 GPUs yes, C2 no); SKTOPT_B200_FILTER_SHARD=1
+        # forces it, =0 forbids it
+        want = os.environ.get("SKTOPT_B200_FILTER_SHARD", "auto")
+        per_rank_min = int(os.environ.get("SKTOPT_B200_FILTER_SHARD_MIN", "750000"))
         if (comm is not None and self.grid is not None
-                and self.grid["np_axes"][2] >= 2 * comm.world
-                and os.environ.get("SKTOPT_B200_FILTER_SHARD", "1") != "0"):
+                and self.grid["np_axes"][2] >= 2 * comm.world and want != "0"
+                and (want == "1" or n // comm.world >= per_rank_min)):
             npx, npy, npz = (int(v) for v in self.grid["np_axes"])
             plane = npx * npy
             cuts = bdist.partition_planes(npz, comm.world) * plane
@@ -134,7 +140,8 @@ class _HelmholtzDevice:
                                      halo=empty)
             self.pcg.set_slab_halo(plane, r - 1 if r > 0 else -1,
                                    r + 1 if r < comm.world - 1 else -1)
-            self.fd = None
+            # (the direct fast-diagonalisation solve of the systems without fixed
+            # nodes stays: replicated it costs 1.7 ms at C5, the sharded PCG 4.6)
         else:
             self.pcg = dev.PcgSolver(n)
         self.radius = None

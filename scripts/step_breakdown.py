@@ -7,6 +7,13 @@ sys.path.insert(0, os.path.join(ROOT, "scikit-topt_b200"))
 import sktopt
 from sktopt._b200 import device as dev
 
+# under torchrun: one rank per GPU, sharded run (rank 0 prints)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+if world > 1:
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 h = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0577
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "logmoc"
@@ -35,8 +42,14 @@ for _ in range(n):
     torch.cuda.synchronize()
     per_step.append(round(1e3 * (time.perf_counter() - ts), 2))
 dt = (time.perf_counter() - t0) / n
+if rank != 0:
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    sys.exit(0)
 print("per-step ms", per_step)
 print("ms/step", dt * 1e3)
 for s in opt.timer.summary():
     print(f"{s.name:60s} {s.total/n*1e3:9.2f} ms/step  n={s.count//n}")
 print("pcg", opt.fem.engine.pcg_log[-n:], "filter iters", opt.filter._dev_state.solve_iters[-8:])
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

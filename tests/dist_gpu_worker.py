@@ -67,12 +67,14 @@ def main():
 
     # sharded Helmholtz filter (PCG on z-slabs) against the replicated one
     os.environ["SKTOPT_B200_FILTER_SHARD"] = "1"
+    os.environ["SKTOPT_B200_HELMHOLTZ_FD"] = "0"      # adjoint system through the sharded PCG too
     F = sktopt.filters.HelmholtzFilterNodal.from_defaults
     dmask = tsk.design_mask
     f_sh = F(tsk.mesh, tsk.elements_volume, 0.4, dmask)
     y_sh, g_sh = f_sh.forward(rho), f_sh.gradient(-rho)
     filter_sharded = f_sh._device().comm is not None
     os.environ["SKTOPT_B200_FILTER_SHARD"] = "0"
+    os.environ.pop("SKTOPT_B200_HELMHOLTZ_FD")
     f_re = F(tsk.mesh, tsk.elements_volume, 0.4, dmask)
     y_re, g_re = f_re.forward(rho), f_re.gradient(-rho)
     os.environ["SKTOPT_B200_FILTER_SHARD"] = "1"
