@@ -269,6 +269,33 @@ int sktb_elem_combine_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
                             const int32_t *child, const uint8_t *ptype,
                             const double *T, const int32_t *cls, const double *scale,
                             double *out, void *stream);
+/* ---- scalar multigrid on tensor grids (heat conduction: the reference's sparse
+ * LU of K, fea/solver_heat.py:191-192, becomes an MG-preconditioned PCG).  The
+ * operators are kept in a 27-point stencil ("DIA") format, vals[k][node] with
+ * k = 9 (dz+1) + 3 (dx+1) + (dy+1): level 0 is converted from the caller's
+ * enforced CSR matrix (conduction + Robin terms), the coarse operators are the
+ * algebraic Galerkin products P^T A P with trilinear P.  np_h: nodes per axis
+ * (x, y, z) of every level, [n_levels][3]; the coarsest level (<= 160 nodes) is
+ * solved exactly.  Transfer tables as in sktb_mg_set_transfer; mask = per-node
+ * uint8 of fixed (Dirichlet) nodes per level (device, caller-owned, may be NULL). */
+typedef struct sktb_smg sktb_smg;
+int sktb_smg_create(sktb_smg **out, int n_levels, const int32_t *np_h, int device);
+void sktb_smg_destroy(sktb_smg *m);
+int sktb_smg_set_mask(sktb_smg *m, int level, const uint8_t *mask);
+int sktb_smg_set_level_sweeps(sktb_smg *m, int level, int nu);
+int sktb_smg_set_transfer(sktb_smg *m, int level, const int32_t *ax_c0,
+                          const int32_t *ax_c1, const double *ax_w0,
+                          const double *ax_w1, const int32_t *axT_f,
+                          const double *axT_w);
+int sktb_smg_setup_csr(sktb_smg *m, const int32_t *row_ptr, const int32_t *col_idx,
+                       const double *vals, void *stream);
+int sktb_smg_vcycle(sktb_smg *m, const double *r, double *z, void *stream);
+/* y = A_level x and a copy of a level's 27 x n stencil values (tests)           */
+int sktb_smg_apply(sktb_smg *m, int level, const double *x, double *y, void *stream);
+int sktb_smg_level_values(sktb_smg *m, int level, double *out27n, void *stream);
+int sktb_pcg_solve_smg(sktb_pcg *s, sktb_smg *smg, const double *b, double *x,
+                       int use_x0, double rtol, int maxiter, int check_every,
+                       int32_t *info_h, double *relres_h, void *stream);
 /* PCG preconditioned by the V-cycle (level 0 may be row-sharded)               */
 int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg, const int32_t *node_ptr,
                            const int32_t *node_col, int64_t n_blocks,

@@ -27,7 +27,7 @@ using namespace sktb;
 
 namespace {
 
-constexpr int kDenseMaxS = 192;  // coarsest level: dense inverse up to this many nodes
+constexpr int kDenseMaxS = 160;  // coarsest level: dense inverse up to this many nodes
 
 struct SLevel {
   int np[3] = {0, 0, 0};  // nodes per axis (x, y, z)

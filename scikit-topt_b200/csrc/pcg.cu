@@ -339,9 +339,28 @@ static int reduce_scalars(sktb_pcg *s, double *loc, double *glob, int count,
   return comm_allreduce_sum(s->comm, loc, glob, count, st);
 }
 
+// scalar stencil multigrid (mg_scalar.cu)
+struct sktb_smg;
+int smg_vcycle(sktb_smg *m, const double *r, double *z, cudaStream_t st);
+int smg_apply_level0(const sktb_smg *m, const double *x, double *y, const double *dotv,
+                     ReduceScratch *rs, double *dot_out, const PcgScalars *S, cudaStream_t st);
+int64_t smg_n(const sktb_smg *m);
+const double *smg_inv_diag(const sktb_smg *m);
+
+// preconditioner handed to the solver: the elasticity V-cycle or the scalar one
+struct PcgPrecond {
+  sktb_mg *mg = nullptr;
+  sktb_smg *smg = nullptr;
+  explicit operator bool() const { return mg || smg; }
+  int apply(const double *r, double *z, cudaStream_t st, sktb_pcg *dist) const {
+    return mg ? mg_vcycle(mg, r, z, st, dist) : smg_vcycle(smg, r, z, st);
+  }
+};
+
 // matrix handed to the solver: CSR (kind 0), node-block CSR for 3 dofs per
-// node (kind 1: rp/ci index node blocks, vals keep the CSR layout) or the
-// matrix-free grid operator (kind 2)
+// node (kind 1: rp/ci index node blocks, vals keep the CSR layout), the
+// matrix-free grid operator (kind 2) or the 27-point stencil format of the
+// scalar multigrid's level 0 (kind 3)
 struct PcgMat {
   int kind;
   int dpn_hint;
@@ -352,11 +371,13 @@ struct PcgMat {
   int max_deg = 0;       // kind 1: largest number of blocks in a node row
   const sktb_gridop *gop = nullptr;  // kind 2
   int64_t node0 = 0;                 // kind 2: first owned node
+  const sktb_smg *smg = nullptr;     // kind 3
 };
 
 static int apply_mat(const PcgMat &A, int64_t n, const double *x, double *y,
                      const double *dotv, ReduceScratch *rs, double *dot_out,
                      const PcgScalars *S, cudaStream_t st) {
+  if (A.kind == 3) return smg_apply_level0(A.smg, x, y, dotv, rs, dot_out, S, st);
   if (A.kind == 2)
     return launch_hexgrid_apply(A.gop, A.node0, n / gridop_dpn(A.gop), x, y, dotv, rs,
                                 dot_out, S, st);
@@ -393,10 +414,11 @@ __global__ void __launch_bounds__(kBlock)
 static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                    const double *b, double *x, int use_x0, double rtol,
                    int maxiter, int check_every, int32_t *info_h,
-                   double *relres_h, void *stream, sktb_mg *mg = nullptr) {
+                   double *relres_h, void *stream, PcgPrecond mg = PcgPrecond()) {
 
   SKTB_REQUIRE(s && inv_diag && b && x, "null argument");
-  SKTB_REQUIRE(A.kind == 2 ? gridop_ready(A.gop) : (A.rp && A.ci && A.vals),
+  SKTB_REQUIRE(A.kind == 3 ? A.smg != nullptr
+                           : A.kind == 2 ? gridop_ready(A.gop) : (A.rp && A.ci && A.vals),
                "null argument");
   SKTB_REQUIRE(maxiter >= 0, "maxiter must be >= 0");
   if (check_every <= 0) check_every = 32;
@@ -424,7 +446,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
   if (reduce_scalars(s, &s->Sloc->rz, &s->S->rz, 6, st)) return 1;
   if (mg) {
     // z = M^-1 r by one V-cycle; p = z; rz = r.z
-    if (mg_vcycle(mg, s->r, s->z, st, s)) return 1;
+    if (mg.apply(s->r, s->z, st, s)) return 1;
     SKTB_CUDA_OK(cudaMemcpyAsync(p_own, s->z, sizeof(double) * n,
                                  cudaMemcpyDeviceToDevice, st));
     pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 1, s->partials,
@@ -479,7 +501,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
         // one all-reduce for (r.z, ||r||^2) after the V-cycle instead of one on
         // each side of it: until then the kernels of the V-cycle see the previous
         // ||r||^2, so at worst the converging iteration runs one idle V-cycle
-        if (mg_vcycle(mg, s->r, s->z, st, s)) return 1;
+        if (mg.apply(s->r, s->z, st, s)) return 1;
         pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 0, s->partials,
                                                s->ticket, s->Sloc, s->S);
         SKTB_COUNT(1);
@@ -537,8 +559,10 @@ extern "C" int sktb_pcg_solve_bsr3_mg(sktb_pcg *s, sktb_mg *mg,
                                       void *stream) {
   SKTB_REQUIRE(s && mg && s->n % 3 == 0, "block solve needs 3 dofs per node");
   PcgMat A{1, 3, node_ptr, node_col, vals, n_blocks, max_deg};
+  PcgPrecond pc;
+  pc.mg = mg;
   return pcg_run(s, A, inv_diag, b, x, use_x0, rtol, maxiter, check_every,
-                 info_h, relres_h, stream, mg);
+                 info_h, relres_h, stream, pc);
 }
 
 // ------------------------------------------------ spectral radius estimate --
@@ -642,8 +666,25 @@ extern "C" int sktb_pcg_solve_grid(sktb_pcg *s, sktb_mg *mg,
   SKTB_REQUIRE(s->n % gridop_dpn(op) == 0 && s->row0 % gridop_dpn(op) == 0,
                "row range is not a whole number of nodes");
   SKTB_REQUIRE(!mg || gridop_dpn(op) == 3, "multigrid needs the 3-dof operator");
+  PcgPrecond pc;
+  pc.mg = mg;
   return pcg_run(s, grid_mat(s, op), inv_diag, b, x, use_x0, rtol, maxiter,
-                 check_every, info_h, relres_h, stream, mg);
+                 check_every, info_h, relres_h, stream, pc);
+}
+
+// PCG on the scalar stencil operator (level 0 of `smg`, set up from the enforced
+// CSR matrix by sktb_smg_setup_csr) preconditioned by its V-cycle
+extern "C" int sktb_pcg_solve_smg(sktb_pcg *s, sktb_smg *smg, const double *b, double *x,
+                                  int use_x0, double rtol, int maxiter, int check_every,
+                                  int32_t *info_h, double *relres_h, void *stream) {
+  SKTB_REQUIRE(s && smg && !s->comm, "bad argument (the scalar multigrid runs on one GPU)");
+  SKTB_REQUIRE(s->n == smg_n(smg), "workspace and multigrid sizes differ");
+  PcgMat A{3, 1, nullptr, nullptr, nullptr};
+  A.smg = smg;
+  PcgPrecond pc;
+  pc.smg = smg;
+  return pcg_run(s, A, smg_inv_diag(smg), b, x, use_x0, rtol, maxiter, check_every, info_h,
+                 relres_h, stream, pc);
 }
 
 extern "C" int sktb_pcg_lambda_max_grid(sktb_pcg *s, const sktb_gridop *op,

@@ -528,6 +528,21 @@ class PcgSolver:
         self.total_iters += self.last_iters
         return x
 
+    def solve_smg(self, smg, b, x, rtol=1e-8, maxiter=300, use_x0=False, check_every=2):
+        """PCG on the scalar stencil operator of ``smg`` (``ScalarMultigrid``, set up
+        from the enforced CSR matrix), preconditioned by its V-cycle."""
+        info = (C.c_int32 * 2)()
+        relres = C.c_double()
+        _lib.check(self.lib.sktb_pcg_solve_smg(
+            self.handle, smg.handle, _ptr(b), _ptr(x), int(bool(use_x0)), float(rtol),
+            int(maxiter), int(check_every), C.cast(info, C.c_void_p),
+            C.cast(C.byref(relres), C.c_void_p), _stream()))
+        self.last_iters = int(info[0])
+        self.last_converged = bool(info[1])
+        self.last_relres = float(relres.value)
+        self.total_iters += self.last_iters
+        return x
+
     def solve_grid(self, gridop, inv_diag, b, x, rtol=1e-8, maxiter=1000, use_x0=False,
                    check_every=32, mg=None):
         """PCG on the matrix-free grid operator (``GridOp``)."""

@@ -54,6 +54,16 @@ SIGNATURES = {
     "sktb_elem_restrict_range": [i64, i64, i64, i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_combine_range": [i64, i64, i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_set_slab_halo": [C.c_void_p, i64, i32, i32],
+    "sktb_smg_create": [C.POINTER(C.c_void_p), i32, C.c_void_p, i32],
+    "sktb_smg_destroy": [C.c_void_p],
+    "sktb_smg_set_mask": [C.c_void_p, i32, c_u8p],
+    "sktb_smg_set_level_sweeps": [C.c_void_p, i32, i32],
+    "sktb_smg_set_transfer": [C.c_void_p, i32, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
+    "sktb_smg_setup_csr": [C.c_void_p, c_i32p, c_i32p, c_f64p, c_stream],
+    "sktb_smg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
+    "sktb_smg_apply": [C.c_void_p, i32, c_f64p, c_f64p, c_stream],
+    "sktb_smg_level_values": [C.c_void_p, i32, c_f64p, c_stream],
+    "sktb_pcg_solve_smg": [C.c_void_p, C.c_void_p, c_f64p, c_f64p, i32, f64, i32, i32, C.c_void_p, C.c_void_p, c_stream],
     "sktb_mg_set_transfer": [C.c_void_p, i32, C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p],
     "sktb_mg_vcycle": [C.c_void_p, c_f64p, c_f64p, c_stream],
     "sktb_gridop_create": [C.POINTER(C.c_void_p), i32, C.c_void_p, C.c_void_p, i32],
@@ -129,6 +139,7 @@ _RESTYPE = {
     "sktb_pcg_destroy": None,
     "sktb_comm_destroy": None,
     "sktb_mg_destroy": None,
+    "sktb_smg_destroy": None,
     "sktb_mesh_node_nnz": C.c_int64,
     "sktb_launch_count": C.c_int64,
 }

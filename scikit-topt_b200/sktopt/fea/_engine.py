@@ -127,7 +127,17 @@ class FeaEngine:
                     self.precond = "mg"
                 except ValueError:
                     self.mg = None
-        if want == "mg" and self.mg is None:
+        # scalar problems (heat): stencil multigrid on tensor grids, one GPU
+        self.smg = None
+        if (dpn == 1 and want != "jacobi" and self.axes is not None and comm is None):
+            from sktopt.fea._multigrid import ScalarMultigrid
+            if dm.n_nodes >= ScalarMultigrid.MIN_FINE_NODES or want == "mg":
+                try:
+                    self.smg = ScalarMultigrid(self, self.axes)
+                    self.precond = "mg"
+                except ValueError:
+                    self.smg = None
+        if want == "mg" and self.mg is None and self.smg is None:
             raise RuntimeError("multigrid preconditioner requested but the mesh is not an "
                                "eligible tensor hexahedral grid (or the run is sharded)")
         self.u = {}  # load index -> device solution (warm start), full length
@@ -217,6 +227,8 @@ class FeaEngine:
                               node0=self.node0)
         else:
             dev.csr_inv_diag(self.row_ptr, self.col_idx, v, out=self.inv_diag, row0=self.row0)
+            if self.smg is not None and self.mg_enabled:
+                self.smg.setup(self.row_ptr, self.col_idx, v)
         if self.mg is not None and self.mg_enabled and vals is None:
             self.mg.setup()
 
@@ -302,6 +314,14 @@ class FeaEngine:
                 self.pcg.solve_grid(self.gridop, self.inv_diag, rhs[lo:hi], x[lo:hi], rtol=rtol,
                                     maxiter=mi, use_x0=True, check_every=32)
             return self._finish_solve(x, rtol)
+        if self.smg is not None and self.mg_enabled and self.smg.setup_count > 0:
+            # scalar stencil multigrid (the operator is the one handed to the last
+            # update_preconditioner call); Jacobi-PCG finishes if it stalls
+            self.pcg.solve_smg(self.smg, rhs[lo:hi], x[lo:hi], rtol=rtol, maxiter=min(mi, 300),
+                               use_x0=self.warm_start, check_every=2)
+            if self.pcg.last_converged:
+                return self._finish_solve(x, rtol)
+            logger.warning("scalar multigrid PCG did not converge; continuing with Jacobi PCG")
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,

@@ -505,3 +505,104 @@ class Multigrid:
             z = torch.empty_like(r)
         _lib.check(self.lib.sktb_mg_vcycle(self.handle, dev._ptr(r), dev._ptr(z), dev._stream()))
         return z
+
+
+class ScalarMultigrid:
+    """Geometric multigrid for a scalar operator on a tensor hexahedral grid
+    (``csrc/mg_scalar.cu``): stands in for the reference's sparse LU of the heat
+    system (``fea/solver_heat.py:191-192``) as the preconditioner of the device
+    PCG.  The level-0 operator is whatever enforced CSR matrix the caller
+    assembled (conduction + real and virtual Robin terms); the coarse operators
+    are its algebraic Galerkin products, rebuilt by ``setup`` whenever it changes."""
+
+    MIN_FINE_NODES = 3000
+    DENSE_MAX_NODES = 160
+
+    def __init__(self, engine, axes):
+        self.lib = _lib.load()
+        self.eng = engine
+        coords = [tuple(axes)]
+        while True:
+            cells = [c.size - 1 for c in coords[-1]]
+            n = int(np.prod([c.size for c in coords[-1]]))
+            if n <= self.DENSE_MAX_NODES or max(cells) <= 1:
+                break
+            coords.append(tuple(a[coarse_index_map(a.size - 1)] for a in coords[-1]))
+        if len(coords) < 2 or int(np.prod([c.size for c in coords[-1]])) > self.DENSE_MAX_NODES:
+            raise ValueError("grid not suited to the scalar multigrid hierarchy")
+        self.coords = coords
+        self.n_levels = len(coords)
+        np_h = np.ascontiguousarray([[c.size for c in lv] for lv in coords], dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(self.lib.sktb_smg_create(C.byref(h), self.n_levels,
+                                            np_h.ctypes.data_as(C.c_void_p),
+                                            torch.cuda.current_device()))
+        self.handle = h
+        self.np_h = np_h
+        self._keep = []
+        mask = engine.dir_mask.cpu().numpy().astype(np.uint8)
+        for l in range(self.n_levels):
+            m_d = dev.to_dev(mask, dev.U8)
+            self._keep.append(m_d)
+            _lib.check(self.lib.sktb_smg_set_mask(h, l, dev._ptr(m_d)))
+            if l + 1 == self.n_levels:
+                break
+            fine_cells = [c.size - 1 for c in coords[l]]
+            coarse_np = [c.size for c in coords[l + 1]]
+            tabs = [axis_tables(n) for n in fine_cells]
+            cat = lambda k, dt: np.ascontiguousarray(np.concatenate([t[k] for t in tabs]).astype(dt))
+            catT = lambda k, dt: np.ascontiguousarray(
+                np.concatenate([t[k] for t in tabs], axis=1).astype(dt))
+            tr = [dev.to_dev(cat(0, np.int32), dev.I32), dev.to_dev(cat(1, np.int32), dev.I32),
+                  dev.to_dev(cat(2, np.float64)), dev.to_dev(cat(3, np.float64)),
+                  dev.to_dev(catT(4, np.int32).ravel(), dev.I32),
+                  dev.to_dev(catT(5, np.float64).ravel())]
+            self._keep.append(tr)
+            _lib.check(self.lib.sktb_smg_set_transfer(h, l, *[dev._ptr(t) for t in tr]))
+            # coarse node fixed iff the coincident fine node is
+            fm = [coarse_index_map(n) for n in fine_cells]
+            npx_f, npy_f = fine_cells[0] + 1, fine_cells[1] + 1
+            Iz, Ix, Iy = np.meshgrid(np.arange(coarse_np[2]), np.arange(coarse_np[0]),
+                                     np.arange(coarse_np[1]), indexing="ij")
+            fnode = (fm[1][Iy] + npy_f * fm[0][Ix] + npy_f * npx_f * fm[2][Iz]).ravel()
+            mask = mask[fnode].copy()
+        sweeps = os.environ.get("SKTOPT_B200_SMG_SWEEPS")
+        if sweeps:
+            sw = [int(v) for v in sweeps.split(",")]
+            for l in range(self.n_levels):
+                _lib.check(self.lib.sktb_smg_set_level_sweeps(h, l, sw[min(l, len(sw) - 1)]))
+        self.setup_count = 0
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_smg_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def setup(self, row_ptr, col_idx, vals):
+        _lib.check(self.lib.sktb_smg_setup_csr(self.handle, dev._ptr(row_ptr), dev._ptr(col_idx),
+                                               dev._ptr(vals), dev._stream()))
+        self.setup_count += 1
+
+    def vcycle(self, r, z=None):
+        if z is None:
+            z = torch.empty_like(r)
+        _lib.check(self.lib.sktb_smg_vcycle(self.handle, dev._ptr(r), dev._ptr(z), dev._stream()))
+        return z
+
+    def apply(self, level, x):
+        n = int(np.prod(self.np_h[level]))
+        y = torch.empty(n, dtype=dev.F64, device="cuda")
+        _lib.check(self.lib.sktb_smg_apply(self.handle, int(level), dev._ptr(x), dev._ptr(y),
+                                           dev._stream()))
+        return y
+
+    def level_values(self, level):
+        n = int(np.prod(self.np_h[level]))
+        out = torch.empty((27, n), dtype=dev.F64, device="cuda")
+        _lib.check(self.lib.sktb_smg_level_values(self.handle, int(level), dev._ptr(out),
+                                                  dev._stream()))
+        return out
