@@ -555,6 +555,73 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_workload(args):
+    """--workload c3 | c4: BASELINE configs 3 and 4 at their named sizes (not the
+    headline: a separate JSON line with iters/s, PCG iterations and the SpMV rate)."""
+    import torch
+    import sktopt
+    from sktopt._b200 import device as dev
+    from scripts import workloads
+    torch.cuda.set_device(0)
+    t0 = time.perf_counter()
+    if args.workload == "c3":
+        tsk = workloads.c3_task(sktopt)
+        name = ("C3: 500,610 Kuhn tets (55x41x37 cells, jittered), 2 load cases, mean compliance, "
+                "OC defaults, 50-iteration schedules")
+    else:
+        tsk = workloads.c4_task(sktopt)
+        name = ("C4: heat conduction 253x253x32 = 2,048,288 hex, thermal compliance, Robin + "
+                "virtual Robin, OC defaults, 50-iteration schedules, intorder 2")
+    tmp = tempfile.mkdtemp(prefix="sktopt_bench_")
+    cfg = sktopt.core.OC_Config(dst_path=tmp, max_iters=50, record_times=50,
+                                solver_option="cg_pyamg")
+    opt = sktopt.core.OC_Optimizer(cfg, tsk)
+    opt.parameterize()
+    opt.export_enabled = False
+    setup_s = time.perf_counter() - t0
+    eng = opt.fem.engine
+    opt.optimize_steps(args.warmup)
+    eng.pcg.set_profile(1)
+    n0 = len(eng.pcg_log)
+    launches0 = dev.launch_count()
+    t, wall = _timed_steps(torch, opt, args.steps, torch.cuda.synchronize)
+    launches = dev.launch_count() - launches0
+    ms_sum, n_s = eng.pcg.get_profile()
+    peak, peak_src = measured_peak()
+    nnz = eng.nnz
+    if eng.smg is not None:
+        op_bytes = eng.n_dof * (27 * 8 + 8 + 8)        # stencil format: 27 values / row + x + y
+        kernel = "dia_apply_kernel<0,true> (27-point stencil format, q = A p + p.q)"
+    elif eng.dpn == 3:
+        op_bytes = nnz * 8 + (nnz // 9) * 4 + eng.n_dof * 16 + (eng.n_dof // 3) * 4
+        kernel = "spmv_bsr3_tma_kernel<true> (node-block columns; operand %.0f MB, L2 resident " \
+                 "below 126 MB)" % (op_bytes / 1e6)
+    else:
+        op_bytes = nnz * 12 + eng.n_dof * 20
+        kernel = "spmv_kernel (scalar CSR)"
+    ms = ms_sum / max(n_s, 1)
+    line = {
+        "metric": "optimizer iters/sec", "workload": name, "value": args.steps / t,
+        "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+        "n_elem": eng.n_elem, "n_dof": eng.n_dof, "nnz": nnz, "setup_s": setup_s,
+        "preconditioner": eng.precond if (eng.mg or eng.smg) else "jacobi",
+        "pcg_iters_per_solve": [l[0] for l in eng.pcg_log[n0:]],
+        "pcg_converged": bool(all(l[1] for l in eng.pcg_log[n0:])),
+        "objective": [float(v) for v in np.asarray(
+            getattr(opt.recorder.as_object(), opt._objective_history_name(tsk)))][-args.steps:],
+        "bisection_steps": list(opt.bisection_steps)[-args.steps:],
+        "roofline": {"bound": "hbm", "kernel": kernel, "bytes_per_launch": op_bytes,
+                     "avg_launch_ms": ms, "samples": n_s,
+                     "achieved": op_bytes / (ms * 1e-3) / 1e9 if n_s else None,
+                     "peak": peak, "unit": "GB/s",
+                     "frac": op_bytes / (ms * 1e-3) / 1e9 / peak if n_s else None,
+                     "peak_source": peak_src},
+        "gpu_launches": int(launches), "dtype": "f64", "data": "synthetic",
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -573,9 +640,13 @@ def main():
                     help="under --gpus N > 1: timed steps of the 8.08M-element C5 run (0: skip)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one extra step inside cudaProfilerStart/Stop before the timed region")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2: the headline (default); c3 / c4: BASELINE configs 3 / 4 at size")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "c2":
+        run_workload(args)
     else:
         run_b200(args)
 
