@@ -455,7 +455,7 @@ def run_b200(args):
             alg_bytes = n_loc_nodes * (24 + 24 + 24 + 1) + n_elem * 8
             roofline = {
                 "bound": "fp64",
-                "kernel": "hexgrid_apply kernel, fp64 + dot variant (matrix-free q = K(rho) p + p.q; the V-cycle runs two more per PCG iteration in fp32)",
+                "kernel": "hexgrid_apply_x2_kernel<double,0,true> (matrix-free q = K(rho) p + p.q, two nodes per thread, coefficients from shared memory; the V-cycle runs two more per PCG iteration in fp32)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp64_peak) if achieved else None,
                 "peak_source": "DFMA-chain probe run by this bench (sktb_fp64_probe, profiles/r2_fp64_probe.md); "
@@ -469,10 +469,10 @@ def run_b200(args):
                         "peak_GBs": peak, "peak_source": peak_src},
                 "note": "the assembled-operator SpMV this replaces streamed 8.44 B/nnz (2.1 GB per "
                         "launch, 0.44 ms at the HBM roofline); the matrix-free product moves "
-                        "~85 MB.  Its DFMAs take the stiffness coefficient as a constant-bank "
-                        "operand, which B200 issues at half the FP64 rate (peak_const_operand, "
-                        "measured by sktb_fp64_probe_const): that is the ceiling this formulation "
-                        "can reach",
+                        "~85 MB.  Round 1's kernel took its coefficients as constant-bank operands "
+                        "(half-rate DFMA on B200, peak_const_operand); this one reads them from "
+                        "shared memory into registers (full-rate DFMA) and is bound by instruction "
+                        "issue at 8 warps / SM (255 registers)",
             }
         else:
             # SURVEY.md 8(d), for the rows this rank owns

@@ -28,6 +28,7 @@
 // dof i of node n fixed (bit 3 = a fixed dof somewhere in the 27-neighbourhood,
 // used by the untiled kernel only).
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "linalg.cuh"
@@ -67,6 +68,11 @@ struct sktb_gridop {
   bool shfl = true;     // y-neighbours by warp shuffle (SKTB_GRIDOP_SHFL=0: all from L1)
   bool scalar_direct = true;  // DPN = 1: untiled stencil kernel (SKTB_GRIDOP_SCALAR_TILED=1: tiled)
   size_t smem = 0;
+  // two-nodes-per-thread kernel (DPN = 3): coefficient tables in global memory,
+  // staged in shared memory by every CTA (SKTB_GRIDOP_X2=0 disables)
+  bool x2 = true;
+  double *kt_d = nullptr;
+  float *ktf_d = nullptr;
 };
 
 static ScalarStencil make_scalar_stencil(const double *ke) {
@@ -553,6 +559,246 @@ __global__ void __launch_bounds__(kBlock, 2)
   }
 }
 
+// ------------- x2 kernel (DPN = 3): two nodes per thread, coefficients in smem --
+// The shuffle kernel above takes every stiffness coefficient as a constant-bank
+// operand (LDCU -> uniform register): 390 LDCU per node row and DFMAs that B200
+// issues at half rate with a uniform operand (sktb_fp64_probe_const), 0.33 of the
+// FP64 peak.  Here
+//  * the 64 valid (dz, dx, dy, element) 3x3 coefficient blocks sit in shared
+//    memory, padded to 16-byte groups (double: 10 per block, float: 12), and
+//    are read with LDS.128 broadcasts into REGISTERS: full-rate DFMA;
+//  * a thread owns the node pair (2 ixp, iy, iz), (2 ixp + 1, iy, iz): the same
+//    coefficient block serves both nodes (node A with neighbour column dx, node
+//    B with column dx + 1), so every coefficient load feeds two FMAs, and the 4
+//    neighbour columns of a plane are loaded once for the pair (12 column loads
+//    per pair instead of 18);
+//  * y-neighbours still come from the adjacent lanes by shuffle.
+// Work items are (iy, ixp, iz) over WHOLE z-planes (single GPU: all of them; a
+// slab-sharded rank: its planes).  Same boundary treatment as the shuffle
+// kernel: indices are clamped, elements outside the grid have modulus 0.
+struct GridX2 {
+  int32_t npx, npy, npz;
+  const double *scale;
+  const uint8_t *dmask;
+  const double *kt;
+  const float *ktf;
+};
+template <typename T> struct X2Tab;
+template <> struct X2Tab<double> {
+  static constexpr int S = 10;
+  __device__ static __forceinline__ void load9(const double *p, double (&c)[9]) {
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    const double2 b = *reinterpret_cast<const double2 *>(p + 2);
+    const double2 d = *reinterpret_cast<const double2 *>(p + 4);
+    const double2 e = *reinterpret_cast<const double2 *>(p + 6);
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y; c[4] = d.x; c[5] = d.y;
+    c[6] = e.x; c[7] = e.y; c[8] = p[8];
+  }
+};
+template <> struct X2Tab<float> {
+  static constexpr int S = 12;
+  __device__ static __forceinline__ void load9(const float *p, float (&c)[9]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    const float4 b = *reinterpret_cast<const float4 *>(p + 4);
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y;
+    c[6] = b.z; c[7] = b.w; c[8] = p[8];
+  }
+};
+constexpr int kX2Slots = 216;  // ((dz+1) 3 + (dx+1)) 3 + (dy+1)) 8 + o
+
+#ifndef SKTB_X2_BLOCK
+#define SKTB_X2_BLOCK 256
+#define SKTB_X2_MINB 1
+#endif
+constexpr int kX2Block = SKTB_X2_BLOCK;
+template <typename T, int MODE, bool DOT>
+__global__ void __launch_bounds__(kX2Block, SKTB_X2_MINB)
+    hexgrid_apply_x2_kernel(const GridX2 P, int z0, int nzs, int64_t node0,
+                            const double *__restrict__ x, double *__restrict__ y,
+                            const double *__restrict__ dotv, double *partials,
+                            unsigned int *ticket, double *dot_out, const PcgScalars *S,
+                            const double *__restrict__ sm_b,
+                            const double *__restrict__ sm_dinv, double sm_omega) {
+  if (S && S->rr <= S->tol2) return;
+  constexpr int TS = X2Tab<T>::S;
+  __shared__ __align__(16) T kt[kX2Slots * TS];
+  {
+    const T *src = sizeof(T) == 8 ? (const T *)P.kt : (const T *)P.ktf;
+    for (int i = threadIdx.x; i < kX2Slots * TS; i += blockDim.x) kt[i] = src[i];
+  }
+  __syncthreads();
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int npxp = (npx + 1) >> 1;
+  const int lane = threadIdx.x & 31;
+  const unsigned n_items = (unsigned)npy * (unsigned)npxp * (unsigned)nzs;
+  const unsigned n_pad = (n_items + 31u) & ~31u;
+  const unsigned trips = (n_pad + kX2Block - 1) / kX2Block;
+  const unsigned per_cta = (trips + gridDim.x - 1) / gridDim.x;
+  const unsigned w_end = min(n_pad, (blockIdx.x + 1) * per_cta * kX2Block);
+  double dot = 0.0;
+  for (unsigned w = blockIdx.x * per_cta * kX2Block + threadIdx.x; w < w_end; w += kX2Block) {
+    const bool live = w < n_items;
+    const unsigned wc = live ? w : n_items - 1;
+    const unsigned t1 = wc / (unsigned)npy;
+    const int iy = (int)(wc - t1 * (unsigned)npy);
+    const unsigned t2 = t1 / (unsigned)npxp;
+    const int ixA = 2 * (int)(t1 - t2 * (unsigned)npxp);
+    const int iz = z0 + (int)t2;
+    const bool hasB = ixA + 1 < npx;
+    const int nA = iy + npy * (ixA + npx * iz);
+    const int nB = hasB ? nA + npy : nA;
+    const unsigned dmA = P.dmask[nA], dmB = P.dmask[nB];
+    const bool near_fixed = ((dmA | dmB) & 8u) != 0;
+    // moduli of the 3 x 2 x 2 elements around the pair (0 outside the grid)
+    T Eg[3][2][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ex = ixA - 1 + a, ey = iy - 1 + b, ez = iz - 1 + c;
+          const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+          Eg[a][b][c] = ok ? (T)__ldg(&P.scale[ey + ny * (ex + nx * ez)]) : (T)0;
+        }
+    T peA[8][3], peB[8][3];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) peA[o][i] = peB[o][i] = (T)0;
+    // 32-bit index arithmetic (3 n_nodes < 2^31 is checked at creation)
+    int cxo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cxo[c] = npy * clampi(ixA - 1 + c, npx - 1) + iy;
+    const int lo = iy > 0 ? -3 : 0, hi = iy < npy - 1 ? 3 : 0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zo = npy * npx * clampi(iz + dz, npz - 1);
+      T col[4][3][3];  // [column ixA-1 .. ixA+2][dy + 1][component]
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int mc = zo + cxo[c];
+        const double *cp = x + 3 * mc;
+#ifdef SKTB_X2_SHFL
+#pragma unroll
+        for (int j = 0; j < 3; ++j) col[c][1][j] = (T)__ldg(cp + j);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          col[c][0][j] = __shfl_up_sync(0xffffffffu, col[c][1][j], 1);
+          col[c][2][j] = __shfl_down_sync(0xffffffffu, col[c][1][j], 1);
+        }
+        if (lane == 0 && iy > 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) col[c][0][j] = (T)__ldg(cp - 3 + j);
+        }
+        if (lane == 31 && iy < npy - 1) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) col[c][2][j] = (T)__ldg(cp + 3 + j);
+        }
+#else
+        // the nine values (iy-1 .. iy+1) x 3 components are contiguous in memory;
+        // the line ends are clamped (their values only feed elements of modulus 0)
+        {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            col[c][0][j] = (T)__ldg(cp + lo + j);
+            col[c][1][j] = (T)__ldg(cp + j);
+            col[c][2][j] = (T)__ldg(cp + hi + j);
+          }
+        }
+#endif
+        if (near_fixed) {  // a fixed dof somewhere around: mask the inputs
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int ky = iy + dy;
+            if (ky < 0 || ky >= npy) continue;
+            const unsigned mb = P.dmask[mc + dy];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if ((mb >> j) & 1u) col[c][dy + 1][j] = (T)0;
+          }
+        }
+      }
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            T c9[9];
+            X2Tab<T>::load9(&kt[((((dz + 1) * 3 + (dx + 1)) * 3 + (dy + 1)) * 8 + o) * TS], c9);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                peA[o][i] = fma(c9[3 * i + j], col[dx + 1][dy + 1][j], peA[o][i]);
+                peB[o][i] = fma(c9[3 * i + j], col[dx + 2][dy + 1][j], peB[o][i]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb == 1 && !hasB) break;
+        const int n = nb ? nB : nA;
+        const unsigned dm = nb ? dmB : dmA;
+        const int r = n - (int)node0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          T acc = (T)0;
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const T E = Eg[(o & 1) + nb][(o >> 1) & 1][o >> 2];
+            acc = fma(E, nb ? peB[o][i] : peA[o][i], acc);
+          }
+          double a = (double)acc;
+          if ((dm >> i) & 1u) a = x[3 * n + i];
+          if (MODE == 1)
+            a = x[3 * n + i] + sm_omega * sm_dinv[3 * r + i] * (sm_b[3 * r + i] - a);
+          y[3 * r + i] = a;
+          if (DOT) dot = fma(a, dotv[3 * r + i], dot);
+        }
+      }
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
+// whole planes only; returns -1 when the range is not eligible
+template <typename T, int MODE>
+static int launch_x2(const sktb_gridop *op, int64_t node0, int64_t n_nodes, const double *x,
+                     double *y, const double *dotv, ReduceScratch *rs, double *dot_out,
+                     const PcgScalars *S, const double *b, const double *dinv, double omega,
+                     cudaStream_t st) {
+  const GridParams<3> &G = op->P3;
+  const int64_t plane = (int64_t)G.npx * G.npy;
+  if (!op->x2 || !op->kt_d || node0 % plane || n_nodes % plane) return -1;
+  GridX2 P{G.npx, G.npy, G.npz, G.scale, G.dmask, op->kt_d, op->ktf_d};
+  const int z0 = (int)(node0 / plane), nzs = (int)(n_nodes / plane);
+  const int64_t items = (int64_t)G.npy * ((G.npx + 1) / 2) * nzs;
+  const int64_t trips = (items + kX2Block - 1) / kX2Block;
+  const int64_t cap = (int64_t)kNumSM * SKTB_X2_MINB;
+  const int g = (int)(trips < cap ? trips : cap);
+  if (dotv)
+    hexgrid_apply_x2_kernel<T, MODE, true><<<g, kX2Block, 0, st>>>(
+        P, z0, nzs, node0, x, y, dotv, rs->partials, rs->ticket, dot_out, S, b, dinv, omega);
+  else
+    hexgrid_apply_x2_kernel<T, MODE, false><<<g, kX2Block, 0, st>>>(
+        P, z0, nzs, node0, x, y, nullptr, nullptr, nullptr, nullptr, S, b, dinv, omega);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
 // ------------------------------ split kernel (DPN = 3): two warps per node --
 // The untiled kernel holds 24 accumulators + 8 moduli per thread (128
 // registers, 16 warps/SM) and is latency bound.  Here a warp PAIR owns 32
@@ -873,6 +1119,11 @@ int launch_hexgrid_apply(const sktb_gridop *op, int64_t node0, int64_t n_nodes,
   if (!op->direct)
     return launch_tiled<3>(op, op->P3, node0, n_nodes, x, y, dotv, rs, dot_out, S, st);
   if (op->shfl) {
+    {
+      const int rc = launch_x2<double, 0>(op, node0, n_nodes, x, y, dotv, rs, dot_out, S, nullptr,
+                                          nullptr, 0.0, st);
+      if (rc != -1) return rc;
+    }
     const int g = grid_for(n_nodes, kBlock, 2);
     if (dotv)
       hexgrid_apply_shfl_kernel<double, 0, true><<<g, kBlock, 0, st>>>(
@@ -916,6 +1167,20 @@ int launch_hexgrid_apply_ex(const sktb_gridop *op, int64_t node0, int64_t n_node
                             const double *x, double *y, bool fp32, const double *b,
                             const double *dinv, double omega, cudaStream_t st) {
   if (op->dpn != 3 || !op->shfl || !op->direct) return -1;
+  {
+    int rc;
+    if (b)
+      rc = fp32 ? launch_x2<float, 1>(op, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr,
+                                      b, dinv, omega, st)
+                : launch_x2<double, 1>(op, node0, n_nodes, x, y, nullptr, nullptr, nullptr,
+                                       nullptr, b, dinv, omega, st);
+    else
+      rc = fp32 ? launch_x2<float, 0>(op, node0, n_nodes, x, y, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, 0.0, st)
+                : launch_x2<double, 0>(op, node0, n_nodes, x, y, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, 0.0, st);
+    if (rc != -1) return rc;
+  }
   const int g = grid_for(n_nodes, kBlock, 2);
 #define SKTB_EX(T, MODE)                                                               \
   hexgrid_apply_shfl_kernel<T, MODE, false><<<g, kBlock, 0, st>>>(                     \
@@ -996,6 +1261,36 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   if (dpn == 3) {
     fill(op->P3, 576);
     choose_tiles<3>(op->P3, &op->smem);
+    {
+      // coefficient blocks of the x2 kernel, slot = (((dz+1) 3 + dx+1) 3 + dy+1) 8 + o
+      const char *envx = getenv("SKTB_GRIDOP_X2");
+      op->x2 = !(envx && envx[0] == '0');
+      std::vector<double> kt((size_t)kX2Slots * 10, 0.0);
+      std::vector<float> ktf((size_t)kX2Slots * 12, 0.f);
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dx = -1; dx <= 1; ++dx)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int o = 0; o < 8; ++o) {
+              const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+              const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+              if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+              const int ca = (1 - ox) + 2 * (1 - oy) + 4 * (1 - oz);
+              const int cb = bx + 2 * by + 4 * bz;
+              const int slot = (((dz + 1) * 3 + (dx + 1)) * 3 + (dy + 1)) * 8 + o;
+              for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                  const double v = ke_cc_h[(3 * ca + i) * 24 + 3 * cb + j];
+                  kt[(size_t)slot * 10 + 3 * i + j] = v;
+                  ktf[(size_t)slot * 12 + 3 * i + j] = (float)v;
+                }
+            }
+      SKTB_CUDA_OK(cudaMalloc(&op->kt_d, sizeof(double) * kt.size()));
+      SKTB_CUDA_OK(cudaMalloc(&op->ktf_d, sizeof(float) * ktf.size()));
+      SKTB_CUDA_OK(cudaMemcpy(op->kt_d, kt.data(), sizeof(double) * kt.size(),
+                              cudaMemcpyHostToDevice));
+      SKTB_CUDA_OK(cudaMemcpy(op->ktf_d, ktf.data(), sizeof(float) * ktf.size(),
+                              cudaMemcpyHostToDevice));
+    }
     SKTB_CUDA_OK(cudaFuncSetAttribute(grid_apply_tiled_kernel<3, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     SKTB_CUDA_OK(cudaFuncSetAttribute(grid_apply_tiled_kernel<3, false>,
@@ -1011,7 +1306,12 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
   return 0;
 }
 
-extern "C" void sktb_gridop_destroy(sktb_gridop *op) { delete op; }
+extern "C" void sktb_gridop_destroy(sktb_gridop *op) {
+  if (!op) return;
+  cudaFree(op->kt_d);
+  cudaFree(op->ktf_d);
+  delete op;
+}
 
 extern "C" int sktb_gridop_set_fields(sktb_gridop *op, const double *scale,
                                       const uint8_t *dmask) {
