@@ -611,6 +611,7 @@ constexpr int kX2Slots = 216;  // ((dz+1) 3 + (dx+1)) 3 + (dy+1)) 8 + o
 #define SKTB_X2_MINB 1
 #endif
 constexpr int kX2Block = SKTB_X2_BLOCK;
+static_assert(kX2Block == kBlock, "grid_reduce folds kBlock / 32 warp partials per CTA");
 template <typename T, int MODE, bool DOT>
 __global__ void __launch_bounds__(kX2Block, SKTB_X2_MINB)
     hexgrid_apply_x2_kernel(const GridX2 P, int z0, int nzs, int64_t node0,
