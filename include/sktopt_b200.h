@@ -269,6 +269,20 @@ int sktb_elem_combine_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
                             const int32_t *child, const uint8_t *ptype,
                             const double *T, const int32_t *cls, const double *scale,
                             double *out, void *stream);
+/* Stress tensor sigma = 2 mu eps(u) + lam tr eps(u) I at every quadrature point
+ * (fea/composer.py:444-494 stress_tensor_skfem); G = physical shape-function
+ * gradients [class][q][a][3] from sktb_geom_tables; out[3][3][n_elem][nqp].      */
+int sktb_element_stress(const sktb_mesh *m, int nqp, const int32_t *elem_class,
+                        const double *G, const double *E_elem, double nu, const double *u,
+                        double *out, void *stream);
+/* Batched, strided, row-major fp64 product C[b] = A[b] . B[b] (optionally times
+ * scale[b] elementwise, same layout as C): the six small dense products of the
+ * direct (fast-diagonalisation) Helmholtz solve that replaces the sparse LU of
+ * filters/helmholtz_filter_nodal.py:121-157 on tensor grids.                    */
+int sktb_dgemm_batched(int M, int N, int K, const double *A, int lda, int64_t stride_a,
+                       const double *B, int ldb, int64_t stride_b, double *C, int ldc,
+                       int64_t stride_c, int batch, const double *scale, int64_t stride_s,
+                       void *stream);
 /* ---- scalar multigrid on tensor grids (heat conduction: the reference's sparse
  * LU of K, fea/solver_heat.py:191-192, becomes an MG-preconditioned PCG).  The
  * operators are kept in a 27-point stencil ("DIA") format, vals[k][node] with

@@ -1213,3 +1213,64 @@ extern "C" int sktb_local_to_nodes(const sktb_mesh *m, const double *local,
   SKTB_KERNEL_OK();
   return 0;
 }
+
+
+// ------------------------------------------------------ stress at quadrature --
+// sigma = 2 mu sym(grad u) + lam tr(sym grad u) I per (element, quadrature point)
+// (reference fea/composer.py:444-494, compute_element_stress_tensor /
+// stress_tensor_skfem; post-processing, not part of the optimiser loop).
+// out[(i*3+j)][e][q], G = physical shape-function gradients [cls][q][a][3].
+template <int NEN>
+__global__ void __launch_bounds__(kBlock)
+    element_stress_kernel(int64_t n_elem, int nqp, const int32_t *__restrict__ conn,
+                          const int32_t *__restrict__ cls, const double *__restrict__ G,
+                          const double *__restrict__ E, double nu,
+                          const double *__restrict__ u, double *__restrict__ out) {
+  const int64_t total = n_elem * nqp;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; id < total; id += stride) {
+    const int64_t e = id / nqp;
+    const int q = (int)(id - e * nqp);
+    const int64_t c = cls ? cls[e] : e;
+    const double *g = G + ((c * nqp + q) * NEN) * 3;
+    double gr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // du_i / dx_j
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) {
+      const int64_t nd = conn[(int64_t)a * n_elem + e];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double ui = u[3 * nd + i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gr[i][j] = fma(ui, g[3 * a + j], gr[i][j]);
+      }
+    }
+    const double Ee = E[e];
+    const double lam = nu * Ee / ((1.0 + nu) * (1.0 - 2.0 * nu)), mu = Ee / (2.0 * (1.0 + nu));
+    const double tr = gr[0][0] + gr[1][1] + gr[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double s = mu * (gr[i][j] + gr[j][i]);
+        if (i == j) s += lam * tr;
+        out[((int64_t)(3 * i + j) * n_elem + e) * nqp + q] = s;
+      }
+  }
+}
+
+extern "C" int sktb_element_stress(const sktb_mesh *m, int nqp, const int32_t *elem_class,
+                                   const double *G, const double *E_elem, double nu,
+                                   const double *u, double *out, void *stream) {
+  SKTB_REQUIRE(m && G && E_elem && u && out && nqp > 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(m->n_elem * nqp);
+  if (m->nen == 8)
+    element_stress_kernel<8><<<grid, kBlock, 0, st>>>(m->n_elem, nqp, m->conn, elem_class, G,
+                                                     E_elem, nu, u, out);
+  else
+    element_stress_kernel<4><<<grid, kBlock, 0, st>>>(m->n_elem, nqp, m->conn, elem_class, G,
+                                                     E_elem, nu, u, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}

@@ -839,3 +839,14 @@ def fp64_peak_tflops(iters: int = 4096, reps: int = 5, const_operand: bool = Fal
 
 def flush_l2(scratch):
     _lib.check(_lib.load().sktb_flush_l2(_ptr(scratch), scratch.numel() * scratch.element_size(), _stream()))
+
+
+def dgemm(A, B, out, M, N, K, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, stride_c=0,
+          scale=None, stride_s=0):
+    """out[b] = A[b] . B[b] (* scale[b] elementwise); row-major, strides in elements
+    (``csrc/dgemm.cu``)."""
+    _lib.check(_lib.load().sktb_dgemm_batched(
+        int(M), int(N), int(K), _ptr(A), int(lda), int(stride_a), _ptr(B), int(ldb),
+        int(stride_b), _ptr(out), int(ldc), int(stride_c), int(batch), _ptr(scale),
+        int(stride_s), _stream()))
+    return out

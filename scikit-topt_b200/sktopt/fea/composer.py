@@ -155,3 +155,63 @@ def strain_energy_skfem(basis, rho, u, E0, Emin, p, nu, elem_func=simp_interpola
 def strain_energy_skfem_multi(basis, rho, U, E0, Emin, p, nu, elem_func=simp_interpolation):
     from sktopt.fea import solver_elastic
     return solver_elastic.strain_energy_skfem_multi(basis, rho, U, E0, Emin, p, nu, elem_func)
+
+
+# ------------------------------------------------------- stress post-processing --
+def compute_element_stress_tensor(w):
+    """sigma = 2 mu eps(u) + lam tr(eps(u)) I at the quadrature points (reference
+    ``fea/composer.py:444-466``, there a scikit-fem ``Functional`` body).  ``w``
+    maps 'uh' to an object whose ``.grad`` is the (3, 3, n_elem, n_qp) displacement
+    gradient (or to that array itself) and 'mu_elem' / 'lam_elem' to (n_qp, n_elem)
+    arrays, as the reference passes them.  Returns (3, 3, n_elem, n_qp)."""
+    uh = w["uh"]
+    grad = np.asarray(getattr(uh, "grad", uh), dtype=np.float64)
+    sym = 0.5 * (grad + np.swapaxes(grad, 0, 1))
+    tr = np.trace(sym, axis1=0, axis2=1)
+    mu = np.asarray(w["mu_elem"]).T[None, None, :, :]
+    lam = np.asarray(w["lam_elem"]).T[None, None, :, :]
+    return 2.0 * mu * sym + lam * np.eye(3)[:, :, None, None] * tr[None, None, :, :]
+
+
+def stress_tensor_skfem(basis, rho, u, E0: float, Emin: float, p: float, nu: float,
+                        elem_func: Callable = simp_interpolation):
+    """Stress tensor of the displacement field ``u`` at every quadrature point of
+    ``basis``: array (3, 3, n_elem, n_qp), the layout
+    ``von_mises_from_stress_tensor`` consumes (reference ``:469-494``).
+
+    (The reference pushes the tensor through ``Functional.elemental``, whose sum
+    over axis 1 collapses the second tensor index instead of the quadrature axis;
+    that accident is not reproduced -- the point values are returned.)"""
+    from sktopt._b200 import device as dev
+    from sktopt._b200 import lib as _lib
+    import torch
+    dev.require_cuda()
+    dm = dev.device_mesh(basis.mesh)
+    on_dev = isinstance(u, torch.Tensor) and u.is_cuda
+    u_d = u if on_dev else dev.to_dev(np.ascontiguousarray(u, dtype=np.float64))
+    rho_d = rho if (isinstance(rho, torch.Tensor) and rho.is_cuda) else dev.to_dev(rho)
+    E = dev.interpolate_modulus(rho_d, E0, Emin, p, ramp=is_ramp(elem_func))
+    N, G, dx, _ = dm.geom_tables(basis.X, basis.W)
+    nq = int(basis.X.shape[1])
+    out = torch.empty((3, 3, dm.n_elem, nq), dtype=dev.F64, device="cuda")
+    _lib.check(_lib.load().sktb_element_stress(
+        dm.handle, nq, dev._ptr(dm.elem_class), dev._ptr(G), dev._ptr(E), float(nu),
+        dev._ptr(u_d), dev._ptr(out), dev._stream()))
+    return out if on_dev else out.cpu().numpy()
+
+
+def von_mises_from_stress_tensor(stress_tensor):
+    """Von Mises stress (n_elem, n_qp) from a (3, 3, n_elem, n_qp) stress tensor
+    (reference ``:497-519``); NumPy arrays and CUDA tensors are both accepted."""
+    s = stress_tensor
+    sqrt = np.sqrt
+    try:
+        import torch
+        if isinstance(s, torch.Tensor):
+            sqrt = torch.sqrt
+    except ImportError:            # pragma: no cover
+        pass
+    s_xx, s_yy, s_zz = s[0, 0], s[1, 1], s[2, 2]
+    s_xy, s_yz, s_zx = s[0, 1], s[1, 2], s[2, 0]
+    return sqrt(0.5 * ((s_xx - s_yy) ** 2 + (s_yy - s_zz) ** 2 + (s_zz - s_xx) ** 2
+                       + 6.0 * (s_xy ** 2 + s_yz ** 2 + s_zx ** 2)))

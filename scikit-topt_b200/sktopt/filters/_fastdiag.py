@@ -15,17 +15,23 @@ of each axis and V = Vz (x) Vx (x) Vy,
 
     V^T A V = diag(1 + r^2 (lam_z + lam_x + lam_y)) =: D,   A^-1 = V D^-1 V^T,
 
-so one solve is six dense products with the small V_d (plain library GEMMs on
-the fp64 tensor pipe: ``torch.matmul`` -> cuBLAS) and one diagonal scaling: a
-direct solve like the reference's LU, exact to rounding, ~10x cheaper than the
-PCG it replaces (20 iterations at rtol 1e-11).  Systems with fixed nodes keep
-the PCG (``_HelmholtzDevice._solve``).
+so one solve is six dense products with the small V_d and one diagonal scaling
+(fused into the third product): a direct solve like the reference's LU, exact to
+rounding, ~10x cheaper than the PCG it replaces (20 iterations at rtol 1e-11).
+The products run on the hand-written batched fp64 kernel ``csrc/dgemm.cu``
+(``sktb_dgemm_batched``); ``SKTOPT_B200_FD_TORCH=1`` switches to ``torch.matmul``
+(cuBLAS), kept only as the cross-check of ``tests/test_gpu_parity.py``.  Systems
+with fixed nodes keep the PCG (``_HelmholtzDevice._solve``).
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import scipy.linalg
 import torch
+
+from sktopt._b200 import device as dev
 
 
 def axis_matrices(c: np.ndarray):
@@ -67,6 +73,31 @@ class FastDiagHelmholtz:
         self.radius = r
 
     def solve(self, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if b.device.type != "cuda" or os.environ.get("SKTOPT_B200_FD_TORCH", "0") == "1":
+            # (host tensors: the CPU test of the factorisation itself, tests/test_oracle.py)
+            return self._solve_torch(b, out)
+        npz, npx, npy = self.shape
+        n, plane = npz * npx * npy, npx * npy
+        if getattr(self, "_w", None) is None:
+            self._w = [torch.empty(n, dtype=torch.float64, device=b.device) for _ in range(2)]
+        w0, w1 = self._w
+        Vz, Vx, Vy = self.V
+        Vzt, Vxt, Vyt = self.Vt
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=b.device)
+        # V^T b: along y (rows x Vy), along x (Vx^T per z-plane), along z (Vz^T), then D^-1
+        dev.dgemm(b, Vy, w0, npz * npx, npy, npy, npy, npy, npy)
+        dev.dgemm(Vxt, w0, w1, npx, npy, npx, npx, npy, npy, batch=npz, stride_b=plane,
+                  stride_c=plane)
+        dev.dgemm(Vzt, w1, w0, npz, plane, npz, npz, plane, plane, scale=self.Dinv)
+        # V (.)
+        dev.dgemm(Vz, w0, w1, npz, plane, npz, npz, plane, plane)
+        dev.dgemm(Vx, w1, w0, npx, npy, npx, npx, npy, npy, batch=npz, stride_b=plane,
+                  stride_c=plane)
+        dev.dgemm(w0, Vyt, out, npz * npx, npy, npy, npy, npy, npy)
+        return out
+
+    def _solve_torch(self, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         npz, npx, npy = self.shape
         Vz, Vx, Vy = self.V
         Vzt, Vxt, Vyt = self.Vt

@@ -14,9 +14,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_OF_SCOPE = {
     "core.misc.add_common_arguments": "argparse wiring of the reference's CLI examples (DESIGN.md 8)",
     "core.misc.args2OC_Config_dict": "argparse wiring of the reference's CLI examples",
-    "fea.composer.compute_element_stress_tensor": "stress post-processing, never called by the loop",
-    "fea.composer.stress_tensor_skfem": "stress post-processing, never called by the loop",
-    "fea.composer.von_mises_from_stress_tensor": "stress post-processing, never called by the loop",
     "fea.solver_heat.avg_temp_skfem": "elemental (T - T_env) integrals: unused by the optimiser, "
                                       "which takes J = sum(T) (solver_heat.py:871-873)",
     "fea.solver_heat.avg_temp_skfem_multi": "same",

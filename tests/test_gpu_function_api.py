@@ -101,3 +101,99 @@ def test_heat_and_energy_function_api(gpu):
     assert np.max(np.abs(E - E_ref)) <= 1e-10 * np.abs(E_ref).max()
     e0 = composer.strain_energy_skfem(tsk.basis, rho_t, u[:, 0], 210e3, 210.0, 3.0, 0.3)
     assert np.array_equal(e0, E[:, 0])
+
+
+def test_fast_diagonalisation_hand_written_products_match_cublas(gpu, monkeypatch):
+    """The six dense products of the direct Helmholtz solve run on csrc/dgemm.cu;
+    torch.matmul (cuBLAS) is kept as the cross-check: same result to 1e-13, on a
+    grid whose sizes are not multiples of the 64 x 64 x 16 tile."""
+    sktopt, dev = gpu
+    import torch
+    from sktopt.filters._fastdiag import FastDiagHelmholtz
+    axes = (np.linspace(0, 8, 71), np.linspace(0, 6, 54), np.linspace(0, 4, 37))
+    fd = FastDiagHelmholtz(axes)
+    fd.set_radius(0.35)
+    n = 71 * 54 * 37
+    b = torch.as_tensor(np.random.default_rng(0).standard_normal(n), device="cuda")
+    x1 = fd.solve(b).clone()
+    monkeypatch.setenv("SKTOPT_B200_FD_TORCH", "1")
+    x2 = fd.solve(b)
+    assert float((x1 - x2).abs().max()) <= 1e-13 * float(x2.abs().max())
+    out = torch.empty_like(b)
+    monkeypatch.delenv("SKTOPT_B200_FD_TORCH")
+    assert fd.solve(b, out=out) is out and torch.equal(out, x1)
+    # plain product, batched with strides, against numpy
+    A = np.random.default_rng(1).standard_normal((3, 70, 33))
+    B = np.random.default_rng(2).standard_normal((3, 33, 45))
+    C = torch.empty((3, 70, 45), dtype=torch.float64, device="cuda")
+    dev.dgemm(dev.to_dev(A), dev.to_dev(B), C, 70, 45, 33, 33, 45, 45, batch=3,
+              stride_a=70 * 33, stride_b=33 * 45, stride_c=70 * 45)
+    assert np.abs(C.cpu().numpy() - A @ B).max() <= 1e-13 * np.abs(A @ B).max()
+
+
+def test_stress_tensor_and_von_mises(gpu):
+    """fea/composer.py:444-519: sigma = 2 mu eps + lam tr(eps) I at the quadrature
+    points.  A linear displacement field has a constant, known strain; a general
+    field is checked against the oracle's gradient tables, hex and tet."""
+    sktopt, dev = gpu
+    from oracle import fem
+    from sktopt._fem import Basis, ElementHex1, ElementTetP1, ElementVector
+    comp = sktopt.fea.composer
+    E0, Emin, p_pow, nu = 210e3, 210.0, 3.0, 0.3
+    for mesh, elem in ((sktopt.mesh.toy_problem.create_box_hex(2.0, 1.0, 1.0, 0.25), ElementHex1()),
+                       (sktopt.mesh.toy_problem.create_box_tet(2.0, 1.0, 1.0, 0.34), ElementTetP1())):
+        basis = Basis(mesh, ElementVector(elem), intorder=2)
+        P, t = mesh.p, mesh.t
+        rho = np.random.default_rng(0).uniform(0.2, 1.0, t.shape[1])
+        H = np.array([[1e-3, 2e-3, 0.0], [-1e-3, 5e-4, 3e-3], [2e-3, 0.0, -1e-3]])
+        u = (H @ P).T.ravel()                          # u_i = H_ij x_j, dof = 3 node + i
+        s = comp.stress_tensor_skfem(basis, rho, u, E0, Emin, p_pow, nu)
+        nq = basis.X.shape[1]
+        assert s.shape == (3, 3, t.shape[1], nq)
+        Ee = fem.simp(rho, E0, Emin, p_pow)
+        lam, mu = nu * Ee / ((1 + nu) * (1 - 2 * nu)), Ee / (2 * (1 + nu))
+        eps = 0.5 * (H + H.T)
+        ref = (2 * mu[None, None, :] * eps[:, :, None]
+               + lam[None, None, :] * np.trace(eps) * np.eye(3)[:, :, None])
+        assert np.abs(s - ref[:, :, :, None]).max() <= 1e-10 * np.abs(ref).max()
+        # general field against the oracle's physical gradients
+        u2 = np.random.default_rng(1).standard_normal(3 * P.shape[1]) * 1e-3
+        s2 = comp.stress_tensor_skfem(basis, rho, u2, E0, Emin, p_pow, nu)
+        _, G, _ = fem.physical_gradients(P, t, basis.X)            # (ne, nq, nen, 3)
+        ue = np.stack([u2[3 * t.astype(np.int64) + c] for c in range(3)], axis=-1)  # (nen, ne, 3)
+        grad = np.einsum("aei,eqaj->ijeq", ue, G)
+        w = {"uh": grad, "mu_elem": np.tile(mu, (nq, 1)), "lam_elem": np.tile(lam, (nq, 1))}
+        ref2 = comp.compute_element_stress_tensor(w)
+        assert np.abs(s2 - ref2).max() <= 1e-10 * np.abs(ref2).max()
+        vm = comp.von_mises_from_stress_tensor(s2)
+        dev_s = s2 - np.trace(s2, axis1=0, axis2=1)[None, None] * np.eye(3)[:, :, None, None] / 3
+        assert np.abs(vm - np.sqrt(1.5 * np.einsum("ijeq,ijeq->eq", dev_s, dev_s))).max() \
+            <= 1e-10 * vm.max()
+        vm_d = comp.von_mises_from_stress_tensor(dev.to_dev(s2))
+        assert np.abs(vm_d.cpu().numpy() - vm).max() <= 1e-12 * vm.max()
+
+
+def test_helmholtz_filter_element(gpu):
+    """Element-graph Helmholtz filter (filters/helmholtz_filter_element.py:195-317,
+    448-536) against the oracle's sparse LU, hex and tet, NumPy and CUDA inputs."""
+    sktopt, dev = gpu
+    from oracle.filters import HelmholtzElementOracle
+    from sktopt.filters.helmholtz_filter_element import (HelmholtzFilterElement,
+                                                         prepare_helmholtz_filter)
+    for mesh in (sktopt.mesh.toy_problem.create_box_hex(2.0, 1.0, 1.0, 0.25),
+                 sktopt.mesh.toy_problem.create_box_tet(2.0, 1.0, 1.0, 0.34)):
+        vol = sktopt.fea.composer.get_elements_volume(mesh)
+        rho = np.random.default_rng(0).uniform(0.0, 1.0, mesh.nelements)
+        ref = HelmholtzElementOracle(mesh.p, mesh.t, 0.4)
+        A, V = prepare_helmholtz_filter(mesh, 0.4)
+        assert abs(A - ref.A).max() <= 1e-13 * abs(ref.A).max()
+        f = HelmholtzFilterElement.from_defaults(mesh, vol, 0.4, solver_option="spsolve")
+        y = f.forward(rho)
+        assert np.abs(y - ref.forward(rho)).max() <= 1e-9
+        g = f.gradient(dev.to_dev(rho))
+        assert g.is_cuda and np.abs(g.cpu().numpy() - ref.gradient(rho)).max() <= 1e-9
+        # the filter preserves the volume-weighted mean (V-weighted column sums of A^-1 V)
+        w = vol / vol.mean()
+        assert abs(np.sum(w * y) - np.sum(w * rho)) <= 1e-8 * np.sum(w)
+        f.update_radius(0.2)
+        assert np.abs(f.forward(rho) - HelmholtzElementOracle(mesh.p, mesh.t, 0.2).forward(rho)).max() <= 1e-9
