@@ -732,13 +732,13 @@ __global__ void __launch_bounds__(kX2Block, SKTB_X2_MINB)
             if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
             T c9[9];
             X2Tab<T>::load9(&kt[((((dz + 1) * 3 + (dx + 1)) * 3 + (dy + 1)) * 8 + o) * TS], c9);
+            // j outermost: six independent accumulators between two FMAs of a chain
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) {
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                peA[o][i] = fma(c9[3 * i + j], col[dx + 1][dy + 1][j], peA[o][i]);
-                peB[o][i] = fma(c9[3 * i + j], col[dx + 2][dy + 1][j], peB[o][i]);
-              }
+              for (int i = 0; i < 3; ++i) peA[o][i] = fma(c9[3 * i + j], col[dx + 1][dy + 1][j], peA[o][i]);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) peB[o][i] = fma(c9[3 * i + j], col[dx + 2][dy + 1][j], peB[o][i]);
             }
           }
         }
