@@ -396,6 +396,9 @@ def run_b200(args):
             f"{[l for l, sh in enumerate(eng.mg.shard) if sh is not None] if eng.mg else []} "
             f"and the Helmholtz filter PCG sharded (NCCL plane exchange + dot all-reduces); "
             f"element-wise stages replicated"),
+        "halo": (None if world == 1 else
+                 "peer memory (NVLink P2P pulls through cudaIpc, one kernel per exchange)"
+                 if getattr(eng.comm, "p2p", False) else "ncclSend / ncclRecv"),
         "rows_per_rank": int(eng.n_local), "halo_dofs": int(getattr(eng, "halo_dofs", 0)),
         "last_compliance": comp_last,
     }

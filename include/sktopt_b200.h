@@ -353,6 +353,19 @@ int sktb_comm_rank(const sktb_comm *c);
 int sktb_comm_world(const sktb_comm *c);
 int sktb_comm_allreduce_sum(sktb_comm *c, const double *src, double *dst,
                             int64_t count, void *stream);
+/* Peer-memory halos (NVLink P2P through cudaIpc; NCCL transport, one GPU per
+ * rank): every rank creates one arena of `bytes` and gets its 64-byte IPC
+ * handle; the launcher all-gathers the handles (rank order) and every rank maps
+ * its neighbours' arenas with sktb_comm_arena_open.  Full-length slab-sharded
+ * vectors (PCG direction, multigrid iterates) are then placed in the arena at
+ * the same offset on every rank and their ghost planes are pulled straight from
+ * the neighbour's copy by one kernel per exchange (device-side flags), instead of
+ * ncclSend / ncclRecv.  status: bytes used, exchanges done, error flag (a spin
+ * on a neighbour timed out).                                                    */
+int sktb_comm_arena_create(sktb_comm *c, int64_t bytes, void *handle64_h);
+int sktb_comm_arena_open(sktb_comm *c, const void *handles_h);
+int sktb_comm_arena_status(const sktb_comm *c, int64_t *used_h, int64_t *epoch_h,
+                           int32_t *err_h);
 /* in-place all-gather of contiguous slices buf[displs[r] .. +counts[r])        */
 int sktb_comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts_h,
                          const int64_t *displs_h, void *stream);

@@ -241,6 +241,132 @@ static int shm_allgatherv(sktb_shm *s, double *buf, const int64_t *counts,
   return 0;
 }
 
+// ------------------------------------------------- peer-memory slab halos --
+namespace {
+sktb_comm *g_arena_comm = nullptr;  // one communicator per process owns the arena
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= e; gives up after ~4 s (sets *err) so that a dead neighbour
+// cannot hang the GPU
+__device__ __forceinline__ bool spin_until(const unsigned long long *p, unsigned long long e,
+                                           unsigned int *err) {
+  const long long t0 = clock64();
+  while (ld_sys(p) < e) {
+    // ~60 s at 1.9 GHz (ranks may be seconds apart after host-side set-up work);
+    // once the flag is up every later spin gives up at once
+    if (*(volatile unsigned int *)err || clock64() - t0 > 120000000000ll) {
+      atomicExch(err, 1u);
+      return false;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+  return true;
+}
+
+// One kernel per exchange.  Epoch e is the same on every rank (same call
+// sequence).  (1) publish: my planes for e are written (stream order) ->
+// ready = e.  (2) for each neighbour: wait for its ready >= e, copy its boundary
+// plane into my ghost plane with cache-bypassing loads.  (3) the last block
+// acknowledges to the neighbours and waits for their acknowledgements, so that
+// no later kernel of this stream overwrites a plane a neighbour still reads.
+__global__ void __launch_bounds__(256)
+    p2p_halo_kernel(P2PFlags *mine, P2PFlags *fprev, P2PFlags *fnext, unsigned long long e,
+                    double *v, const double *vprev, const double *vnext, int64_t own0,
+                    int64_t n_own, int64_t plane) {
+  __shared__ int ok;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    st_sys(&mine->ready, e);
+  }
+  for (int side = 0; side < 2; ++side) {
+    P2PFlags *fp = side ? fnext : fprev;
+    if (!fp) continue;
+    if (threadIdx.x == 0) ok = spin_until(&fp->ready, e, &mine->err) ? 1 : 0;
+    __syncthreads();
+    if (ok) {
+      // previous rank: its last plane sits right below my first one (global
+      // indexing); next rank: its first plane right above my last one
+      const int64_t off = side ? own0 + n_own : own0 - plane;
+      const double *src = (side ? vnext : vprev) + off;
+      double *dst = v + off;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
+           i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __ldcv(src + i);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&mine->done_cnt, 1u);
+    if (t == gridDim.x - 1) {
+      mine->done_cnt = 0u;
+      __threadfence_system();
+      if (fprev) st_sys(&fprev->ack[1], e);  // I am the previous rank's "next"
+      if (fnext) st_sys(&fnext->ack[0], e);
+      if (fprev) spin_until(&mine->ack[0], e, &mine->err);
+      if (fnext) spin_until(&mine->ack[1], e, &mine->err);
+    }
+  }
+}
+}  // namespace
+
+// my arena + its IPC handle (64 bytes); the launcher all-gathers the handles and
+// hands them to sktb_comm_arena_open
+extern "C" int sktb_comm_arena_create(sktb_comm *c, int64_t bytes, void *handle64_h) {
+  SKTB_REQUIRE(c && bytes >= 4096 && handle64_h, "bad argument");
+  SKTB_REQUIRE(!c->shm, "peer-memory halos need one GPU per rank (NCCL transport)");
+  SKTB_CUDA_OK(cudaSetDevice(c->device));
+  sktb_arena *a = new sktb_arena();
+  a->bytes = (size_t)bytes;
+  SKTB_CUDA_OK(cudaMalloc((void **)&a->base, a->bytes));
+  SKTB_CUDA_OK(cudaMemset(a->base, 0, a->bytes));
+  cudaIpcMemHandle_t h;
+  SKTB_CUDA_OK(cudaIpcGetMemHandle(&h, a->base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64_h, &h, 64);
+  c->arena = a;
+  return 0;
+}
+
+// handles_h: world x 64 bytes (rank order); maps the previous and the next rank's arena
+extern "C" int sktb_comm_arena_open(sktb_comm *c, const void *handles_h) {
+  SKTB_REQUIRE(c && c->arena && handles_h, "bad argument");
+  SKTB_CUDA_OK(cudaSetDevice(c->device));
+  for (int side = 0; side < 2; ++side) {
+    const int r = side ? c->rank + 1 : c->rank - 1;
+    if (r < 0 || r >= c->world) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles_h + (size_t)64 * r, 64);
+    void *p = nullptr;
+    SKTB_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->arena->peer[side] = (char *)p;
+  }
+  g_arena_comm = c;
+  return 0;
+}
+
+extern "C" int sktb_comm_arena_status(const sktb_comm *c, int64_t *used_h, int64_t *epoch_h,
+                                      int32_t *err_h) {
+  SKTB_REQUIRE(c && used_h && epoch_h && err_h, "null argument");
+  *used_h = c->arena ? (int64_t)c->arena->used : 0;
+  *epoch_h = c->arena ? (int64_t)c->arena->epoch : 0;
+  *err_h = 0;
+  if (c->arena) {
+    P2PFlags f;
+    SKTB_CUDA_OK(cudaMemcpy(&f, c->arena->base, sizeof(f), cudaMemcpyDeviceToHost));
+    *err_h = (int32_t)f.err;
+  }
+  return 0;
+}
+
 // -------------------------------------------------------------------- C ABI --
 extern "C" int sktb_comm_unique_id(void *id128_h) {
   SKTB_REQUIRE(id128_h, "null argument");
@@ -276,6 +402,13 @@ extern "C" int sktb_comm_create(sktb_comm **out, const void *id128_h, int rank,
 extern "C" void sktb_comm_destroy(sktb_comm *c) {
   if (!c) return;
   if (c->nccl && g_api.ok) g_api.CommDestroy((NcclComm)c->nccl);
+  if (c->arena) {
+    if (g_arena_comm == c) g_arena_comm = nullptr;
+    for (int side = 0; side < 2; ++side)
+      if (c->arena->peer[side]) cudaIpcCloseMemHandle(c->arena->peer[side]);
+    cudaFree(c->arena->base);
+    delete c->arena;
+  }
   if (c->shm) {
     munmap(c->shm->base, c->shm->bytes);
     close(c->shm->fd);
@@ -308,6 +441,46 @@ int comm_allreduce_sum(sktb_comm *c, const double *src, double *dst,
   if (c->shm) return shm_allreduce(c->shm, src, dst, count, st);
   NCCL_OK(g_api.AllReduce(src, dst, (size_t)count, kNcclFloat64, kNcclSum,
                           (NcclComm)c->nccl, st));
+  return 0;
+}
+
+int dev_alloc_exchangeable(double **out, size_t n_doubles) {
+  sktb_comm *c = g_arena_comm;
+  const size_t bytes = (sizeof(double) * n_doubles + 255) & ~(size_t)255;
+  if (c && c->arena && c->arena->used + bytes <= c->arena->bytes) {
+    *out = (double *)(c->arena->base + c->arena->used);
+    c->arena->used += bytes;
+    return 0;  // (the arena was zero-filled at creation)
+  }
+  SKTB_CUDA_OK(cudaMalloc((void **)out, sizeof(double) * n_doubles));
+  SKTB_CUDA_OK(cudaMemset(*out, 0, sizeof(double) * n_doubles));
+  return 0;
+}
+
+void dev_free(void *p) {
+  sktb_comm *c = g_arena_comm;
+  if (p && c && c->arena && (char *)p >= c->arena->base &&
+      (char *)p < c->arena->base + c->arena->bytes)
+    return;  // bump allocation: released with the arena
+  cudaFree(p);
+}
+
+int comm_slab_halo_p2p(sktb_comm *c, double *v, int64_t own0, int64_t n_own, int64_t plane,
+                       int prev, int next, cudaStream_t st) {
+  sktb_arena *a = c ? c->arena : nullptr;
+  if (!a || (char *)v < a->base || (char *)v >= a->base + a->bytes) return -1;
+  if ((prev >= 0 && !a->peer[0]) || (next >= 0 && !a->peer[1])) return -1;
+  const size_t off = (size_t)((char *)v - a->base);
+  const unsigned long long e = ++a->epoch;
+  P2PFlags *mine = (P2PFlags *)a->base;
+  P2PFlags *fp = prev >= 0 ? (P2PFlags *)a->peer[0] : nullptr;
+  P2PFlags *fn = next >= 0 ? (P2PFlags *)a->peer[1] : nullptr;
+  const double *vp = prev >= 0 ? (const double *)(a->peer[0] + off) : nullptr;
+  const double *vn = next >= 0 ? (const double *)(a->peer[1] + off) : nullptr;
+  int grid = (int)((plane + 2047) / 2048);
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  p2p_halo_kernel<<<grid, 256, 0, st>>>(mine, fp, fn, e, v, vp, vn, own0, n_own, plane);
+  SKTB_KERNEL_OK();
   return 0;
 }
 

@@ -16,9 +16,27 @@
 
 struct sktb_shm;  // comm.cu
 
+// Symmetric arena for peer-memory halos (NVLink P2P, cudaIpc): every rank
+// allocates one arena of the same size and bump-allocates its full-length,
+// slab-sharded vectors from it in the same order, so a vector sits at the same
+// offset on every rank and the neighbour's copy is peer_base + (ptr - my_base).
+struct P2PFlags {                 // first 256 bytes of the arena
+  unsigned long long ready;       // last exchange this rank has published
+  unsigned long long ack[2];      // [0] written by the previous rank, [1] by the next one
+  unsigned int done_cnt;          // block counter of the exchange kernel
+  unsigned int err;               // a spin timed out
+};
+struct sktb_arena {
+  char *base = nullptr;           // my arena (device)
+  size_t bytes = 0, used = 256;   // header = P2PFlags
+  char *peer[2] = {nullptr, nullptr};  // previous / next rank's arena, mapped here
+  unsigned long long epoch = 0;   // exchanges done (identical on all ranks)
+};
+
 struct sktb_comm {
   void *nccl = nullptr;  // ncclComm_t
   sktb_shm *shm = nullptr;
+  sktb_arena *arena = nullptr;  // peer-memory halos (NCCL transport only)
   int rank = 0;
   int world = 1;
   int device = 0;
@@ -43,6 +61,16 @@ int comm_exchange(sktb_comm *c, int n_peers, const int *peers,
 // the same with one (pointer, count) pair per peer and direction: contiguous
 // slabs are sent straight from / received straight into the vectors
 int comm_p2p(sktb_comm *c, int n_ops, const P2POp *ops, cudaStream_t st);
+// Device memory for a full-length vector that takes part in slab halo exchanges:
+// from the current communicator's symmetric arena when there is one (then the
+// exchange runs over peer memory), else cudaMalloc.  dev_free handles both.
+int dev_alloc_exchangeable(double **out, size_t n_doubles);
+void dev_free(void *p);
+// ghost planes of v pulled straight from the neighbours' copies over NVLink
+// (one kernel: publish, wait for the neighbour, copy, acknowledge); returns -1
+// when v is not an arena vector (caller: NCCL send / recv)
+int comm_slab_halo_p2p(sktb_comm *c, double *v, int64_t own0, int64_t n_own, int64_t plane,
+                       int prev, int next, cudaStream_t st);
 // in-place all-gather of variable-sized contiguous slices of `buf`
 int comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts,
                     const int64_t *displs, cudaStream_t st);

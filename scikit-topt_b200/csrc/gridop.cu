@@ -631,7 +631,9 @@ __global__ void __launch_bounds__(kX2Block, SKTB_X2_MINB)
   const int npx = P.npx, npy = P.npy, npz = P.npz;
   const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
   const int npxp = (npx + 1) >> 1;
+#ifdef SKTB_X2_SHFL
   const int lane = threadIdx.x & 31;
+#endif
   const unsigned n_items = (unsigned)npy * (unsigned)npxp * (unsigned)nzs;
   const unsigned n_pad = (n_items + 31u) & ~31u;
   const unsigned trips = (n_pad + kX2Block - 1) / kX2Block;

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <utility>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -86,13 +87,13 @@ extern "C" void sktb_mg_destroy(sktb_mg *m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (auto &l : m->lv) {
-    cudaFree(l.x);
+    dev_free(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
     cudaFree(l.dense_inv);
     cudaFree(l.d);
-    cudaFree(l.x2);
-    cudaFree(l.res);
+    dev_free(l.x2);
+    dev_free(l.res);
   }
   delete m;
 }
@@ -162,19 +163,22 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   if (l.n_global < n_nodes) l.n_global = n_nodes;
   if (!l.sharded && level > 0) l.node0 = 0;
   if (l.n_nodes != n_nodes || !l.x) {
-    cudaFree(l.x);
+    dev_free(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
-    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
-    SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
+    if (l.sharded) {
+      if (dev_alloc_exchangeable(&l.x, (size_t)3 * l.n_global)) return 1;
+    } else {
+      SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
+      SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
+    }
     SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
-    cudaFree(l.x2);
+    dev_free(l.x2);
     l.x2 = nullptr;
     if (level > 0 && l.sharded) {
       // second full-length iterate of the fused Jacobi sweeps
-      SKTB_CUDA_OK(cudaMalloc(&l.x2, sizeof(double) * 3 * l.n_global));
-      SKTB_CUDA_OK(cudaMemset(l.x2, 0, sizeof(double) * 3 * l.n_global));
+      if (dev_alloc_exchangeable(&l.x2, (size_t)3 * l.n_global)) return 1;
     } else if (level > 0 && n_nodes <= kTailMaxNodes) {
       SKTB_CUDA_OK(cudaMalloc(&l.x2, sizeof(double) * 3 * n_nodes));
     }
@@ -201,11 +205,15 @@ extern "C" int sktb_mg_set_level0_grid(sktb_mg *m, const sktb_gridop *op,
   MgLevel &l = m->lv[0];
   if (l.n_global < n_nodes) l.n_global = n_nodes;
   if (l.n_nodes != n_nodes || !l.x) {
-    cudaFree(l.x);
+    dev_free(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
-    SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
-    SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
+    if (l.sharded) {
+      if (dev_alloc_exchangeable(&l.x, (size_t)3 * l.n_global)) return 1;
+    } else {
+      SKTB_CUDA_OK(cudaMalloc(&l.x, sizeof(double) * 3 * l.n_global));
+      SKTB_CUDA_OK(cudaMemset(l.x, 0, sizeof(double) * 3 * l.n_global));
+    }
     SKTB_CUDA_OK(cudaMalloc(&l.b, sizeof(double) * 3 * n_nodes));
     SKTB_CUDA_OK(cudaMalloc(&l.tmp, sizeof(double) * 3 * n_nodes));
   }
@@ -225,7 +233,7 @@ extern "C" int sktb_mg_set_level0_range(sktb_mg *m, int64_t node0,
   SKTB_REQUIRE(m && node0 >= 0 && n_global > 0, "bad argument");
   MgLevel &l = m->lv[0];
   if (l.n_global != n_global) {
-    cudaFree(l.x);
+    dev_free(l.x);
     l.x = nullptr;
   }
   l.node0 = node0;
@@ -246,9 +254,9 @@ extern "C" int sktb_mg_set_level_slab(sktb_mg *m, int level, int64_t node0,
                "bad argument");
   MgLevel &l = m->lv[level];
   if (l.n_global != n_global || l.sharded != (plane_nodes > 0)) {
-    cudaFree(l.x);
+    dev_free(l.x);
     l.x = nullptr;
-    cudaFree(l.res);
+    dev_free(l.res);
     l.res = nullptr;
   }
   l.node0 = node0;
@@ -1092,8 +1100,7 @@ static int level_restrict(MgLevel &l, MgLevel &c, const double *b, sktb_pcg *dis
     // sharded -> sharded: the owned coarse rows need the fine residual on one
     // ghost plane each side: r = b - Ax into the full-length buffer, exchange
     if (!l.res) {
-      SKTB_CUDA_OK(cudaMalloc(&l.res, sizeof(double) * 3 * l.n_global));
-      SKTB_CUDA_OK(cudaMemset(l.res, 0, sizeof(double) * 3 * l.n_global));
+      if (dev_alloc_exchangeable(&l.res, (size_t)3 * l.n_global)) return 1;
     }
     mg_residual_kernel<<<grid_for(3 * l.n_nodes), kBlock, 0, st>>>(
         3 * l.n_nodes, b, l.tmp, l.res + 3 * l.node0);

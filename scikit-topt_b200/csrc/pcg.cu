@@ -79,8 +79,12 @@ static int pcg_alloc(sktb_pcg *s) {
   SKTB_CUDA_OK(cudaMalloc(&s->r, sizeof(double) * s->n));
   SKTB_CUDA_OK(cudaMalloc(&s->z, sizeof(double) * s->n));
   SKTB_CUDA_OK(cudaMalloc(&s->q, sizeof(double) * s->n));
-  SKTB_CUDA_OK(cudaMalloc(&s->p, sizeof(double) * s->n_global));
-  SKTB_CUDA_OK(cudaMemset(s->p, 0, sizeof(double) * s->n_global));
+  if (s->comm) {
+    if (dev_alloc_exchangeable(&s->p, (size_t)s->n_global)) return 1;
+  } else {
+    SKTB_CUDA_OK(cudaMalloc(&s->p, sizeof(double) * s->n_global));
+    SKTB_CUDA_OK(cudaMemset(s->p, 0, sizeof(double) * s->n_global));
+  }
   SKTB_CUDA_OK(cudaMalloc(&s->S, sizeof(PcgScalars)));
   SKTB_CUDA_OK(cudaMemset(s->S, 0, sizeof(PcgScalars)));
   SKTB_CUDA_OK(cudaMallocHost(&s->S_h, sizeof(PcgScalars)));
@@ -151,7 +155,7 @@ extern "C" void sktb_pcg_destroy(sktb_pcg *s) {
   cudaSetDevice(s->device);
   cudaFree(s->r);
   cudaFree(s->z);
-  cudaFree(s->p);
+  dev_free(s->p);
   cudaFree(s->q);
   if (s->Sloc != s->S) cudaFree(s->Sloc);
   cudaFree(s->S);
@@ -279,6 +283,10 @@ __global__ void __launch_bounds__(kBlock)
 int slab_halo_exchange(sktb_comm *c, double *v, int64_t own0, int64_t n_own,
                        int64_t plane, int prev, int next, cudaStream_t st) {
   if (!c || plane <= 0) return 0;
+  {
+    const int rc = comm_slab_halo_p2p(c, v, own0, n_own, plane, prev, next, st);
+    if (rc != -1) return rc;
+  }
   P2POp ops[2];
   int n = 0;
   if (prev >= 0) ops[n++] = {prev, v + own0, plane, v + own0 - plane, plane};

@@ -29,6 +29,8 @@ class Comm:
     def __init__(self, rank: int, world: int, device: int, unique_id: bytes):
         self.lib = _lib.load()
         self.rank, self.world, self.device = rank, world, device
+        self.unique_id = bytes(unique_id)
+        self.p2p = False
         h = C.c_void_p()
         buf = C.create_string_buffer(unique_id, 128)
         _lib.check(self.lib.sktb_comm_create(C.byref(h), C.cast(buf, C.c_void_p),
@@ -43,6 +45,41 @@ class Comm:
             except Exception:
                 pass
             self.handle = None
+
+    def setup_peer_arena(self):
+        """Symmetric arena for peer-memory halo exchanges (``csrc/comm.cuh``): NCCL
+        transport only (one GPU per rank).  ``SKTOPT_B200_P2P_HALO=0`` keeps the
+        ncclSend / ncclRecv exchange; ``SKTOPT_B200_ARENA_MB`` sizes the arena
+        (default 3072).  Every rank must succeed, else none uses it."""
+        import os
+        import torch.distributed as dist
+        self.p2p = False
+        if self.unique_id[:4] == b"SHM:" or os.environ.get("SKTOPT_B200_P2P_HALO", "1") == "0":
+            return
+        mb = int(os.environ.get("SKTOPT_B200_ARENA_MB", "3072"))
+        buf = C.create_string_buffer(64)
+        ok = self.lib.sktb_comm_arena_create(self.handle, C.c_int64(mb << 20),
+                                             C.cast(buf, C.c_void_p)) == 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (ok, buf.raw))
+        if not all(h[0] for h in handles):
+            return
+        cat = C.create_string_buffer(b"".join(h[1] for h in handles), 64 * self.world)
+        ok = self.lib.sktb_comm_arena_open(self.handle, C.cast(cat, C.c_void_p)) == 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        self.p2p = all(flags)
+        if not self.p2p:
+            raise RuntimeError("peer arenas could not be mapped on every rank "
+                               "(set SKTOPT_B200_P2P_HALO=0 to use NCCL send / recv)")
+
+    def arena_status(self):
+        """(bytes used, exchanges done, error flag) of the peer arena."""
+        used, epoch, err = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(self.lib.sktb_comm_arena_status(
+            self.handle, C.cast(C.byref(used), C.c_void_p), C.cast(C.byref(epoch), C.c_void_p),
+            C.cast(C.byref(err), C.c_void_p)))
+        return int(used.value), int(epoch.value), int(err.value)
 
     def allreduce_sum(self, src, dst=None):
         dst = src if dst is None else dst
@@ -97,6 +134,7 @@ def default_comm():
         box = [make_unique_id(transport()) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         _DEFAULT = Comm(rank, world, torch.cuda.current_device(), box[0])
+        _DEFAULT.setup_peer_arena()
     return _DEFAULT
 
 

@@ -94,6 +94,9 @@ SIGNATURES = {
     "sktb_comm_rank": [C.c_void_p],
     "sktb_comm_world": [C.c_void_p],
     "sktb_comm_allreduce_sum": [C.c_void_p, c_f64p, c_f64p, i64, c_stream],
+    "sktb_comm_arena_create": [C.c_void_p, i64, C.c_void_p],
+    "sktb_comm_arena_open": [C.c_void_p, C.c_void_p],
+    "sktb_comm_arena_status": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "sktb_comm_allgatherv": [C.c_void_p, c_f64p, C.c_void_p, C.c_void_p, c_stream],
     "sktb_pcg_create_dist": [C.POINTER(C.c_void_p), C.c_void_p, i64, i64, i64, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32],
     "sktb_pcg_set_profile": [C.c_void_p, i32],

@@ -345,6 +345,9 @@ class FeaEngine:
             counts = self.dpn * np.diff(self.cuts)
             displs = self.dpn * self.cuts[:-1]
             self.comm.allgatherv(x, counts, displs)
+            if getattr(self.comm, "p2p", False) and self.comm.arena_status()[2]:
+                raise RuntimeError("peer-memory halo exchange timed out waiting for a "
+                                   "neighbour rank (a rank died or stalled for > 60 s)")
         self.pcg_log.append((self.pcg.last_iters, self.pcg.last_converged,
                              self.pcg.last_relres))
         if not self.pcg.last_converged:

@@ -112,6 +112,10 @@ def main():
         ref = optim.run(pr, "oc", max_iters=4)
         rel = float(np.max(np.abs(comp - ref["compliance"]) / np.abs(ref["compliance"])))
         drho = float(np.max(np.abs(rho_fin.cpu().numpy() - ref["rho_final"])))
+        p2p = bool(getattr(eng.comm, "p2p", False))
+        arena = eng.comm.arena_status() if p2p else (0, 0, 0)
+        print(f"DIST_P2P p2p={p2p} arena_bytes={arena[0]} exchanges={arena[1]} err={arena[2]}")
+        assert arena[2] == 0
         print(f"DIST_RESULT world={world} slab={slab} sharded_mg_levels={n_sharded_levels} "
               f"err_u={err_u:.3e} err_c={err_c:.3e} rows_equal={rows_equal} "
               f"iters={iters_sharded}/{iters_single} filter_sharded={filter_sharded} "
