@@ -265,7 +265,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *p, unsigned
       atomicExch(err, 1u);
       return false;
     }
-    __nanosleep(200);
+    __nanosleep(40);
   }
   __threadfence_system();
   return true;
@@ -297,9 +297,19 @@ __global__ void __launch_bounds__(256)
       const int64_t off = side ? own0 + n_own : own0 - plane;
       const double *src = (side ? vnext : vprev) + off;
       double *dst = v + off;
+      // four independent loads in flight per thread: the copy is bound by the
+      // NVLink round trip (~2 us), not by bandwidth
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
-           i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __ldcv(src + i);
+           i += 4 * stride) {
+        double t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          t[k] = (i + k * stride < plane) ? __ldcv(src + i + k * stride) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + k * stride < plane) dst[i + k * stride] = t[k];
+      }
     }
     __syncthreads();
   }
@@ -477,8 +487,8 @@ int comm_slab_halo_p2p(sktb_comm *c, double *v, int64_t own0, int64_t n_own, int
   P2PFlags *fn = next >= 0 ? (P2PFlags *)a->peer[1] : nullptr;
   const double *vp = prev >= 0 ? (const double *)(a->peer[0] + off) : nullptr;
   const double *vn = next >= 0 ? (const double *)(a->peer[1] + off) : nullptr;
-  int grid = (int)((plane + 2047) / 2048);
-  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  int grid = (int)((plane + 1023) / 1024);  // 4 entries per thread in one pass
+  grid = grid < 1 ? 1 : (grid > 2 * sktb::kNumSM ? 2 * sktb::kNumSM : grid);
   p2p_halo_kernel<<<grid, 256, 0, st>>>(mine, fp, fn, e, v, vp, vn, own0, n_own, plane);
   SKTB_KERNEL_OK();
   return 0;

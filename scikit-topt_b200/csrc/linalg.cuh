@@ -97,3 +97,15 @@ int pcg_allreduce_vec(sktb_pcg *s, double *buf, int64_t n, cudaStream_t st);
 // previous and the next rank (-1: none), straight from / into the vector.
 int slab_halo_exchange(sktb_comm *c, double *v, int64_t own0, int64_t n_own,
                        int64_t plane, int prev, int next, cudaStream_t st);
+
+// Phase timing of the sharded solve (SKTB_PHASE_PROF=1): CUDA events at the phase
+// boundaries of every PCG iteration / V-cycle, summed per phase over a solve and
+// printed by rank 0 when the solve ends (profiles/r2_phase_*.txt).  Off: no cost.
+enum PhaseId {
+  PH_HALO_P = 0, PH_SPMV, PH_AR_PQ, PH_UPDATE, PH_VC_L0, PH_VC_HALO, PH_VC_L1, PH_VC_TRANS,
+  PH_VC_COARSE, PH_VC_UP1, PH_VC_UP0, PH_RZ, PH_AR_RZ, PH_DIR, PH_COUNT
+};
+void phase_mark(int id, cudaStream_t st);   // the time since the previous mark goes to `id`
+void phase_begin(cudaStream_t st);
+void phase_report(int rank, int iters);
+bool phase_on();

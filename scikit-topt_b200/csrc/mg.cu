@@ -1126,7 +1126,11 @@ static int level_restrict(MgLevel &l, MgLevel &c, const double *b, sktb_pcg *dis
   SKTB_COUNT(1);
   // sharded fine level, replicated coarse level: every rank summed its own fine
   // rows into the whole coarse vector
-  if (part && !c.sharded && dist && pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st)) return 1;
+  if (part && !c.sharded && dist) {
+    phase_mark(l.gop || l.node0 >= 0 ? (l.sharded && l.vals ? PH_VC_L1 : PH_VC_L0) : PH_VC_L0, st);
+    if (pcg_allreduce_vec(dist, c.b, 3 * c.n_nodes, st)) return 1;
+    phase_mark(PH_VC_TRANS, st);
+  }
   return 0;
 }
 
@@ -1201,8 +1205,10 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       if (level_halo(l, l.x, dist, st)) return 1;
       if (level_spmv(l, l.x, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
       if (level_restrict(l, m->lv[k + 1], b, dist, st)) return 1;
+      phase_mark(k == 0 ? PH_VC_L0 : (l.sharded ? PH_VC_L1 : PH_VC_COARSE), st);
     }
   }
+  phase_mark(PH_VC_COARSE, st);
   // upward sweep
   bool z_done = false;
   for (int k = (k_tail < L ? k_tail - 1 : L - 2); k >= 0; --k) {
@@ -1241,7 +1247,10 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     if (level_halo(l, l.x, dist, st)) return 1;
     if (k > 0 && m->fused_sweeps) {  // last post-smoothing sweep
       const int rc = level_sweep(l, b, om, st);
-      if (rc == 0) continue;
+      if (rc == 0) {
+        phase_mark(l.sharded ? PH_VC_UP1 : PH_VC_COARSE, st);
+        continue;
+      }
       if (rc != -1) return rc;
     }
     if (k == 0 && l.gop) {
@@ -1250,6 +1259,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
                                        b, l.inv_diag, om, st);
       if (rc == 0) {
         z_done = true;
+        phase_mark(PH_VC_UP0, st);
         continue;
       }
       if (rc != -1) return rc;

@@ -13,6 +13,7 @@
 // direction p is a full-length vector on every rank; before each SpMV the
 // entries other ranks need are packed, exchanged with grouped ncclSend/ncclRecv
 // and scattered into the ghost slots of p.  Matrix column indices stay global.
+#include <cstdlib>
 #include <vector>
 
 #include "comm.cuh"
@@ -419,6 +420,62 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// ------------------------------------------------------------ phase timing --
+namespace {
+struct PhaseProf {
+  bool on = false, init = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> id;
+  size_t n = 0;
+} g_ph;
+}  // namespace
+bool phase_on() {
+  if (!g_ph.init) {
+    g_ph.init = true;
+    const char *e = getenv("SKTB_PHASE_PROF");
+    g_ph.on = e && e[0] == '1';
+  }
+  return g_ph.on;
+}
+void phase_begin(cudaStream_t st) {
+  if (!phase_on()) return;
+  g_ph.n = 0;
+  phase_mark(-1, st);
+}
+void phase_mark(int id, cudaStream_t st) {
+  if (!phase_on()) return;
+  if (g_ph.n == g_ph.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_ph.ev.push_back(e);
+    g_ph.id.push_back(0);
+  }
+  g_ph.id[g_ph.n] = id;
+  cudaEventRecord(g_ph.ev[g_ph.n++], st);
+}
+void phase_report(int rank, int iters) {
+  if (!phase_on() || g_ph.n < 2) return;
+  static const char *names[PH_COUNT] = {
+      "halo(p)", "A p (+p.q)", "allreduce p.q", "update x,r", "V: level-0 down", "V: halos",
+      "V: level-1 (sharded levels >= 1)", "V: transition allreduce", "V: replicated coarse levels",
+      "V: level-1 up", "V: level-0 up", "r.z", "allreduce r.z,||r||", "direction p"};
+  double sum[PH_COUNT] = {0};
+  for (size_t i = 1; i < g_ph.n; ++i) {
+    if (g_ph.id[i] < 0) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ph.ev[i - 1], g_ph.ev[i]) == cudaSuccess) sum[g_ph.id[i]] += ms;
+  }
+  if (rank != 0) return;
+  double tot = 0;
+  for (int k = 0; k < PH_COUNT; ++k) tot += sum[k];
+  fprintf(stderr, "[phase] solve of %d iterations, %.3f ms in marked phases (%.3f ms / iteration)\n",
+          iters, tot, iters ? tot / iters : 0.0);
+  for (int k = 0; k < PH_COUNT; ++k)
+    if (sum[k] > 0)
+      fprintf(stderr, "[phase]   %-36s %8.3f ms  %5.1f %%  %7.1f us/it\n", names[k], sum[k],
+              100 * sum[k] / tot, iters ? 1e3 * sum[k] / iters : 0.0);
+}
+
 static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
                    const double *b, double *x, int use_x0, double rtol,
                    int maxiter, int check_every, int32_t *info_h,
@@ -465,6 +522,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
   }
   int launched = 0;
   int n_ev = 0;
+  phase_begin(st);
   while (true) {
     SKTB_CUDA_OK(cudaMemcpyAsync(s->S_h, s->S, sizeof(PcgScalars),
                                  cudaMemcpyDeviceToHost, st));
@@ -493,6 +551,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
     if (batch > check_every) batch = check_every;
     for (int it = 0; it < batch; ++it) {
       if (halo_exchange(s, s->p, st)) return 1;
+      phase_mark(PH_HALO_P, st);
       // sample only the first iteration of a batch: it is certain to do work
       const bool sample = s->prof_every > 0 && it == 0 &&
                           ((launched / check_every) % s->prof_every == 0) &&
@@ -501,10 +560,13 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
       if (apply_mat(A, n, s->p, s->q, p_own, &rs, &s->Sloc->pq, s->S, st))
         return 1;
       if (sample) SKTB_CUDA_OK(cudaEventRecord(s->ev1[n_ev++], st));
+      phase_mark(PH_SPMV, st);
       if (reduce_scalars(s, &s->Sloc->pq, &s->S->pq, 1, st)) return 1;
+      phase_mark(PH_AR_PQ, st);
       pcg_update_kernel<<<vgrid, kBlock, 0, st>>>(n, p_own, s->q, inv_diag, x,
                                                  s->r, s->z, s->partials,
                                                  s->ticket, s->Sloc, s->S);
+      phase_mark(PH_UPDATE, st);
       if (mg) {
         // one all-reduce for (r.z, ||r||^2) after the V-cycle instead of one on
         // each side of it: until then the kernels of the V-cycle see the previous
@@ -513,16 +575,20 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
         pcg_rz_kernel<<<vgrid, kBlock, 0, st>>>(n, s->r, s->z, 0, s->partials,
                                                s->ticket, s->Sloc, s->S);
         SKTB_COUNT(1);
+        phase_mark(PH_RZ, st);
       }
       if (reduce_scalars(s, &s->Sloc->rz_new, &s->S->rz_new, 2, st)) return 1;
+      phase_mark(PH_AR_RZ, st);
       pcg_direction_kernel<<<vgrid, kBlock, 0, st>>>(n, s->z, p_own, s->ticket,
                                                     s->S);
       SKTB_COUNT(2);
+      phase_mark(PH_DIR, st);
     }
     SKTB_KERNEL_CHECK();
     launched += batch;
   }
   const PcgScalars &h = *s->S_h;
+  if (mg && phase_on()) phase_report(s->comm ? s->comm->rank : 0, launched);
   if (info_h) {
     info_h[0] = h.iters;
     info_h[1] = (h.rr <= h.tol2) ? 1 : 0;

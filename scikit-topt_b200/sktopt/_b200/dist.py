@@ -48,13 +48,17 @@ class Comm:
 
     def setup_peer_arena(self):
         """Symmetric arena for peer-memory halo exchanges (``csrc/comm.cuh``): NCCL
-        transport only (one GPU per rank).  ``SKTOPT_B200_P2P_HALO=0`` keeps the
-        ncclSend / ncclRecv exchange; ``SKTOPT_B200_ARENA_MB`` sizes the arena
-        (default 3072).  Every rank must succeed, else none uses it."""
+        transport only (one GPU per rank), opt-in with ``SKTOPT_B200_P2P_HALO=1``.
+        Measured on 4 x B200 (C5, profiles/r2_bench_4gpu*.json): 80.8 ms / step with
+        the peer-memory pulls against 77.3 ms with grouped ncclSend / ncclRecv -- the
+        publish / pull / acknowledge handshake costs two NVLink round trips per
+        exchange, NCCL's FIFO one -- so NCCL stays the default.
+        ``SKTOPT_B200_ARENA_MB`` sizes the arena (default 3072).  Every rank must
+        succeed, else none uses it."""
         import os
         import torch.distributed as dist
         self.p2p = False
-        if self.unique_id[:4] == b"SHM:" or os.environ.get("SKTOPT_B200_P2P_HALO", "1") == "0":
+        if self.unique_id[:4] == b"SHM:" or os.environ.get("SKTOPT_B200_P2P_HALO", "0") != "1":
             return
         mb = int(os.environ.get("SKTOPT_B200_ARENA_MB", "3072"))
         buf = C.create_string_buffer(64)

@@ -24,6 +24,8 @@ def test_sharded_solve_and_loop(world, shard_min):
     env["SKTOPT_B200_MG_SHARD_MIN"] = str(shard_min)
     if torch.cuda.device_count() < world:
         env["SKTOPT_DIST_ONE_GPU"] = "1"
+    elif shard_min == 300:
+        env["SKTOPT_B200_P2P_HALO"] = "1"     # one GPU per rank: cover the peer-memory halos too
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + world + (1 if shard_min > 10**6 else 0) * 10),
