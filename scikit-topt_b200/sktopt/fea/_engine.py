@@ -148,6 +148,8 @@ class FeaEngine:
         self.u_hist = {}
         self._hist_pool = {}
         self._proj_tmp = []
+        self._pcg_pool, self._stream_pool = [], []   # concurrent load cases (solve_many)
+        self._rhs_pool = []
         self.pcg_log = []  # (iters, converged, relres) of every solve
 
     @property
@@ -231,6 +233,13 @@ class FeaEngine:
                 self.smg.setup(self.row_ptr, self.col_idx, v)
         if self.mg is not None and self.mg_enabled and vals is None:
             self.mg.setup()
+
+    def rhs_slot(self, load: int):
+        """Right-hand side buffer of one load case (multi-load problems keep all of
+        them alive at once)."""
+        while len(self._rhs_pool) <= load:
+            self._rhs_pool.append(torch.empty(self.n_dof, dtype=dev.F64, device="cuda"))
+        return self._rhs_pool[load]
 
     def solution(self, load: int):
         if load not in self.u:
@@ -339,6 +348,76 @@ class FeaEngine:
                            rhs[lo:hi], x[lo:hi], dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
                            use_x0=True, check_every=32, block3=True, max_deg=self.max_deg)
         return self._finish_solve(x, rtol)
+
+    def solve_many(self, rhs_list, rtol: float, maxiter: int | None):
+        """One solve per right-hand side (load case) on the current operator.
+        Returns the solutions (``self.solution(i)``).
+
+        On one GPU with the Jacobi-preconditioned assembled operator (unstructured
+        meshes: BASELINE config 3) the load cases run CONCURRENTLY, one CUDA stream
+        and one PCG workspace per load driven by its own host thread: such a solve
+        is a chain of small dependent launches on an L2-resident operator, so two
+        of them overlap almost perfectly.  (The reference solves all loads against
+        one LU factorisation, ``fea/solver_elastic.py:386-390``.)  Everything else
+        (multigrid, matrix-free, sharded) solves them one after the other."""
+        n = len(rhs_list)
+        concurrent = (n > 1 and not self.sharded and not self.matrix_free
+                      and not (self.mg is not None and self.mg_enabled)
+                      and not (self.smg is not None and self.mg_enabled)
+                      and os.environ.get("SKTOPT_B200_CONCURRENT_LOADS", "1") != "0")
+        if not concurrent:
+            return [self.solve(b, i, rtol, maxiter) for i, b in enumerate(rhs_list)]
+        import threading
+        xs = [self.solution(i) for i in range(n)]
+        for i, b in enumerate(rhs_list):            # host-synchronous: one after the other
+            self._project_start(b, i, xs[i])
+        while len(self._pcg_pool) < n - 1:
+            self._pcg_pool.append(dev.PcgSolver(self.n_dof))
+            self._stream_pool.append(torch.cuda.Stream())
+        pcgs = [self.pcg] + self._pcg_pool[:n - 1]
+        mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
+        block3 = self.spmv_format == "bsr3"
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        errors = [None] * n
+
+        def work(i):
+            try:
+                st = main if i == 0 else self._stream_pool[i - 1]
+                with torch.cuda.stream(st):
+                    st.wait_event(ready)
+                    pcgs[i].solve(self.node_ptr_loc if block3 else self.row_ptr,
+                                  self.node_col_loc if block3 else self.col_idx,
+                                  self.vals, self.inv_diag, rhs_list[i], xs[i],
+                                  dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
+                                  use_x0=self.warm_start, check_every=32, block3=block3,
+                                  max_deg=getattr(self, "max_deg", 0))
+            except Exception as e:                    # re-raised on the caller's thread
+                errors[i] = e
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(1, n)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        for i in range(1, n):
+            main.wait_stream(self._stream_pool[i - 1])
+        for e in errors:
+            if e is not None:
+                raise e
+        for i in range(n):
+            self.pcg_log.append((pcgs[i].last_iters, pcgs[i].last_converged, pcgs[i].last_relres))
+            if not pcgs[i].last_converged:
+                msg = (f"PCG (load {i}) stopped at {pcgs[i].last_iters} iterations with "
+                       f"relres={pcgs[i].last_relres:.3e} (rtol={rtol:g})")
+                far = (not np.isfinite(pcgs[i].last_relres)
+                       or pcgs[i].last_relres > 100.0 * rtol)
+                if far and os.environ.get("SKTOPT_B200_STRICT_SOLVE", "1") != "0":
+                    raise RuntimeError(msg)
+                logger.warning(msg)
+        return xs
 
     def _finish_solve(self, x, rtol):
         if self.sharded:

@@ -116,11 +116,15 @@ def _run_loads(basis, dirichlet_dofs, force_list, E0, Emin, p, nu0, rho, u_all,
     n_loads = len(force_list)
     comp = np.empty(n_loads)
     with _section(timer, "solve"):
+        rhs = []
         for i, f in enumerate(force_list):
             f_d = f if _is_dev(f) else dev.to_dev(f)
-            dev.enforce_rhs(f_d, None, eng.dir_mask, None, out=eng.rhs)
-            u = eng.solve(eng.rhs, i, solver_cfg.rtol, solver_cfg.maxiter)
-            comp[i] = dev.dot(eng.rhs, u)
+            b = eng.rhs if n_loads == 1 else eng.rhs_slot(i)
+            dev.enforce_rhs(f_d, None, eng.dir_mask, None, out=b)
+            rhs.append(b)
+        us = eng.solve_many(rhs, solver_cfg.rtol, solver_cfg.maxiter)
+        for i, u in enumerate(us):
+            comp[i] = dev.dot(rhs[i], u)
             if u_all is not None:
                 if _is_dev(u_all):
                     (u_all[:, i] if u_all.ndim == 2 else u_all).copy_(u)
