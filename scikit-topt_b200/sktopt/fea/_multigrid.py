@@ -142,6 +142,59 @@ def chebyshev_coefficients(lam_max: float, lam_min: float, degree: int):
     return c1, c2
 
 
+def plan_slab_sharding(coords, plane_cuts0, world: int, rank: int, shard_min: int):
+    """z-slab ownership of every multigrid level, pure host logic.
+
+    ``coords[l]`` = (xs, ys, zs) node coordinates of level l; ``plane_cuts0`` = the
+    world+1 node-plane boundaries of level 0.  A coarse plane belongs to the rank
+    that owns the coincident fine plane.  Assembled levels with at least
+    ``shard_min`` nodes (and >= 2 planes on every rank) are sharded: a rank stores
+    the rows of its planes and computes the Galerkin element matrices of its slab
+    only (plus the element planes the coarser levels' products need).  The first
+    replicated level gets its element matrices from slab-wise products that are
+    all-gathered (an even split of its element planes).
+
+    Returns (shard, first_replicated, gather_plan, plane_cuts): ``shard[l]`` is
+    None (level 0 and replicated levels) or a dict with the owned node range
+    [node0, node1), ``plane`` nodes per plane, ``prev`` / ``next`` ranks and the
+    element range [elem0, elem1) whose matrices the rank computes."""
+    L = len(coords)
+    shard = [None] * L
+    zc = [np.asarray(plane_cuts0, dtype=np.int64)]           # plane cuts per level
+    for l in range(1, L):
+        nz_f = coords[l - 1][2].size - 1
+        fmap = coarse_index_map(nz_f)                        # fine plane of coarse plane
+        owner = np.searchsorted(zc[-1], fmap, side="right") - 1
+        zc.append(np.searchsorted(owner, np.arange(world + 1), side="left").astype(np.int64))
+    last = 0
+    for l in range(1, L - 1):
+        xs, ys, zs = coords[l]
+        if xs.size * ys.size * zs.size < shard_min or np.diff(zc[l]).min() < 2:
+            break
+        last = l
+    if last == 0:
+        return shard, 1, None, zc
+    lr = last + 1
+    cz_lr = coords[lr][2].size - 1
+    a = np.round(np.linspace(0, cz_lr, world + 1)).astype(np.int64)
+    plane_e = lambda l: (coords[l][0].size - 1) * (coords[l][1].size - 1)
+    gather_plan = dict(level=lr, cuts=a, plane_elems=plane_e(lr))
+    need_lo, need_hi = int(a[rank]), int(a[rank + 1])
+    for l in range(last, 0, -1):
+        cz = coords[l][2].size - 1
+        z0, z1 = int(zc[l][rank]), int(zc[l][rank + 1])
+        lo, hi = max(z0 - 1, 0), min(z1, cz)                 # element planes touching my nodes
+        if need_hi > need_lo:                                # + the children of what level l+1 needs
+            lo, hi = min(lo, 2 * need_lo), max(hi, min(2 * need_hi, cz))
+        npl = coords[l][0].size * coords[l][1].size
+        shard[l] = dict(node0=z0 * npl, node1=z1 * npl, plane=npl,
+                        prev=rank - 1 if rank > 0 else -1,
+                        next=rank + 1 if rank < world - 1 else -1,
+                        elem0=lo * plane_e(l), elem1=hi * plane_e(l))
+        need_lo, need_hi = lo, hi
+    return shard, lr, gather_plan, zc
+
+
 class Multigrid:
     """Grid hierarchy + Galerkin set-up for one elasticity engine."""
 
@@ -273,59 +326,17 @@ class Multigrid:
     SHARD_MIN_NODES = 300000
 
     def _plan_sharding(self):
-        """z-slab ownership of every level.  Level 0 follows the
-        engine's node range; a coarse plane belongs to the rank that owns the
-        coincident fine plane.  Assembled levels with at least
-        ``SKTOPT_B200_MG_SHARD_MIN`` nodes (and >= 2 planes on every rank) are
-        sharded: a rank stores the rows of its planes and computes the Galerkin
-        element matrices of its slab only.  The first replicated level gets its
-        element matrices from slab-wise products that are all-gathered."""
+        """z-slab ownership of every level: see ``plan_slab_sharding``."""
         eng = self.eng
-        L = self.n_levels
-        self.shard = [None] * L
+        self.shard = [None] * self.n_levels
         self.first_replicated = 1
         self.gather_plan = None
         comm = eng.comm
         if comm is None or getattr(eng, "plane_cuts", None) is None:
             return
-        world, rank = comm.world, comm.rank
         shard_min = int(os.environ.get("SKTOPT_B200_MG_SHARD_MIN", self.SHARD_MIN_NODES))
-        zc = [np.asarray(eng.plane_cuts, dtype=np.int64)]   # plane cuts per level
-        for l in range(1, L):
-            nz_f = self.coords[l - 1][2].size - 1
-            fmap = coarse_index_map(nz_f)                    # fine plane of coarse plane
-            owner = np.searchsorted(zc[-1], fmap, side="right") - 1
-            zc.append(np.searchsorted(owner, np.arange(world + 1), side="left").astype(np.int64))
-        self.plane_cuts = zc
-        last = 0
-        for l in range(1, L - 1):
-            xs, ys, zs = self.coords[l]
-            if xs.size * ys.size * zs.size < shard_min or np.diff(zc[l]).min() < 2:
-                break
-            last = l
-        self.first_replicated = last + 1
-        if last == 0:
-            return
-        # element planes whose matrices this rank needs, from the coarsest
-        # sharded level upwards; the first replicated level is split evenly for
-        # the all-gather of its element matrices
-        lr = self.first_replicated
-        cz_lr = self.coords[lr][2].size - 1
-        a = np.round(np.linspace(0, cz_lr, world + 1)).astype(np.int64)
-        plane_e = lambda l: (self.coords[l][0].size - 1) * (self.coords[l][1].size - 1)
-        self.gather_plan = dict(level=lr, cuts=a, plane_elems=plane_e(lr))
-        need_lo, need_hi = int(a[rank]), int(a[rank + 1])
-        for l in range(last, 0, -1):
-            cz = self.coords[l][2].size - 1
-            z0, z1 = int(zc[l][rank]), int(zc[l][rank + 1])
-            lo = min(max(z0 - 1, 0), 2 * need_lo) if need_hi > need_lo else max(z0 - 1, 0)
-            hi = max(min(z1, cz), min(2 * need_hi, cz)) if need_hi > need_lo else min(z1, cz)
-            npl = self.coords[l][0].size * self.coords[l][1].size
-            self.shard[l] = dict(node0=z0 * npl, node1=z1 * npl, plane=npl,
-                                 prev=rank - 1 if rank > 0 else -1,
-                                 next=rank + 1 if rank < world - 1 else -1,
-                                 elem0=lo * plane_e(l), elem1=hi * plane_e(l))
-            need_lo, need_hi = lo, hi
+        self.shard, self.first_replicated, self.gather_plan, self.plane_cuts = \
+            plan_slab_sharding(self.coords, eng.plane_cuts, comm.world, comm.rank, shard_min)
 
     def __del__(self):
         h = getattr(self, "handle", None)

@@ -109,3 +109,52 @@ def test_chebyshev_coefficients_reproduce_the_polynomial():
     sigma = (lmax + lmin) / (lmax - lmin)
     bound = 1.0 / np.cosh(deg * np.arccosh(sigma))
     assert err.max() <= bound * (1.0 + 1e-9)
+
+
+def test_slab_sharding_plan_covers_what_every_rank_needs():
+    """plan_slab_sharding (host logic of the sharded multigrid set-up): ownership is
+    a partition by whole planes on every level, every element matrix a rank needs
+    -- for the rows it assembles, for its share of the gathered level and for the
+    Galerkin products of the coarser sharded levels -- lies in its element range."""
+    from sktopt._b200.dist import partition_planes
+    from sktopt.fea._multigrid import child_tables, coarse_index_map, plan_slab_sharding
+    for cells, world in (((20, 14, 33), 2), ((17, 9, 40), 3), ((12, 10, 64), 4), ((8, 6, 97), 8)):
+        coords = [tuple(np.linspace(0, 1, n + 1) for n in cells)]
+        while max(c.size - 1 for c in coords[-1]) > 2:
+            coords.append(tuple(a[coarse_index_map(a.size - 1)] for a in coords[-1]))
+        cuts0 = partition_planes(cells[2] + 1, world)
+        plans = [plan_slab_sharding(coords, cuts0, world, r, 300) for r in range(world)]
+        first_rep = plans[0][1]
+        assert first_rep >= 2, (cells, world)              # at least level 1 is sharded here
+        for l in range(1, first_rep):
+            npl = coords[l][0].size * coords[l][1].size
+            n_nodes = npl * coords[l][2].size
+            ranges = [(p[0][l]["node0"], p[0][l]["node1"]) for p in plans]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_nodes
+            assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+            assert all((b - a) % npl == 0 and (b - a) >= 2 * npl for a, b in ranges)
+        for r, (shard, lr, gp, zc) in enumerate(plans):
+            assert lr == first_rep and gp["level"] == lr
+            assert gp["cuts"][0] == 0 and gp["cuts"][-1] == coords[lr][2].size - 1
+            # element planes needed on the gathered level -> children on the level below, ...
+            need = set(range(int(gp["cuts"][r]), int(gp["cuts"][r + 1])))
+            for l in range(lr - 1, 0, -1):
+                cx, cy, cz = (c.size - 1 for c in coords[l])
+                pe = cx * cy
+                sh = shard[l]
+                e_lo, e_hi = sh["elem0"] // pe, sh["elem1"] // pe
+                assert sh["elem0"] % pe == 0 and sh["elem1"] % pe == 0
+                children = {z for E in need for z in (2 * E, 2 * E + 1) if z < cz}
+                z0, z1 = sh["node0"] // sh["plane"], sh["node1"] // sh["plane"]
+                touching = {z for z in range(cz) if z + 1 >= z0 and z < z1}   # nodes z, z+1
+                assert children | touching <= set(range(e_lo, e_hi)), (cells, world, r, l)
+                need = set(range(e_lo, e_hi))
+        # child tables agree with the "2E, 2E+1" rule used above
+        fine = tuple(c.size - 1 for c in coords[0])
+        coarse = tuple(c.size - 1 for c in coords[1])
+        child, _ = child_tables(fine, coarse)
+        ez_c = np.arange(child.shape[1]) // (coarse[0] * coarse[1])
+        for ch in range(8):
+            ok = child[ch] >= 0
+            ez_f = child[ch][ok] // (fine[0] * fine[1])
+            assert np.all((ez_f == 2 * ez_c[ok]) | (ez_f == 2 * ez_c[ok] + 1))
