@@ -375,6 +375,8 @@ int sktb_comm_allgatherv(sktb_comm *c, double *buf, const int64_t *counts_h,
  * indices received from it (ghost slots of the full-length direction vector).
  * sktb_pcg_solve then takes local row_ptr/vals/inv_diag/b/x and global col_idx;
  * dot products are all-reduced in the stream (2 all-reduces per iteration).    */
+/* first host poll of the next solve after n iterations (then every check_every) */
+int sktb_pcg_set_first_batch(sktb_pcg *s, int n);
 /* z-slab halo of a row-sharded PCG on a tensor grid: whole planes of plane_dofs
  * entries exchanged with prev_rank / next_rank (-1: none) straight from / into
  * the full-length vectors, instead of the packed index lists                   */

@@ -44,6 +44,8 @@ struct sktb_pcg {
   // index lists above when plane > 0
   int64_t slab_plane = 0;
   int slab_prev = -1, slab_next = -1;
+  // iterations to run before the first host poll of the NEXT solve (0: check_every)
+  int first_batch = 0;
   // in-situ SpMV timing
   int prof_every = 0;
   static constexpr int kMaxProf = 64;
@@ -294,6 +296,17 @@ int slab_halo_exchange(sktb_comm *c, double *v, int64_t own0, int64_t n_own,
   if (next >= 0)
     ops[n++] = {next, v + own0 + n_own - plane, plane, v + own0 + n_own, plane};
   return comm_p2p(c, n, ops, st);
+}
+
+// The host polls the convergence flag every `check_every` iterations; a caller
+// that knows how many iterations the previous, similar solve took can ask for
+// the first poll to happen only after `n` iterations (one solve, then reset):
+// fewer pipeline drains, and with check_every = 1 afterwards no V-cycle runs
+// past convergence.
+extern "C" int sktb_pcg_set_first_batch(sktb_pcg *s, int n) {
+  SKTB_REQUIRE(s && n >= 0, "bad argument");
+  s->first_batch = n;
+  return 0;
 }
 
 extern "C" int sktb_pcg_set_slab_halo(sktb_pcg *s, int64_t plane_dofs, int prev_rank,
@@ -548,7 +561,8 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
     }
     if (s->S_h->rr <= s->S_h->tol2 || launched >= maxiter) break;
     int batch = maxiter - launched;
-    if (batch > check_every) batch = check_every;
+    const int want = (launched == 0 && s->first_batch > 0) ? s->first_batch : check_every;
+    if (batch > want) batch = want;
     for (int it = 0; it < batch; ++it) {
       if (halo_exchange(s, s->p, st)) return 1;
       phase_mark(PH_HALO_P, st);
@@ -587,6 +601,7 @@ static int pcg_run(sktb_pcg *s, const PcgMat &A, const double *inv_diag,
     SKTB_KERNEL_CHECK();
     launched += batch;
   }
+  s->first_batch = 0;
   const PcgScalars &h = *s->S_h;
   if (mg && phase_on()) phase_report(s->comm ? s->comm->rank : 0, launched);
   if (info_h) {

@@ -488,6 +488,10 @@ class PcgSolver:
         _lib.check(self.lib.sktb_pcg_set_slab_halo(self.handle, int(plane_dofs),
                                                    int(prev_rank), int(next_rank)))
 
+    def set_first_batch(self, n: int):
+        """First convergence poll of the next solve after ``n`` iterations."""
+        _lib.check(self.lib.sktb_pcg_set_first_batch(self.handle, int(max(n, 0))))
+
     def set_profile(self, every_n: int):
         _lib.check(self.lib.sktb_pcg_set_profile(self.handle, int(every_n)))
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "sktb_elem_restrict_range": [i64, i64, i64, i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_combine_range": [i64, i64, i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_set_slab_halo": [C.c_void_p, i64, i32, i32],
+    "sktb_pcg_set_first_batch": [C.c_void_p, i32],
     "sktb_element_stress": [C.c_void_p, i32, c_i32p, c_f64p, c_f64p, f64, c_f64p, c_f64p, c_stream],
     "sktb_dgemm_batched": [i32, i32, i32, c_f64p, i32, i64, c_f64p, i32, i64, c_f64p, i32, i64, i32, c_f64p, i64, c_stream],
     "sktb_smg_create": [C.POINTER(C.c_void_p), i32, C.c_void_p, i32],

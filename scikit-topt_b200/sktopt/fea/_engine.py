@@ -150,6 +150,7 @@ class FeaEngine:
         self._proj_tmp = []
         self._pcg_pool, self._stream_pool = [], []   # concurrent load cases (solve_many)
         self._rhs_pool = []
+        self._last_iters = {}    # load -> iterations of its previous multigrid solve
         self.pcg_log = []  # (iters, converged, relres) of every solve
 
     @property
@@ -314,10 +315,18 @@ class FeaEngine:
         use_mg = self.mg is not None and self.mg_enabled and vals is None
         mi_first = min(mi, 400) if use_mg else mi
         if self.matrix_free and vals is None:
+            if use_mg:
+                # poll where the previous solve of this load converged (minus one),
+                # then after every iteration: no V-cycle runs past convergence and
+                # the pipeline drains 2-4 times per solve instead of every 2 iterations
+                prev = self._last_iters.get(load, 0)
+                self.pcg.set_first_batch(max(prev - 1, 2))
             self.pcg.solve_grid(self.gridop, self.inv_diag, rhs[lo:hi], x[lo:hi], rtol=rtol,
                                 maxiter=mi_first, use_x0=self.warm_start,
-                                check_every=2 if use_mg else 32,
+                                check_every=1 if use_mg else 32,
                                 mg=self.mg if use_mg else None)
+            if use_mg:
+                self._last_iters[load] = self.pcg.last_iters
             if use_mg and not self.pcg.last_converged:
                 logger.warning("multigrid PCG did not converge; continuing with Jacobi PCG")
                 self.pcg.solve_grid(self.gridop, self.inv_diag, rhs[lo:hi], x[lo:hi], rtol=rtol,
