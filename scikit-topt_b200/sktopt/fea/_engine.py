@@ -151,6 +151,7 @@ class FeaEngine:
         self._pcg_pool, self._stream_pool = [], []   # concurrent load cases (solve_many)
         self._rhs_pool = []
         self._last_iters = {}    # load -> iterations of its previous multigrid solve
+        self._setup_stream, self._mg_ready = None, None
         self.pcg_log = []  # (iters, converged, relres) of every solve
 
     @property
@@ -198,6 +199,7 @@ class FeaEngine:
 
     # ------------------------------------------------------------------
     def set_modulus(self, rho, c_max, c_min, p, ramp=False):
+        self._wait_mg()        # a set-up still running on the side stream reads self.scale
         dev.interpolate_modulus(rho, c_max, c_min, p, ramp=ramp, out=self.scale)
         return self.scale
 
@@ -222,7 +224,7 @@ class FeaEngine:
             self.gridop.set_scale(self.scale)
             self.gridop.inv_diag(self.node0, self.node1 - self.node0, out=self.inv_diag)
             if self.mg is not None and self.mg_enabled:
-                self.mg.setup()
+                self._mg_setup()
             return
         v = self.vals if vals is None else vals
         if self.dpn == 3:
@@ -234,6 +236,34 @@ class FeaEngine:
                 self.smg.setup(self.row_ptr, self.col_idx, v)
         if self.mg is not None and self.mg_enabled and vals is None:
             self.mg.setup()
+
+    def _mg_setup(self):
+        """Galerkin set-up of the multigrid hierarchy.  On one GPU (after the first
+        set-up, which also measures the smoother damping) it runs on a second
+        stream: the ~2 ms chain of small kernels overlaps the start-vector
+        projection of the first load (operator products + host-read dots on the main
+        stream); ``solve`` waits for it before the first V-cycle.
+        ``SKTOPT_B200_MG_ASYNC_SETUP=0`` keeps everything on one stream."""
+        self._mg_ready = None
+        if (self.sharded or self.mg.setup_count == 0
+                or os.environ.get("SKTOPT_B200_MG_ASYNC_SETUP", "1") == "0"):
+            self.mg.setup()
+            return
+        if self._setup_stream is None:
+            self._setup_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        with torch.cuda.stream(self._setup_stream):
+            self._setup_stream.wait_event(start)
+            self.mg.setup()
+            self._mg_ready = torch.cuda.Event()
+            self._mg_ready.record(self._setup_stream)
+
+    def _wait_mg(self):
+        if self._mg_ready is not None:
+            torch.cuda.current_stream().wait_event(self._mg_ready)
+            self._mg_ready = None
 
     def rhs_slot(self, load: int):
         """Right-hand side buffer of one load case (multi-load problems keep all of
@@ -316,6 +346,7 @@ class FeaEngine:
         mi_first = min(mi, 400) if use_mg else mi
         if self.matrix_free and vals is None:
             if use_mg:
+                self._wait_mg()
                 # poll where the previous solve of this load converged (minus one),
                 # then after every iteration: no V-cycle runs past convergence and
                 # the pipeline drains 2-4 times per solve instead of every 2 iterations
@@ -340,6 +371,7 @@ class FeaEngine:
             if self.pcg.last_converged:
                 return self._finish_solve(x, rtol)
             logger.warning("scalar multigrid PCG did not converge; continuing with Jacobi PCG")
+        self._wait_mg()
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,

@@ -514,6 +514,9 @@ class Multigrid:
     def vcycle(self, r, z=None):
         if z is None:
             z = torch.empty_like(r)
+        wait = getattr(self.eng, "_wait_mg", None)
+        if wait is not None:
+            wait()                 # a set-up running on the engine's side stream
         _lib.check(self.lib.sktb_mg_vcycle(self.handle, dev._ptr(r), dev._ptr(z), dev._stream()))
         return z
 
