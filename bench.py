@@ -312,7 +312,10 @@ def run_b200(args):
         out_h.copy_(st.rho, non_blocking=True)          # D2H of the step's result
         torch.cuda.synchronize()
         comp_last = float(st.compliance)
-        rho_h.copy_(out_h)
+        # the result buffer is the next step's input buffer (no host-side copy: a
+        # multi-threaded torch CPU copy leaves its OpenMP workers spinning on the
+        # cores the solver's host threads need, measured +2 ms on the next step)
+        rho_h, out_h = out_h, rho_h
     ev1.record()
     barrier()
     t_e2e_wall = time.perf_counter() - w0

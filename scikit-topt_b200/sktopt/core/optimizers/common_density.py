@@ -524,11 +524,19 @@ class DensityMethod(DensityMethodBase):
 
             st.dC_drho_full.zero_()
             u_max = []
+            # optimisers whose update needs filter solves that depend only on the
+            # filtered field (LogMOC's volume chain) may start them now, on a side
+            # stream, behind the state solve (joined before the filter is used again)
+            prefetch = getattr(self, "_prefetch_start", None)
+            if prefetch is not None:
+                prefetch(st, beta)
             with self._timed_section("objective_and_energy"):
                 with self._timed_section("objective"):
                     compliance_avg = self.fem.objectives_multi_load(
                         st.rho_projected, p, st.u_dofs, timer=self.timer,
                         force_scale=neumann_scale).mean()
+                if prefetch is not None:
+                    self._prefetch_join()
                 with self._timed_section("energy"):
                     energy = self.fem.energy_multi_load(st.rho_projected, p, st.u_dofs)
                     if n_tasks == 1:
