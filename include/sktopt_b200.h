@@ -208,6 +208,25 @@ int sktb_elem_restrict_range(int64_t n_coarse, int64_t e_lo, int64_t e_hi,
                              const double *fine_ke, const double *unit,
                              const int32_t *cls, const double *scale, double *out,
                              void *stream);
+/* Algebraic Galerkin product A_c = P^T A P of a node-block (3 dofs per node)
+ * operator whose nodes form a lattice (node = iy + npy*ix + npy*npx*iz) with ANY
+ * geometry or element type (jittered / graded hexahedra, the Kuhn tetrahedra of
+ * MeshTet.init_tensor): the set-up of pyamg.smoothed_aggregation_solver(K),
+ * fea/solver_elastic.py:94-100, where the element-wise kernels above (uniform
+ * hexahedra) do not apply.  P = the trilinear index-space interpolation of
+ * sktb_mg_set_transfer (same tables); fine / coarse operators in the node-block
+ * layout of sktb_spmv_bsr3 (coarse graph = the 27-point lattice graph, given by
+ * the caller); rows / columns of fixed fine dofs (fine_mask, may be NULL) are
+ * left out, fixed coarse dofs (coarse_mask, may be NULL) become identity rows.
+ * One warp per coarse node, fixed summation order, no atomics.                  */
+int sktb_galerkin_bsr3_lattice(const int32_t *fine_np_h, const int32_t *coarse_np_h,
+                               const int32_t *ax_c0, const int32_t *ax_c1,
+                               const double *ax_w0, const double *ax_w1,
+                               const int32_t *axT_f, const double *axT_w,
+                               const int32_t *fine_node_ptr, const int32_t *fine_node_col,
+                               const double *fine_vals, const uint8_t *fine_mask,
+                               const int32_t *coarse_node_ptr, const int32_t *coarse_node_col,
+                               const uint8_t *coarse_mask, double *coarse_vals, void *stream);
 /* ---- matrix-free operators for uniform hexahedral tensor grids --------------
  * Replace the assembled matrix inside the solvers where the reference hands
  * scipy/pyamg an assembled one (elasticity: fea/solver_elastic.py:94-104,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "sktb_mg_set_level_slab": [C.c_void_p, i32, i64, i64, i64, i32, i32],
     "sktb_mg_level_apply": [C.c_void_p, i32, C.c_void_p, c_f64p, c_f64p, c_stream],
     "sktb_elem_restrict_range": [i64, i64, i64, i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
+    "sktb_galerkin_bsr3_lattice": [C.c_void_p, C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_u8p, c_i32p, c_i32p, c_u8p, c_f64p, c_stream],
     "sktb_elem_combine_range": [i64, i64, i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_pcg_set_slab_halo": [C.c_void_p, i64, i32, i32],
     "sktb_pcg_set_first_batch": [C.c_void_p, i32],

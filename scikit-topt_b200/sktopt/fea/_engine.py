@@ -117,16 +117,32 @@ class FeaEngine:
         want = os.environ.get("SKTOPT_B200_PRECOND", "auto").lower()
         if want not in ("jacobi", "mg", "auto"):
             raise ValueError("SKTOPT_B200_PRECOND must be jacobi, mg or auto")
-        if dpn == 3 and want != "jacobi" and dm.elem_class is not None:
-            from sktopt.fea._multigrid import Multigrid
+        self.lattice = None
+        if dpn == 3 and want != "jacobi":
+            from sktopt.fea._multigrid import Multigrid, detect_lattice
             big = dm.n_nodes >= Multigrid.MIN_FINE_NODES or want == "mg"
-            if axes is not None and big:
+            om = os.environ.get("SKTOPT_B200_MG_OMEGA")
+            om = None if om is None else float(om)
+            if axes is not None and big and dm.elem_class is not None:
                 try:
-                    om = os.environ.get("SKTOPT_B200_MG_OMEGA")
-                    self.mg = Multigrid(self, axes, omega=None if om is None else float(om))
+                    self.mg = Multigrid(self, axes, omega=om)
                     self.precond = "mg"
                 except ValueError:
                     self.mg = None
+            elif (big and comm is None
+                  and os.environ.get("SKTOPT_B200_LATTICE_MG", "1") != "0"):
+                # lattice TOPOLOGY with any geometry / element type (jittered or
+                # graded hexahedra, Kuhn tetrahedra of MeshTet.init_tensor): the
+                # same grid hierarchy with algebraic Galerkin coarse operators
+                rp_h, ci_h = dm.node_graph_cached()
+                self.lattice = detect_lattice(rp_h, ci_h, dm.n_nodes)
+                if self.lattice is not None:
+                    try:
+                        idx_axes = tuple(np.arange(n, dtype=np.float64) for n in self.lattice)
+                        self.mg = Multigrid(self, idx_axes, omega=om, algebraic=True)
+                        self.precond = "mg"
+                    except ValueError:
+                        self.mg = None
         # scalar problems (heat): stencil multigrid on tensor grids, one GPU
         self.smg = None
         if (dpn == 1 and want != "jacobi" and self.axes is not None and comm is None):
@@ -138,8 +154,9 @@ class FeaEngine:
                 except ValueError:
                     self.smg = None
         if want == "mg" and self.mg is None and self.smg is None:
-            raise RuntimeError("multigrid preconditioner requested but the mesh is not an "
-                               "eligible tensor hexahedral grid (or the run is sharded)")
+            raise RuntimeError("multigrid preconditioner requested but the mesh is neither a "
+                               "tensor hexahedral grid nor lattice-numbered (or the run is "
+                               "sharded)")
         self.u = {}  # load index -> device solution (warm start), full length
         self.warm_start = True
         # start vector = Galerkin projection of the new system onto the span of the

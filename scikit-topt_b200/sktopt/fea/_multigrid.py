@@ -38,6 +38,75 @@ def detect_tensor_grid(mesh):
     return xs, ys, zs
 
 
+def lattice_graph(nx: int, ny: int, nz: int):
+    """Node graph (CSR, columns ascending, int32) of the 27-point lattice stencil
+    on nx x ny x nz nodes, node = iy + ny*ix + ny*nx*iz."""
+    iz, ix, iy = np.meshgrid(np.arange(nz), np.arange(nx), np.arange(ny), indexing="ij")
+    iz, ix, iy = iz.ravel(), ix.ravel(), iy.ravel()
+    cols, ok = [], []
+    for dz in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                jz, jx, jy = iz + dz, ix + dx, iy + dy
+                ok.append((jz >= 0) & (jz < nz) & (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny))
+                cols.append(jy + ny * (jx + nx * jz))
+    ok = np.stack(ok, axis=1)
+    cols = np.stack(cols, axis=1)
+    rp = np.concatenate([[0], np.cumsum(ok.sum(axis=1))]).astype(np.int32)
+    return rp, cols[ok].astype(np.int32)
+
+
+def detect_lattice(node_ptr, node_col, n_nodes: int):
+    """(nx, ny, nz) node counts if the node graph is a sub-graph of the 27-point
+    stencil of a lattice numbered like ``init_tensor`` (node = iy + ny*ix +
+    ny*nx*iz, at least 3 nodes along x and y), else None.  Only the topology
+    matters: the geometry may be jittered or graded and the elements may be
+    hexahedra or the Kuhn tetrahedra of ``MeshTet.init_tensor``."""
+    rp = np.asarray(node_ptr, dtype=np.int64)
+    ci = np.asarray(node_col, dtype=np.int64)
+    n = int(n_nodes)
+    if n < 27 or ci.size == 0:
+        return None
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    pos = np.unique((ci - rows)[ci > rows])
+    if pos.size == 0 or pos[0] != 1:
+        return None
+
+    def split(v, m):
+        """v = r + m*q with r in {-1, 0, 1}, or None"""
+        q = (v + 1) // m
+        r = v - m * q
+        return (q, r) if np.all(np.abs(r) <= 1) else None
+
+    big = pos[pos > 1]
+    if big.size == 0:
+        return None
+    for ny in (int(big[0]), int(big[0]) + 1):
+        if ny < 3 or n % ny:
+            continue
+        sp = split(pos, ny)
+        if sp is None:
+            continue
+        m = np.unique(sp[0][sp[0] > 0])
+        if m.size == 0 or m[0] != 1:
+            continue
+        mb = m[m > 1]
+        cand = [n // ny] if mb.size == 0 else [int(mb[0]), int(mb[0]) + 1]
+        for nx in cand:
+            if nx < 3 or (n // ny) % nx:
+                continue
+            nz = n // (ny * nx)
+            if split(m, nx) is None:
+                continue
+            # full check: every edge joins lattice neighbours
+            ay, ar = rows % ny, rows // ny
+            by, br = ci % ny, ci // ny
+            if (np.all(np.abs(ay - by) <= 1) and np.all(np.abs(ar % nx - br % nx) <= 1)
+                    and np.all(np.abs(ar // nx - br // nx) <= 1)):
+                return int(nx), int(ny), int(nz)
+    return None
+
+
 def coarse_index_map(n_cells: int) -> np.ndarray:
     """Fine node index of every coarse node along one axis."""
     nc = (n_cells + 1) // 2
@@ -202,9 +271,14 @@ class Multigrid:
     DENSE_MAX_DOFS = 160
 
     def __init__(self, engine, axes, omega: float | None = None, nu_coarse: int = 30,
-                 coarsest_max_cells: int = 6):
+                 coarsest_max_cells: int = 6, algebraic: bool = False):
         self.lib = _lib.load()
         self.eng = engine
+        # algebraic = True: lattice topology only (any geometry / element type);
+        # level 0 is the engine's assembled node-block matrix and the coarse
+        # operators are P^T A P formed matrix to matrix (csrc/galerkin_bsr.cu);
+        # ``axes`` then only carries the node counts
+        self.algebraic = bool(algebraic)
         self.omega_auto = omega is None
         self.omega = 0.5 if omega is None else float(omega)
         nu_coarse = int(os.environ.get("SKTOPT_B200_MG_NU_COARSE", nu_coarse))
@@ -224,9 +298,10 @@ class Multigrid:
         self.n_levels = len(coords)
         if self.n_levels < 2:
             raise ValueError("grid too small for a multigrid hierarchy")
-        fine_mesh = engine.basis.mesh
-        bits = vertex_bits(fine_mesh)
-        self.Qtab = dev.to_dev(q_tables(bits).ravel())
+        if not self.algebraic:
+            fine_mesh = engine.basis.mesh
+            bits = vertex_bits(fine_mesh)
+            self.Qtab = dev.to_dev(q_tables(bits).ravel())
         h = C.c_void_p()
         _lib.check(self.lib.sktb_mg_create(C.byref(h), self.n_levels, torch.cuda.current_device()))
         self.handle = h
@@ -246,14 +321,20 @@ class Multigrid:
         self._plan_sharding()
         for l in range(1, self.n_levels):
             cxs, cys, czs = coords[l]
-            mesh_c = MeshHex.init_tensor(cxs, cys, czs)
-            if not np.array_equal(vertex_bits(mesh_c), bits):
-                raise RuntimeError("coarse and fine meshes disagree on local vertex order")
-            dm = dev.DeviceMesh(mesh_c)
-            rp_h, ci_h = dm.node_graph()
             fine_cells = tuple(c.size - 1 for c in coords[l - 1])
             coarse_cells = tuple(c.size - 1 for c in coords[l])
-            child, ptype = child_tables(fine_cells, coarse_cells)
+            if self.algebraic:
+                dm = None
+                rp_h, ci_h = lattice_graph(cxs.size, cys.size, czs.size)
+                n_nodes_c, n_elem_c = int(cxs.size * cys.size * czs.size), 0
+            else:
+                mesh_c = MeshHex.init_tensor(cxs, cys, czs)
+                if not np.array_equal(vertex_bits(mesh_c), bits):
+                    raise RuntimeError("coarse and fine meshes disagree on local vertex order")
+                dm = dev.DeviceMesh(mesh_c)
+                rp_h, ci_h = dm.node_graph()
+                n_nodes_c, n_elem_c = dm.n_nodes, dm.n_elem
+                child, ptype = child_tables(fine_cells, coarse_cells)
             sh = self.shard[l]
             if sh is not None:
                 # owned rows only (global columns); element matrices of the slab
@@ -262,8 +343,8 @@ class Multigrid:
                 rp_loc, ci_loc = rp_h[n0:n1 + 1] - s_, ci_h[s_:e_]
                 n_ke = sh["elem1"] - sh["elem0"]
             else:
-                rp_loc, ci_loc, n0, n1 = rp_h, ci_h, 0, dm.n_nodes
-                n_ke = dm.n_elem
+                rp_loc, ci_loc, n0, n1 = rp_h, ci_h, 0, n_nodes_c
+                n_ke = n_elem_c
             # Dirichlet mask: a coarse dof is fixed iff the coincident fine dof is
             fm = [coarse_index_map(n) for n in fine_cells]
             npx_f, npy_f = fine_cells[0] + 1, fine_cells[1] + 1
@@ -272,15 +353,16 @@ class Multigrid:
             fnode = (fm[1][Iy] + npy_f * fm[0][Ix] + npy_f * npx_f * fm[2][Iz]).ravel()
             mask_c = mask_f.reshape(-1, 3)[fnode].ravel().copy()
             lvl = dict(
-                dm=dm, n_nodes=dm.n_nodes, n_elem=dm.n_elem, node0=n0, node1=n1,
+                dm=dm, n_nodes=n_nodes_c, n_elem=n_elem_c, node0=n0, node1=n1,
                 node_ptr=dev.to_dev(rp_loc, dev.I32), node_col=dev.to_dev(ci_loc, dev.I32),
                 max_deg=int(np.diff(rp_loc).max()),
                 vals=torch.empty(9 * ci_loc.size, dtype=dev.F64, device="cuda"),
                 inv_diag=torch.empty(3 * (n1 - n0), dtype=dev.F64, device="cuda"),
                 mask=dev.to_dev(mask_c, dev.U8),
-                ke=torch.empty((n_ke, 576), dtype=dev.F64, device="cuda"),
-                child=dev.to_dev(child, dev.I32), ptype=dev.to_dev(ptype, dev.U8),
             )
+            if not self.algebraic:
+                lvl.update(ke=torch.empty((n_ke, 576), dtype=dev.F64, device="cuda"),
+                           child=dev.to_dev(child, dev.I32), ptype=dev.to_dev(ptype, dev.U8))
             self.levels.append(lvl)
             # transfer tables fine (l-1) -> coarse (l), concatenated [x | y | z]
             tabs = [axis_tables(n) for n in fine_cells]
@@ -309,9 +391,11 @@ class Multigrid:
         self.cheb_alpha = float(os.environ.get("SKTOPT_B200_MG_CHEB_ALPHA", "0"))
         self.setup_count = 0
         # level 0 -> 1 tables T[cls][type][c] = Q_c^T Ke0[cls] Q_c (host, once)
+        self.T01 = None
+        if self.algebraic:
+            return
         ke0 = engine.unit_ke.cpu().numpy().reshape(-1, 24, 24)
         Q = q_tables(bits)
-        self.T01 = None
         if ke0.shape[0] <= 16:
             T = np.zeros((ke0.shape[0], 8, 8, 24, 24))
             eye3 = np.eye(3)
@@ -332,7 +416,7 @@ class Multigrid:
         self.first_replicated = 1
         self.gather_plan = None
         comm = eng.comm
-        if comm is None or getattr(eng, "plane_cuts", None) is None:
+        if comm is None or getattr(eng, "plane_cuts", None) is None or self.algebraic:
             return
         shard_min = int(os.environ.get("SKTOPT_B200_MG_SHARD_MIN", self.SHARD_MIN_NODES))
         self.shard, self.first_replicated, self.gather_plan, self.plane_cuts = \
@@ -448,6 +532,21 @@ class Multigrid:
             cnt = np.diff(gp["cuts"]) * gp["plane_elems"] * 576
             eng.comm.allgatherv(lv["ke"].view(-1), cnt, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
 
+    def _galerkin_algebraic(self, l: int, st):
+        """vals of level ``l`` = P^T A_{l-1} P, matrix to matrix."""
+        eng, lv, tr = self.eng, self.levels[l], self.transfers[l - 1]
+        if l == 1:
+            fp, fc, fv, fm = eng.node_ptr_loc, eng.node_col_loc, eng.vals, eng.dir_mask
+        else:
+            f = self.levels[l - 1]
+            fp, fc, fv, fm = f["node_ptr"], f["node_col"], f["vals"], f["mask"]
+        _lib.check(self.lib.sktb_galerkin_bsr3_lattice(
+            tr["fnp"].ctypes.data_as(C.c_void_p), tr["cnp"].ctypes.data_as(C.c_void_p),
+            dev._ptr(tr["c0"]), dev._ptr(tr["c1"]), dev._ptr(tr["w0"]), dev._ptr(tr["w1"]),
+            dev._ptr(tr["fT"]), dev._ptr(tr["wT"]), dev._ptr(fp), dev._ptr(fc), dev._ptr(fv),
+            dev._ptr(fm), dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]),
+            dev._ptr(lv["mask"]), dev._ptr(lv["vals"]), st))
+
     def setup(self):
         """Galerkin coarse operators for the engine's current modulus field;
         call after the engine assembled level 0 and its inverse diagonal."""
@@ -473,6 +572,14 @@ class Multigrid:
         for l in range(1, self.n_levels):
             lv = self.levels[l]
             sh = self.shard[l]
+            if self.algebraic:
+                self._galerkin_algebraic(l, st)
+                dev.bsr3_inv_diag(lv["node_ptr"], lv["node_col"], lv["vals"], out=lv["inv_diag"])
+                _lib.check(lib.sktb_mg_set_level(
+                    self.handle, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()),
+                    lv["max_deg"], dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]),
+                    dev._ptr(lv["vals"]), dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+                continue
             self._galerkin_level(l, st)
             if sh is not None:
                 lv["dm"].assemble_rows(3, sh["node0"], sh["node1"], lv["ke"], scale=None,

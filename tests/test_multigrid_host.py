@@ -158,3 +158,130 @@ def test_slab_sharding_plan_covers_what_every_rank_needs():
             ok = child[ch] >= 0
             ez_f = child[ch][ok] // (fine[0] * fine[1])
             assert np.all((ez_f == 2 * ez_c[ok]) | (ez_f == 2 * ez_c[ok] + 1))
+
+
+# ---------------------------------------------------------------- lattice meshes --
+def _node_graph(t, n):
+    nen = t.shape[0]
+    r = np.repeat(t, nen, axis=0).ravel()
+    c = np.tile(t, (nen, 1)).ravel()
+    G = sp.csr_matrix((np.ones(r.size), (r, c)), shape=(n, n))
+    G.sum_duplicates()
+    G.sort_indices()
+    return G.indptr, G.indices
+
+
+def test_lattice_detection_and_graph():
+    """``detect_lattice`` reads the node counts off the node graph alone (hexahedra:
+    27-point stencil, Kuhn tetrahedra: 15 points) and rejects other numberings;
+    ``lattice_graph`` is the node graph of the hexahedral lattice."""
+    from sktopt._fem import MeshHex, MeshTet
+    from sktopt.fea._multigrid import detect_lattice, lattice_graph
+    for M, dims in ((MeshTet, (6, 5, 4)), (MeshHex, (6, 5, 4)), (MeshTet, (9, 4, 7)),
+                    (MeshHex, (4, 4, 4)), (MeshTet, (4, 4, 2)), (MeshHex, (3, 3, 12))):
+        m = M.init_tensor(*[np.linspace(0, 1, d) for d in dims])
+        rp, ci = _node_graph(m.t, m.p.shape[1])
+        assert detect_lattice(rp, ci, m.p.shape[1]) == dims, (M.__name__, dims)
+    m = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in (6, 5, 4)])
+    n = m.p.shape[1]
+    rp, ci = _node_graph(m.t, n)
+    rp2, ci2 = lattice_graph(6, 5, 4)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    assert rp2.dtype == np.int32 and ci2.dtype == np.int32
+    perm = np.random.default_rng(0).permutation(n)
+    assert detect_lattice(*_node_graph(perm[m.t], n), n) is None
+    # this package's tetrahedral box (Kuhn split of the tensor grid) qualifies
+    from sktopt.mesh.toy_problem import create_box_tet
+    mt = create_box_tet(1.0, 1.0, 1.0, 0.2)
+    assert detect_lattice(*_node_graph(mt.t, mt.p.shape[1]), mt.p.shape[1]) == (6, 6, 6)
+    # a line of cells (fewer than 3 nodes along y) and a tiny graph do not
+    m2 = MeshHex.init_tensor(np.linspace(0, 1, 9), np.linspace(0, 1, 2), np.linspace(0, 1, 5))
+    assert detect_lattice(*_node_graph(m2.t, m2.p.shape[1]), m2.p.shape[1]) is None
+
+
+def test_algebraic_galerkin_gather_rule():
+    """NumPy restatement of the gather rule of ``galerkin_bsr3_lattice_kernel``
+    (csrc/galerkin_bsr.cu): coarse block (I, J) = sum over the fine nodes i that
+    interpolate from I and the blocks (i, j) of their rows with j interpolating from
+    J of w_iI w_jJ A_ij, fixed fine rows / columns left out, fixed coarse dofs as
+    identity.  It must equal P^T A P built from the same axis tables, on jittered
+    Kuhn tetrahedra with odd and even node counts."""
+    from sktopt._fem import MeshTet
+    from sktopt.fea._multigrid import axis_tables, coarse_index_map, lattice_graph
+    cells = (5, 4, 3)
+    m = MeshTet.init_tensor(*[np.linspace(0, 1, c + 1) for c in cells])
+    p = m.p.copy()
+    p += np.random.default_rng(1).uniform(-0.03, 0.03, p.shape)
+    from sktopt.mesh.utils import fix_tetrahedron_orientation
+    t = fix_tetrahedron_orientation(m.t, p)
+    n = p.shape[1]
+    rho = np.random.default_rng(2).uniform(0.1, 1.0, t.shape[1])
+    K = fem.assemble_stiffness(p, t, rho, 1.0, 1e-3, 3.0, 0.3)
+    clamp = np.nonzero(m.p[0] < 1e-9)[0]
+    D = np.unique((3 * clamp[:, None] + np.arange(3)).ravel())
+    A, _ = fem.enforce(K, np.zeros(3 * n), D)
+    A = A.tocsr()
+    fmask = np.zeros(3 * n, bool)
+    fmask[D] = True
+    fnx, fny, fnz = (c + 1 for c in cells)
+    tabs = [axis_tables(c) for c in cells]
+    cn = [(c + 1) // 2 + 1 for c in cells]
+    cnx, cny, cnz = cn
+    fm = [coarse_index_map(c) for c in cells]
+    Iz, Ix, Iy = np.meshgrid(np.arange(cnz), np.arange(cnx), np.arange(cny), indexing="ij")
+    fnode = (fm[1][Iy] + fny * fm[0][Ix] + fny * fnx * fm[2][Iz]).ravel()
+    cmask = fmask.reshape(-1, 3)[fnode].ravel()
+    rp, ci = _node_graph(t, n)
+    crp, cci = lattice_graph(cnx, cny, cnz)
+
+    def w_axis(ax, f, J):
+        c0, c1, w0, w1, _, _ = tabs[ax]
+        w = 0.0
+        if c0[f] == J:
+            w += w0[f]
+        if c1[f] == J and c1[f] != c0[f]:
+            w += w1[f]
+        return w
+
+    nc = cnx * cny * cnz
+    got = sp.lil_matrix((3 * nc, 3 * nc))
+    Ad = A.toarray()
+    for I in range(nc):
+        Iy_, Ix_, Iz_ = I % cny, (I // cny) % cnx, I // (cny * cnx)
+        for J in cci[crp[I]:crp[I + 1]]:
+            Jy, Jx, Jz = J % cny, (J // cny) % cnx, J // (cny * cnx)
+            acc = np.zeros((3, 3))
+            for sz in range(3):
+                fz = tabs[2][4][sz, Iz_]
+                for sx in range(3):
+                    fx = tabs[0][4][sx, Ix_]
+                    for sy in range(3):
+                        fy = tabs[1][4][sy, Iy_]
+                        if min(fz, fx, fy) < 0:
+                            continue
+                        wI = tabs[2][5][sz, Iz_] * tabs[0][5][sx, Ix_] * tabs[1][5][sy, Iy_]
+                        i = fy + fny * (fx + fnx * fz)
+                        for j in ci[rp[i]:rp[i + 1]]:
+                            jy, jx, jz = j % fny, (j // fny) % fnx, j // (fny * fnx)
+                            w = w_axis(2, jz, Jz) * w_axis(0, jx, Jx) * w_axis(1, jy, Jy) * wI
+                            if w == 0.0:
+                                continue
+                            blk = Ad[3 * i:3 * i + 3, 3 * j:3 * j + 3].copy()
+                            blk[fmask[3 * i:3 * i + 3], :] = 0.0
+                            blk[:, fmask[3 * j:3 * j + 3]] = 0.0
+                            acc += w * blk
+            for a in range(3):
+                for b in range(3):
+                    v = acc[a, b]
+                    if cmask[3 * I + a] or cmask[3 * J + b]:
+                        v = 1.0 if (I == J and a == b) else 0.0
+                    got[3 * I + a, 3 * J + b] = v
+    P = _prolongation(cells)
+    free_f = sp.diags((~fmask).astype(float))
+    free_c = sp.diags((~cmask).astype(float))
+    ref = (free_c @ P.T @ free_f @ A @ free_f @ P @ free_c + sp.diags(cmask.astype(float))).tocsr()
+    assert abs(got.tocsr() - ref).max() <= 1e-13 * abs(ref).max()
+    # nothing of P^T A P falls outside the 27-point coarse graph
+    full = (P.T @ free_f @ A @ free_f @ P).tocoo()
+    G = sp.csr_matrix((np.ones(cci.size), cci, crp), shape=(nc, nc))
+    assert np.all(G[full.row // 3, full.col // 3] == 1.0)
