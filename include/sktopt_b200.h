@@ -189,6 +189,9 @@ int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_np_h,
                          const int32_t *ax_c1, const double *ax_w0,
                          const double *ax_w1, const int32_t *axT_f,
                          const double *axT_w);
+/* dst (a second set of work vectors on the same level operators, e.g. one per
+ * concurrently solved load case) borrows src's exact coarsest-level inverse        */
+int sktb_mg_share_coarsest(sktb_mg *dst, const sktb_mg *src);
 /* z = M^-1 r (one V-cycle)                                                    */
 int sktb_mg_vcycle(sktb_mg *m, const double *r, double *z, void *stream);
 /* Galerkin coarse element matrices: out[E] = sum_c Q^T K_child Q over the

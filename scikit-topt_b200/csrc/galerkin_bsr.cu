@@ -10,11 +10,11 @@
 // element-wise Galerkin kernels of mg.cu (uniform hexahedra) do not apply.
 //
 // Gather formulation, no atomics, fixed summation order (bit-reproducible):
-// one warp per coarse node I, lane s < 27 owns the 3x3 block of the coarse
-// neighbour J = I + (dz, dx, dy).  The warp walks the <= 27 fine nodes i that
-// interpolate from I and, for each, the blocks (i, j) of the fine row; a lane
-// adds w_iI * w_jJ * A_ij when j interpolates from its J.  All lanes read the
-// same A_ij (one broadcast load per value).
+// one CTA per coarse node I, nine warps, lane s < 27 of each owns the 3x3 block of
+// the coarse neighbour J = I + (dz, dx, dy).  A warp walks a third of a third of
+// the <= 27 fine nodes i that interpolate from I and, for each, the blocks (i, j)
+// of the fine row; a lane adds w_iI * w_jJ * A_ij when j interpolates from its J.
+// All lanes read the same A_ij (one broadcast load per value).
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -39,7 +39,9 @@ __device__ __forceinline__ double axis_weight(const LatticeTransfer &T, int off,
   return w;
 }
 
-__global__ void __launch_bounds__(kBlock)
+constexpr int kGalWarps = 9;   // one warp per (sz, sx) pair of fine parent slots
+
+__global__ void __launch_bounds__(32 * kGalWarps)
     galerkin_bsr3_lattice_kernel(const LatticeTransfer T, const int32_t *__restrict__ fptr,
                                  const int32_t *__restrict__ fcol,
                                  const double *__restrict__ fvals,
@@ -47,12 +49,18 @@ __global__ void __launch_bounds__(kBlock)
                                  const int32_t *__restrict__ cptr,
                                  const int32_t *__restrict__ ccol,
                                  const uint8_t *__restrict__ cmask, double *__restrict__ cvals) {
-  const int lane = threadIdx.x & 31;
+  // CTA = one coarse node I.  Warp w walks the fine parents with (sz, sx) =
+  // (w / 3, w % 3) (<= 3 fine nodes, <= 81 blocks); its lanes own the 27 coarse
+  // neighbours.  The nine partial blocks of a neighbour are then added in warp
+  // order (fixed order: bit-reproducible).  A serial walk of all 27 parents by one
+  // warp is latency bound on the small levels (729 dependent steps).
+  __shared__ double part[kGalWarps][27][9];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n_coarse = T.cnx * T.cny * T.cnz;
   const int tot = T.cnx + T.cny + T.cnz;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
   const int dy = lane % 3 - 1, dx = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-  for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < n_coarse; I += warps) {
+  const int sz = wid / 3, sx = wid % 3;
+  for (int I = blockIdx.x; I < n_coarse; I += gridDim.x) {
     const int Iy = I % T.cny, Ix = (I / T.cny) % T.cnx, Iz = I / (T.cny * T.cnx);
     const int Jx = Ix + dx, Jy = Iy + dy, Jz = Iz + dz;
     const bool live = lane < 27 && Jx >= 0 && Jx < T.cnx && Jy >= 0 && Jy < T.cny && Jz >= 0 &&
@@ -60,83 +68,84 @@ __global__ void __launch_bounds__(kBlock)
     double acc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = 0.0;
-    for (int sz = 0; sz < 3; ++sz) {
-      const int fz = __ldg(&T.fT[sz * tot + T.cnx + T.cny + Iz]);
-      if (fz < 0) continue;
-      const double wz = __ldg(&T.wT[sz * tot + T.cnx + T.cny + Iz]);
-      for (int sx = 0; sx < 3; ++sx) {
-        const int fx = __ldg(&T.fT[sx * tot + Ix]);
-        if (fx < 0) continue;
-        const double wzx = wz * __ldg(&T.wT[sx * tot + Ix]);
-        for (int sy = 0; sy < 3; ++sy) {
-          const int fy = __ldg(&T.fT[sy * tot + T.cnx + Iy]);
-          if (fy < 0) continue;
-          const double wI = wzx * __ldg(&T.wT[sy * tot + T.cnx + Iy]);
-          const int i = fy + T.fny * (fx + T.fnx * fz);
-          const int s0 = __ldg(&fptr[i]), deg = __ldg(&fptr[i + 1]) - s0;
-          const double *vp = fvals + (int64_t)9 * s0;
-          bool ri[3] = {false, false, false};   // fixed rows of node i contribute nothing
+    const int fz = __ldg(&T.fT[sz * tot + T.cnx + T.cny + Iz]);
+    const int fx = __ldg(&T.fT[sx * tot + Ix]);
+    if (fz >= 0 && fx >= 0) {
+      const double wzx = __ldg(&T.wT[sz * tot + T.cnx + T.cny + Iz]) * __ldg(&T.wT[sx * tot + Ix]);
+      for (int sy = 0; sy < 3; ++sy) {
+        const int fy = __ldg(&T.fT[sy * tot + T.cnx + Iy]);
+        if (fy < 0) continue;
+        const double wI = wzx * __ldg(&T.wT[sy * tot + T.cnx + Iy]);
+        const int i = fy + T.fny * (fx + T.fnx * fz);
+        const int s0 = __ldg(&fptr[i]), deg = __ldg(&fptr[i + 1]) - s0;
+        const double *vp = fvals + (int64_t)9 * s0;
+        bool ri[3] = {false, false, false};   // fixed rows of node i contribute nothing
+        if (fmask) {
+          ri[0] = fmask[3 * i] != 0;
+          ri[1] = fmask[3 * i + 1] != 0;
+          ri[2] = fmask[3 * i + 2] != 0;
+        }
+        if (ri[0] && ri[1] && ri[2]) continue;
+        for (int k = 0; k < deg; ++k) {
+          const int j = __ldg(&fcol[s0 + k]);
+          const int jy = j % T.fny, jr = j / T.fny;
+          const int jx = jr % T.fnx, jz = jr / T.fnx;
+          double w = 0.0;
+          if (live) {
+            w = axis_weight(T, T.fnx + T.fny, jz, Jz);
+            if (w != 0.0) w *= axis_weight(T, 0, jx, Jx);
+            if (w != 0.0) w *= axis_weight(T, T.fnx, jy, Jy);
+          }
+          if (__ballot_sync(0xffffffffu, w != 0.0) == 0u) continue;
+          w *= wI;
+          bool cj[3] = {false, false, false};
           if (fmask) {
-            ri[0] = fmask[3 * i] != 0;
-            ri[1] = fmask[3 * i + 1] != 0;
-            ri[2] = fmask[3 * i + 2] != 0;
+            cj[0] = fmask[3 * j] != 0;
+            cj[1] = fmask[3 * j + 1] != 0;
+            cj[2] = fmask[3 * j + 2] != 0;
           }
-          if (ri[0] && ri[1] && ri[2]) continue;
-          for (int k = 0; k < deg; ++k) {
-            const int j = __ldg(&fcol[s0 + k]);
-            const int jy = j % T.fny, jr = j / T.fny;
-            const int jx = jr % T.fnx, jz = jr / T.fnx;
-            double w = 0.0;
-            if (live) {
-              w = axis_weight(T, T.fnx + T.fny, jz, Jz);
-              if (w != 0.0) w *= axis_weight(T, 0, jx, Jx);
-              if (w != 0.0) w *= axis_weight(T, T.fnx, jy, Jy);
-            }
-            if (__ballot_sync(0xffffffffu, w != 0.0) == 0u) continue;
-            w *= wI;
-            bool cj[3] = {false, false, false};
-            if (fmask) {
-              cj[0] = fmask[3 * j] != 0;
-              cj[1] = fmask[3 * j + 1] != 0;
-              cj[2] = fmask[3 * j + 2] != 0;
-            }
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-              if (ri[a]) continue;
+          for (int a = 0; a < 3; ++a) {
+            if (ri[a]) continue;
 #pragma unroll
-              for (int b = 0; b < 3; ++b) {
-                if (cj[b]) continue;
-                acc[3 * a + b] += w * __ldg(&vp[(int64_t)a * 3 * deg + 3 * k + b]);
-              }
+            for (int b = 0; b < 3; ++b) {
+              if (cj[b]) continue;
+              acc[3 * a + b] += w * __ldg(&vp[(int64_t)a * 3 * deg + 3 * k + b]);
             }
           }
         }
       }
     }
-    if (live) {
-      const int J = Jy + T.cny * (Jx + T.cnx * Jz);
-      const int c0 = __ldg(&cptr[I]), cdeg = __ldg(&cptr[I + 1]) - c0;
-      int kc = -1;
-      for (int k = 0; k < cdeg; ++k)
-        if (__ldg(&ccol[c0 + k]) == J) {
-          kc = k;
-          break;
-        }
-      if (kc >= 0) {
-        double *op = cvals + (int64_t)9 * c0;
+    if (lane < 27) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+      for (int q = 0; q < 9; ++q) part[wid][lane][q] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 243) {
+      const int s = threadIdx.x / 9, q = threadIdx.x % 9;
+      const int a = q / 3, b = q % 3;
+      const int ox = Ix + (s / 3) % 3 - 1, oy = Iy + s % 3 - 1, oz = Iz + s / 9 - 1;
+      if (ox >= 0 && ox < T.cnx && oy >= 0 && oy < T.cny && oz >= 0 && oz < T.cnz) {
+        double v = 0.0;
 #pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            double v = acc[3 * a + b];
-            const bool diag = (J == I) && (a == b);
-            if (cmask && (cmask[3 * I + a] || cmask[3 * J + b])) v = diag ? 1.0 : 0.0;
-            if (diag && !(v > 0.0)) v = 1.0;   // a coarse dof nothing interpolates from
-            op[(int64_t)a * 3 * cdeg + 3 * kc + b] = v;
+        for (int w = 0; w < kGalWarps; ++w) v += part[w][s][q];
+        const int J = oy + T.cny * (ox + T.cnx * oz);
+        const int c0 = __ldg(&cptr[I]), cdeg = __ldg(&cptr[I + 1]) - c0;
+        int kc = -1;
+        for (int k = 0; k < cdeg; ++k)
+          if (__ldg(&ccol[c0 + k]) == J) {
+            kc = k;
+            break;
           }
+        if (kc >= 0) {
+          const bool diag = (J == I) && (a == b);
+          if (cmask && (cmask[3 * I + a] || cmask[3 * J + b])) v = diag ? 1.0 : 0.0;
+          if (diag && !(v > 0.0)) v = 1.0;   // a coarse dof nothing interpolates from
+          cvals[(int64_t)9 * c0 + (int64_t)a * 3 * cdeg + 3 * kc + b] = v;
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -171,7 +180,8 @@ extern "C" int sktb_galerkin_bsr3_lattice(
   T.fT = axT_f;
   T.wT = axT_w;
   const int64_t n_coarse = (int64_t)T.cnx * T.cny * T.cnz;
-  galerkin_bsr3_lattice_kernel<<<grid_for(n_coarse * 32, kBlock, 8), kBlock, 0,
+  const int64_t cap = (int64_t)kNumSM * 32;
+  galerkin_bsr3_lattice_kernel<<<(int)(n_coarse < cap ? n_coarse : cap), 32 * kGalWarps, 0,
                                  (cudaStream_t)stream>>>(
       T, fine_node_ptr, fine_node_col, fine_vals, fine_mask, coarse_node_ptr, coarse_node_col,
       coarse_mask, coarse_vals);

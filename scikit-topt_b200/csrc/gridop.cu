@@ -71,6 +71,12 @@ struct sktb_gridop {
   // two-nodes-per-thread kernel (DPN = 3): coefficient tables in global memory,
   // staged in shared memory by every CTA (SKTB_GRIDOP_X2=0 disables)
   bool x2 = true;
+  // x2 with the element modulus folded into the inputs (6 accumulators per node
+  // pair, 16 warps per SM): 1 = single-precision products only (default: the
+  // V-cycle's level-0 products, 0.607 -> 0.590 ms per cycle at C2), 2 = fp64 too
+  // (SKTB_GRIDOP_X2S=1; measured SLOWER there: 0.089-0.095 vs 0.081 ms, the extra
+  // 28 % of FP64 instructions outweigh the doubled occupancy), 0 = never (=0)
+  int x2s = 1;
   double *kt_d = nullptr;
   float *ktf_d = nullptr;
 };
@@ -777,6 +783,164 @@ __global__ void __launch_bounds__(kX2Block, SKTB_X2_MINB)
   }
 }
 
+// ------- x2s kernel: the x2 kernel with the element modulus folded into the INPUT --
+// The x2 kernel keeps one partial product per (node, element) until the end
+// (y_i = sum_o E_o pe[o][i]): 48 accumulators per node pair, 255 registers, 8
+// warps per SM, and the FP64 pipe waits on latencies (0.37-0.43 of its peak).
+// Here every neighbour value is scaled by the modulus of the element it is seen
+// through (s = E_o x_m, 3 multiplies) and added straight into the 3 outputs of the
+// node: 6 (x 2 for independent chains) accumulators per pair, only two neighbour
+// columns live at a time, 128 registers, 16 warps per SM; 1536 instead of 1200
+// FP64 instructions per pair (+28 %).  Same tables, same work split, same boundary
+// treatment and epilogue as the x2 kernel.  Measured at C2 (B200): fp64 0.089-0.095
+// ms against 0.081 ms for x2 (the FP64 pipe is ~50 % instead of 43 % busy, not
+// enough to pay for the extra instructions), so fp64 products keep x2; the fp32
+// products of the V-cycle gain (0.607 -> 0.590 ms per cycle) and use this kernel.
+template <typename T, int MODE, bool DOT>
+__global__ void __launch_bounds__(kX2Block, 2)
+    hexgrid_apply_x2s_kernel(const GridX2 P, int z0, int nzs, int64_t node0,
+                             const double *__restrict__ x, double *__restrict__ y,
+                             const double *__restrict__ dotv, double *partials,
+                             unsigned int *ticket, double *dot_out, const PcgScalars *S,
+                             const double *__restrict__ sm_b,
+                             const double *__restrict__ sm_dinv, double sm_omega) {
+  if (S && S->rr <= S->tol2) return;
+  constexpr int TS = X2Tab<T>::S;
+  __shared__ __align__(16) T kt[kX2Slots * TS];
+  {
+    const T *src = sizeof(T) == 8 ? (const T *)P.kt : (const T *)P.ktf;
+    for (int i = threadIdx.x; i < kX2Slots * TS; i += blockDim.x) kt[i] = src[i];
+  }
+  __syncthreads();
+  const int npx = P.npx, npy = P.npy, npz = P.npz;
+  const int nx = npx - 1, ny = npy - 1, nz = npz - 1;
+  const int npxp = (npx + 1) >> 1;
+  const unsigned n_items = (unsigned)npy * (unsigned)npxp * (unsigned)nzs;
+  const unsigned n_pad = (n_items + 31u) & ~31u;
+  const unsigned trips = (n_pad + kX2Block - 1) / kX2Block;
+  const unsigned per_cta = (trips + gridDim.x - 1) / gridDim.x;
+  const unsigned w_end = min(n_pad, (blockIdx.x + 1) * per_cta * kX2Block);
+  double dot = 0.0;
+  for (unsigned w = blockIdx.x * per_cta * kX2Block + threadIdx.x; w < w_end; w += kX2Block) {
+    const bool live = w < n_items;
+    const unsigned wc = live ? w : n_items - 1;
+    const unsigned t1 = wc / (unsigned)npy;
+    const int iy = (int)(wc - t1 * (unsigned)npy);
+    const unsigned t2 = t1 / (unsigned)npxp;
+    const int ixA = 2 * (int)(t1 - t2 * (unsigned)npxp);
+    const int iz = z0 + (int)t2;
+    const bool hasB = ixA + 1 < npx;
+    const int nA = iy + npy * (ixA + npx * iz);
+    const int nB = hasB ? nA + npy : nA;
+    const unsigned dmA = P.dmask[nA], dmB = P.dmask[nB];
+    const bool near_fixed = ((dmA | dmB) & 8u) != 0;
+    T Eg[3][2][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ex = ixA - 1 + a, ey = iy - 1 + b, ez = iz - 1 + c;
+          const bool ok = ex >= 0 && ex < nx && ey >= 0 && ey < ny && ez >= 0 && ez < nz;
+          Eg[a][b][c] = ok ? (T)__ldg(&P.scale[ey + ny * (ex + nx * ez)]) : (T)0;
+        }
+    T yA[2][3], yB[2][3];   // two independent chains per output
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) yA[h][i] = yB[h][i] = (T)0;
+    int cxo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cxo[c] = npy * clampi(ixA - 1 + c, npx - 1) + iy;
+    const int lo = iy > 0 ? -3 : 0, hi = iy < npy - 1 ? 3 : 0;
+    // the plane loop stays rolled: unrolled, ptxas hoists the loads of all three
+    // planes and spills ~700 B per thread at 128 registers
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zo = npy * npx * clampi(iz + dz, npz - 1);
+      T col[4][3][3];  // [column ixA-1 .. ixA+2][dy + 1][component]; two live at a time
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int mc = zo + cxo[c];
+        const double *cp = x + 3 * mc;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          col[c][0][j] = (T)__ldg(cp + lo + j);
+          col[c][1][j] = (T)__ldg(cp + j);
+          col[c][2][j] = (T)__ldg(cp + hi + j);
+        }
+        if (near_fixed) {
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int ky = iy + dy;
+            if (ky < 0 || ky >= npy) continue;
+            const unsigned mb = P.dmask[mc + dy];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if ((mb >> j) & 1u) col[c][dy + 1][j] = (T)0;
+          }
+        }
+        if (c == 0) continue;
+        // node A sees column c-1 as dx, node B column c: blocks (dz, dx = c - 2)
+        const int dx = c - 2;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = o >> 2;
+            const int bx = dx + 1 - ox, by = dy + 1 - oy, bz = dz + 1 - oz;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            T c9[9];
+            X2Tab<T>::load9(&kt[((((dz + 1) * 3 + (dx + 1)) * 3 + (dy + 1)) * 8 + o) * TS], c9);
+            const T EA = Eg[ox][oy][oz], EB = Eg[ox + 1][oy][oz];
+            T sA[3], sB[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              sA[j] = EA * col[dx + 1][dy + 1][j];
+              sB[j] = EB * col[dx + 2][dy + 1][j];
+            }
+#ifdef SKTB_X2S_SINGLE_CHAIN
+            const int h = 0;
+#else
+            const int h = (o ^ (o >> 1) ^ (o >> 2)) & 1;
+#endif
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) yA[h][i] = fma(c9[3 * i + j], sA[j], yA[h][i]);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) yB[h][i] = fma(c9[3 * i + j], sB[j], yB[h][i]);
+            }
+          }
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb == 1 && !hasB) break;
+        const int n = nb ? nB : nA;
+        const unsigned dm = nb ? dmB : dmA;
+        const int r = n - (int)node0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double a = nb ? (double)(yB[0][i] + yB[1][i]) : (double)(yA[0][i] + yA[1][i]);
+          if ((dm >> i) & 1u) a = x[3 * n + i];
+          if (MODE == 1)
+            a = x[3 * n + i] + sm_omega * sm_dinv[3 * r + i] * (sm_b[3 * r + i] - a);
+          y[3 * r + i] = a;
+          if (DOT) dot = fma(a, dotv[3 * r + i], dot);
+        }
+      }
+    }
+  }
+  if (DOT) {
+    double v[1] = {dot};
+    grid_reduce<1>(v, partials, ticket, dot_out);
+  }
+}
+
 // whole planes only; returns -1 when the range is not eligible
 template <typename T, int MODE>
 static int launch_x2(const sktb_gridop *op, int64_t node0, int64_t n_nodes, const double *x,
@@ -792,6 +956,18 @@ static int launch_x2(const sktb_gridop *op, int64_t node0, int64_t n_nodes, cons
   const int64_t trips = (items + kX2Block - 1) / kX2Block;
   const int64_t cap = (int64_t)kNumSM * SKTB_X2_MINB;
   const int g = (int)(trips < cap ? trips : cap);
+  if (op->x2s == 2 || (op->x2s == 1 && sizeof(T) == 4)) {
+    const int64_t cap2 = (int64_t)kNumSM * 2;   // 128 registers: two CTAs per SM
+    const int g2 = (int)(trips < cap2 ? trips : cap2);
+    if (dotv)
+      hexgrid_apply_x2s_kernel<T, MODE, true><<<g2, kX2Block, 0, st>>>(
+          P, z0, nzs, node0, x, y, dotv, rs->partials, rs->ticket, dot_out, S, b, dinv, omega);
+    else
+      hexgrid_apply_x2s_kernel<T, MODE, false><<<g2, kX2Block, 0, st>>>(
+          P, z0, nzs, node0, x, y, nullptr, nullptr, nullptr, nullptr, S, b, dinv, omega);
+    SKTB_KERNEL_OK();
+    return 0;
+  }
   if (dotv)
     hexgrid_apply_x2_kernel<T, MODE, true><<<g, kX2Block, 0, st>>>(
         P, z0, nzs, node0, x, y, dotv, rs->partials, rs->ticket, dot_out, S, b, dinv, omega);
@@ -1268,6 +1444,8 @@ extern "C" int sktb_gridop_create(sktb_gridop **out, int dpn, const int32_t *np_
       // coefficient blocks of the x2 kernel, slot = (((dz+1) 3 + dx+1) 3 + dy+1) 8 + o
       const char *envx = getenv("SKTB_GRIDOP_X2");
       op->x2 = !(envx && envx[0] == '0');
+      const char *envs = getenv("SKTB_GRIDOP_X2S");
+      if (envs) op->x2s = envs[0] == '1' ? 2 : (envs[0] == '0' ? 0 : 1);
       std::vector<double> kt((size_t)kX2Slots * 10, 0.0);
       std::vector<float> ktf((size_t)kX2Slots * 12, 0.f);
       for (int dz = -1; dz <= 1; ++dz)

@@ -36,7 +36,8 @@ struct MgLevel {
   const double *vals = nullptr, *inv_diag = nullptr;
   const uint8_t *mask = nullptr;  // per dof, may be null
   const sktb_gridop *gop = nullptr;  // level 0 only: matrix-free operator
-  double *dense_inv = nullptr;       // coarsest level only: dense inverse (owned)
+  double *dense_inv = nullptr;       // coarsest level only: dense inverse (owned unless shared)
+  bool dense_shared = false;         // dense_inv belongs to another hierarchy (sktb_mg_share_coarsest)
   int dense_n = 0;                   // 0: not factored
   double *x = nullptr, *b = nullptr, *tmp = nullptr;  // owned work vectors
   // level 0 only: rows owned by this rank (node0 = 0, n_nodes = n_global when
@@ -90,7 +91,7 @@ extern "C" void sktb_mg_destroy(sktb_mg *m) {
     dev_free(l.x);
     cudaFree(l.b);
     cudaFree(l.tmp);
-    cudaFree(l.dense_inv);
+    if (!l.dense_shared) cudaFree(l.dense_inv);
     cudaFree(l.d);
     dev_free(l.x2);
     dev_free(l.res);
@@ -754,6 +755,7 @@ extern "C" int sktb_mg_factor_coarsest(sktb_mg *m, void *stream) {
     l.dense_n = 0;
     return 0;
   }
+  SKTB_REQUIRE(!l.dense_shared, "the coarsest level borrows another hierarchy's inverse");
   SKTB_CUDA_OK(cudaSetDevice(m->device));
   if (!l.dense_inv)
     SKTB_CUDA_OK(cudaMalloc(&l.dense_inv, sizeof(double) * kDenseMax * kDenseMax));
@@ -769,6 +771,24 @@ extern "C" int sktb_mg_factor_coarsest(sktb_mg *m, void *stream) {
       (int)l.n_nodes, l.node_ptr, l.node_col, l.vals, l.dense_inv);
   SKTB_KERNEL_OK();
   l.dense_n = n;
+  return 0;
+}
+
+// A second V-cycle workspace on the same level operators (concurrent load cases:
+// one hierarchy of work vectors per CUDA stream) borrows the exact inverse of the
+// coarsest level instead of factoring it again.  Call after sktb_mg_set_level of
+// dst's coarsest level and after src was factored; the caller orders the streams.
+extern "C" int sktb_mg_share_coarsest(sktb_mg *dst, const sktb_mg *src) {
+  SKTB_REQUIRE(dst && src && dst != src && dst->lv.size() == src->lv.size() &&
+                   dst->lv.size() >= 2,
+               "bad argument");
+  MgLevel &d = dst->lv.back();
+  const MgLevel &c = src->lv.back();
+  SKTB_REQUIRE(d.n_nodes == c.n_nodes && d.vals == c.vals, "the coarsest levels differ");
+  SKTB_REQUIRE(d.dense_shared || !d.dense_inv, "dst already owns an inverse");
+  d.dense_inv = c.dense_inv;
+  d.dense_n = c.dense_n;
+  d.dense_shared = true;
   return 0;
 }
 

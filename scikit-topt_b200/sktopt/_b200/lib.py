@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsktopt_b200.so")
+# SKTOPT_B200_LIB: another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("SKTOPT_B200_LIB") or os.path.join(_HERE, "libsktopt_b200.so")
 
 _lib = None
 
@@ -83,6 +84,7 @@ SIGNATURES = {
     "sktb_mg_set_level_sweeps": [C.c_void_p, i32, i32],
     "sktb_mg_set_level_cheby": [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p],
     "sktb_mg_factor_coarsest": [C.c_void_p, c_stream],
+    "sktb_mg_share_coarsest": [C.c_void_p, C.c_void_p],
     "sktb_mg_set_level0_grid": [C.c_void_p, C.c_void_p, i64, c_f64p, c_u8p],
     "sktb_elem_combine": [i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_restrict": [i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],

@@ -166,6 +166,7 @@ class FeaEngine:
         self._hist_pool = {}
         self._proj_tmp = []
         self._pcg_pool, self._stream_pool = [], []   # concurrent load cases (solve_many)
+        self._mg_pool = []
         self._rhs_pool = []
         self._last_iters = {}    # load -> iterations of its previous multigrid solve
         self._setup_stream, self._mg_ready = None, None
@@ -389,15 +390,20 @@ class FeaEngine:
                 return self._finish_solve(x, rtol)
             logger.warning("scalar multigrid PCG did not converge; continuing with Jacobi PCG")
         self._wait_mg()
+        if use_mg:
+            # predicted polling, as on the matrix-free path
+            self.pcg.set_first_batch(max(self._last_iters.get(load, 0) - 1, 2))
         self.pcg.solve(self.node_ptr_loc if block3 else self.row_ptr,
                        self.node_col_loc if block3 else self.col_idx,
                        self.vals if vals is None else vals, self.inv_diag,
                        rhs[lo:hi], x[lo:hi],
                        dpn_hint=self.dpn, rtol=rtol, maxiter=mi_first,
                        use_x0=self.warm_start,
-                       check_every=2 if use_mg else 32, block3=block3,
+                       check_every=1 if use_mg else 32, block3=block3,
                        max_deg=getattr(self, "max_deg", 0),
                        mg=self.mg if use_mg else None)
+        if use_mg:
+            self._last_iters[load] = self.pcg.last_iters
         if use_mg and not self.pcg.last_converged:
             # safety net: a V-cycle that stopped contracting (smoother out of its
             # stability range) must not cost the solve -- finish with Jacobi
@@ -411,17 +417,19 @@ class FeaEngine:
         """One solve per right-hand side (load case) on the current operator.
         Returns the solutions (``self.solution(i)``).
 
-        On one GPU with the Jacobi-preconditioned assembled operator (unstructured
-        meshes: BASELINE config 3) the load cases run CONCURRENTLY, one CUDA stream
-        and one PCG workspace per load driven by its own host thread: such a solve
-        is a chain of small dependent launches on an L2-resident operator, so two
-        of them overlap almost perfectly.  (The reference solves all loads against
-        one LU factorisation, ``fea/solver_elastic.py:386-390``.)  Everything else
-        (multigrid, matrix-free, sharded) solves them one after the other."""
+        On one GPU with an assembled operator (unstructured or lattice-numbered
+        meshes: BASELINE config 3) the load cases run CONCURRENTLY, one CUDA stream,
+        one PCG workspace and (with multigrid) one V-cycle workspace per load, each
+        driven by its own host thread: such a solve is a chain of small dependent
+        launches on an L2-resident operator, so two of them overlap almost perfectly.
+        (The reference solves all loads against one LU factorisation,
+        ``fea/solver_elastic.py:386-390``.)  Matrix-free, scalar-multigrid and
+        sharded engines solve them one after the other."""
         n = len(rhs_list)
+        use_mg = self.mg is not None and self.mg_enabled
         concurrent = (n > 1 and not self.sharded and not self.matrix_free
-                      and not (self.mg is not None and self.mg_enabled)
                       and not (self.smg is not None and self.mg_enabled)
+                      and not (use_mg and self.mg.cheb_alpha > 0.0)
                       and os.environ.get("SKTOPT_B200_CONCURRENT_LOADS", "1") != "0")
         if not concurrent:
             return [self.solve(b, i, rtol, maxiter) for i, b in enumerate(rhs_list)]
@@ -435,6 +443,17 @@ class FeaEngine:
         pcgs = [self.pcg] + self._pcg_pool[:n - 1]
         mi = default_maxiter(self.n_dof) if maxiter is None else int(maxiter)
         block3 = self.spmv_format == "bsr3"
+        # multigrid (assembled level 0, e.g. the lattice hierarchy of BASELINE config
+        # 3's tetrahedra): one V-cycle workspace per load on the shared operators
+        mgs = [None] * n
+        if use_mg:
+            from sktopt.fea._multigrid import MultigridWorkspace
+            self._wait_mg()
+            while len(self._mg_pool) < n - 1:
+                self._mg_pool.append(MultigridWorkspace(self.mg))
+            mgs = [self.mg] + self._mg_pool[:n - 1]
+            for w in mgs[1:]:
+                w.refresh()
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
@@ -445,12 +464,26 @@ class FeaEngine:
                 st = main if i == 0 else self._stream_pool[i - 1]
                 with torch.cuda.stream(st):
                     st.wait_event(ready)
+                    if use_mg:
+                        pcgs[i].set_first_batch(max(self._last_iters.get(i, 0) - 1, 2))
                     pcgs[i].solve(self.node_ptr_loc if block3 else self.row_ptr,
                                   self.node_col_loc if block3 else self.col_idx,
                                   self.vals, self.inv_diag, rhs_list[i], xs[i],
-                                  dpn_hint=self.dpn, rtol=rtol, maxiter=mi,
-                                  use_x0=self.warm_start, check_every=32, block3=block3,
-                                  max_deg=getattr(self, "max_deg", 0))
+                                  dpn_hint=self.dpn, rtol=rtol,
+                                  maxiter=min(mi, 400) if use_mg else mi,
+                                  use_x0=self.warm_start, check_every=1 if use_mg else 32,
+                                  block3=block3, max_deg=getattr(self, "max_deg", 0),
+                                  mg=mgs[i])
+                    if use_mg:
+                        self._last_iters[i] = pcgs[i].last_iters
+                    if use_mg and not pcgs[i].last_converged:
+                        # safety net, as in ``solve``: finish with Jacobi-PCG
+                        logger.warning("multigrid PCG did not converge; continuing with "
+                                       "Jacobi PCG")
+                        pcgs[i].solve(self.node_ptr_loc, self.node_col_loc, self.vals,
+                                      self.inv_diag, rhs_list[i], xs[i], dpn_hint=self.dpn,
+                                      rtol=rtol, maxiter=mi, use_x0=True, check_every=32,
+                                      block3=True, max_deg=self.max_deg)
             except Exception as e:                    # re-raised on the caller's thread
                 errors[i] = e
 

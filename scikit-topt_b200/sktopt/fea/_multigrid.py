@@ -384,7 +384,10 @@ class Multigrid:
         # smoothing sweeps per level: "a,b,c,..." for levels 0,1,2,... (last value
         # repeats).  Levels 0/1 carry the cost, the cheap coarse levels get more sweeps
         # (measured at C2: 34 -> 22 PCG iterations)
-        sweeps = [int(v) for v in os.environ.get("SKTOPT_B200_MG_SWEEPS", "1,1,2,3").split(",")]
+        # (lattice hierarchy, assembled level 0: the products are cheap next to the
+        # ~50 small launches of a cycle, two sweeps everywhere pay: C3 44.6 -> 37.1 ms)
+        sweeps = [int(v) for v in os.environ.get(
+            "SKTOPT_B200_MG_SWEEPS", "2,2,2,3" if self.algebraic else "1,1,2,3").split(",")]
         self.sweeps = [sweeps[min(l, len(sweeps) - 1)] for l in range(self.n_levels)]
         for l, nu in enumerate(self.sweeps):
             _lib.check(self.lib.sktb_mg_set_level_sweeps(h, l, nu))
@@ -626,6 +629,65 @@ class Multigrid:
             wait()                 # a set-up running on the engine's side stream
         _lib.check(self.lib.sktb_mg_vcycle(self.handle, dev._ptr(r), dev._ptr(z), dev._stream()))
         return z
+
+
+class MultigridWorkspace:
+    """A second set of V-cycle work vectors on the level operators of ``parent``
+    (assembled level 0, one GPU): load cases solved concurrently on their own CUDA
+    streams each need their own iterates and right-hand sides, the operators,
+    masks, transfer tables, damping and the exact coarsest-level inverse are the
+    parent's.  ``refresh`` must follow every ``parent.setup()``."""
+
+    def __init__(self, parent: "Multigrid"):
+        if parent.eng.matrix_free or parent.eng.sharded or parent.cheb_alpha > 0.0:
+            raise ValueError("workspace clones need an assembled, unsharded hierarchy")
+        self.parent = parent
+        self.lib = lib = parent.lib
+        h = C.c_void_p()
+        _lib.check(lib.sktb_mg_create(C.byref(h), parent.n_levels, torch.cuda.current_device()))
+        self.handle = h
+        _lib.check(lib.sktb_mg_set_params(h, float(parent.omega), int(parent.nu_coarse)))
+        _lib.check(lib.sktb_mg_set_precision(h, int(parent.fp32)))
+        _lib.check(lib.sktb_mg_set_fused_tail(h, 0))
+        for l, tr in enumerate(parent.transfers):
+            _lib.check(lib.sktb_mg_set_transfer(
+                h, l, tr["fnp"].ctypes.data_as(C.c_void_p), tr["cnp"].ctypes.data_as(C.c_void_p),
+                dev._ptr(tr["c0"]), dev._ptr(tr["c1"]), dev._ptr(tr["w0"]), dev._ptr(tr["w1"]),
+                dev._ptr(tr["fT"]), dev._ptr(tr["wT"])))
+        for l, nu in enumerate(parent.sweeps):
+            _lib.check(lib.sktb_mg_set_level_sweeps(h, l, nu))
+        self.setup_count = -1
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.sktb_mg_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def refresh(self):
+        par, lib, h = self.parent, self.lib, self.handle
+        if self.setup_count == par.setup_count:
+            return
+        eng = par.eng
+        _lib.check(lib.sktb_mg_set_level0_range(h, int(eng.node0), int(eng.dm.n_nodes)))
+        _lib.check(lib.sktb_mg_set_level(
+            h, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()), int(eng.max_deg),
+            dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc), dev._ptr(eng.vals),
+            dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        for l in range(1, par.n_levels):
+            lv = par.levels[l]
+            _lib.check(lib.sktb_mg_set_level(
+                h, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()), lv["max_deg"],
+                dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
+                dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+        _lib.check(lib.sktb_mg_share_coarsest(h, par.handle))
+        if par.lambda_max is not None:
+            for l, lam in enumerate(par.lambda_max):
+                _lib.check(lib.sktb_mg_set_level_omega(h, l, float(1.75 / (1.03 * lam))))
+        self.setup_count = par.setup_count
 
 
 class ScalarMultigrid:
