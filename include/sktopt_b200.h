@@ -189,6 +189,18 @@ int sktb_mg_set_transfer(sktb_mg *m, int level, const int32_t *fine_np_h,
                          const int32_t *ax_c1, const double *ax_w0,
                          const double *ax_w1, const int32_t *axT_f,
                          const double *axT_w);
+/* single-precision copy of a level's values (same node-block layout, made with
+ * sktb_f64_to_f32; device, caller-owned): the V-cycle's products on that level
+ * stream half the bytes, accumulation stays fp64.  Call after sktb_mg_set_level
+ * (which forgets the copy); NULL switches back to the fp64 values.                */
+int sktb_mg_set_level_vals32(sktb_mg *m, int level, const float *vals32);
+/* out[i] = (float) in[i]  (in 16-byte, out 8-byte aligned)                         */
+int sktb_f64_to_f32(int64_t n, const double *in, float *out, void *stream);
+/* y = A x with single-precision values in the layout of sktb_spmv_bsr3 (bulk-async
+ * pipeline of sktb_spmv_bsr3_tma, fp64 x / y / accumulation)                       */
+int sktb_spmv_bsr3_tma_f32(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                           const int32_t *node_ptr, const int32_t *node_col,
+                           const float *vals, const double *x, double *y, void *stream);
 /* dst (a second set of work vectors on the same level operators, e.g. one per
  * concurrently solved load case) borrows src's exact coarsest-level inverse        */
 int sktb_mg_share_coarsest(sktb_mg *dst, const sktb_mg *src);

@@ -60,6 +60,13 @@ int launch_spmv_bsr3_tma_jacobi(int64_t n_nodes, int64_t n_blocks, int max_deg,
                                 const double *vals, const double *x, double *y,
                                 const JacobiEpi &epi, cudaStream_t st);
 
+// values kept in single precision (large multigrid levels: half the HBM stream,
+// fp64 accumulation); epi.b == nullptr: plain product
+int launch_spmv_bsr3_tma_f32(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                             const int32_t *node_ptr, const int32_t *node_col,
+                             const float *vals, const double *x, double *y,
+                             const JacobiEpi &epi, cudaStream_t st);
+
 // below ~8k nodes the bulk-async pipeline's fixed start-up (~10 us) exceeds the
 // work and the warp-per-node kernel is faster (measured: 2.7k nodes 13 -> 7 us,
 // 16k nodes 13 vs 17 us)

@@ -34,6 +34,9 @@ struct MgLevel {
   int max_deg = 0;
   const int32_t *node_ptr = nullptr, *node_col = nullptr;
   const double *vals = nullptr, *inv_diag = nullptr;
+  // single-precision copy of vals (caller-owned, may be null): the V-cycle's
+  // products on this level stream it instead (sktb_mg_set_level_vals32)
+  const float *vals32 = nullptr;
   const uint8_t *mask = nullptr;  // per dof, may be null
   const sktb_gridop *gop = nullptr;  // level 0 only: matrix-free operator
   double *dense_inv = nullptr;       // coarsest level only: dense inverse (owned unless shared)
@@ -192,8 +195,18 @@ extern "C" int sktb_mg_set_level(sktb_mg *m, int level, int64_t n_nodes,
   l.node_ptr = node_ptr;
   l.node_col = node_col;
   l.vals = vals;
+  l.vals32 = nullptr;
   l.inv_diag = inv_diag;
   l.mask = mask;
+  return 0;
+}
+
+// single-precision copy of the level's values (same layout; sktb_f64_to_f32) for
+// the V-cycle's products; call after sktb_mg_set_level, which forgets it
+extern "C" int sktb_mg_set_level_vals32(sktb_mg *m, int level, const float *vals32) {
+  SKTB_REQUIRE(m && level >= 0 && level < (int)m->lv.size(), "bad level");
+  SKTB_REQUIRE(m->lv[level].vals, "set the level before its single-precision copy");
+  m->lv[level].vals32 = vals32;
   return 0;
 }
 
@@ -1003,9 +1016,13 @@ static int level_spmv(const MgLevel &l, const double *x, double *y, cudaStream_t
     return launch_hexgrid_apply(l.gop, l.node0, l.n_nodes, x, y, nullptr, nullptr,
                                 nullptr, nullptr, st);
   }
-  int rc = l.n_nodes < kTmaMinNodes ? -1 : launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
-                                l.node_col, l.vals, x, y, nullptr, nullptr,
-                                nullptr, nullptr, st);
+  int rc = -1;
+  if (l.n_nodes >= kTmaMinNodes && l.vals32)
+    rc = launch_spmv_bsr3_tma_f32(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr, l.node_col,
+                                  l.vals32, x, y, JacobiEpi(), st);
+  if (rc == -1 && l.n_nodes >= kTmaMinNodes)
+    rc = launch_spmv_bsr3_tma(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr, l.node_col, l.vals,
+                              x, y, nullptr, nullptr, nullptr, nullptr, st);
   if (rc != -1) return rc;
   return launch_spmv_bsr3(l.n_nodes, l.node_ptr, l.node_col, l.vals, x, y,
                           nullptr, nullptr, nullptr, nullptr, st);
@@ -1030,10 +1047,13 @@ static int level_sweep(MgLevel &l, const double *b, double omega, cudaStream_t s
     epi.xo = l.x + 3 * l.node0;
     y = l.x2 + 3 * l.node0;
   }
-  int rc = l.n_nodes < kTmaMinNodes
-               ? -1
-               : launch_spmv_bsr3_tma_jacobi(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr,
-                                             l.node_col, l.vals, l.x, y, epi, st);
+  int rc = -1;
+  if (l.n_nodes >= kTmaMinNodes && l.vals32)
+    rc = launch_spmv_bsr3_tma_f32(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr, l.node_col,
+                                  l.vals32, l.x, y, epi, st);
+  if (rc == -1 && l.n_nodes >= kTmaMinNodes)
+    rc = launch_spmv_bsr3_tma_jacobi(l.n_nodes, l.n_blocks, l.max_deg, l.node_ptr, l.node_col,
+                                     l.vals, l.x, y, epi, st);
   if (rc == -1)
     rc = launch_spmv_bsr3_jacobi(l.n_nodes, l.node_ptr, l.node_col, l.vals, l.x, y, epi, st);
   if (rc) return rc;

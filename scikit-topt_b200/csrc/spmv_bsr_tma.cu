@@ -30,12 +30,20 @@ constexpr int kStages = 3;
 constexpr int kMaxDeg = 27;   // hex8 node graph
 constexpr int kConsumerWarps = 6;
 constexpr int kProducerWarp = 6;
-constexpr int kValCap = kTile * 9 * kMaxDeg + 2;  // doubles (+ alignment slack)
 constexpr int kColCap = kTile * kMaxDeg + 8;      // int32   (+ alignment slack)
 constexpr int kPtrCap = 36;                       // >= 33 slots (one per producer lane + end)
-constexpr int kStageBytes = kValCap * 8 + kColCap * 4 + kPtrCap * 4;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 16;
-static_assert(kStageBytes % 16 == 0, "stages must stay 16-byte aligned");
+// V = double: the PCG operator; V = float: multigrid levels whose values are kept
+// in single precision (half the HBM stream of a V-cycle product; the accumulation
+// stays fp64)
+template <typename V> struct TmaCfg {
+  static constexpr int kAlign = 16 / (int)sizeof(V);              // values per 16 bytes
+  static constexpr int kValCap = kTile * 9 * kMaxDeg + 2 * kAlign;  // + alignment slack
+  static constexpr int kValBytes = kValCap * (int)sizeof(V);
+  static constexpr int kStageBytes = kValBytes + kColCap * 4 + kPtrCap * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 16;
+  static_assert(kValBytes % 16 == 0 && kStageBytes % 16 == 0,
+                "stages must stay 16-byte aligned");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -77,28 +85,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
-struct StagePtrs {
-  double *vals;
+template <typename V> struct StagePtrs {
+  V *vals;
   int32_t *cols;
   int32_t *nptr;
 };
 
-__device__ __forceinline__ StagePtrs stage_ptrs(unsigned char *smem, int s) {
-  unsigned char *b = smem + (size_t)s * kStageBytes;
-  StagePtrs p;
-  p.vals = (double *)b;
-  p.cols = (int32_t *)(b + kValCap * 8);
-  p.nptr = (int32_t *)(b + kValCap * 8 + kColCap * 4);
+template <typename V>
+__device__ __forceinline__ StagePtrs<V> stage_ptrs(unsigned char *smem, int s) {
+  unsigned char *b = smem + (size_t)s * TmaCfg<V>::kStageBytes;
+  StagePtrs<V> p;
+  p.vals = (V *)b;
+  p.cols = (int32_t *)(b + TmaCfg<V>::kValBytes);
+  p.nptr = (int32_t *)(b + TmaCfg<V>::kValBytes + kColCap * 4);
   return p;
 }
 
 // producer warp: stage the tile's node_ptr slice and issue its two bulk copies
+template <typename V>
 __device__ __forceinline__ void issue_tile(
     unsigned char *smem, uint64_t *full, int s, int64_t tile, int64_t n_nodes,
     int64_t n_blocks, const int32_t *__restrict__ node_ptr,
-    const int32_t *__restrict__ node_col, const double *__restrict__ vals) {
+    const int32_t *__restrict__ node_col, const V *__restrict__ vals) {
+  constexpr int64_t AL = TmaCfg<V>::kAlign;
   const int lane = threadIdx.x & 31;
-  StagePtrs sp = stage_ptrs(smem, s);
+  StagePtrs<V> sp = stage_ptrs<V>(smem, s);
   const int64_t n_a = tile * kTile;
   const int64_t n_b = (n_a + kTile < n_nodes) ? n_a + kTile : n_nodes;
   const int nn = (int)(n_b - n_a);
@@ -110,14 +121,15 @@ __device__ __forceinline__ void issue_tile(
   __syncwarp();
   if (lane == 0) {
     // 16-byte aligned windows around the tile's values / block columns
-    const int64_t v_lo = (int64_t)9 * s_a - (s_a & 1);
-    const int64_t v_hi = ((int64_t)9 * s_b + 1) & ~(int64_t)1;
+    const int64_t v_lo = ((int64_t)9 * s_a) & ~(AL - 1);
+    const int64_t v_hi = ((int64_t)9 * s_b + AL - 1) & ~(AL - 1);
     const int64_t v_end = (int64_t)9 * n_blocks;
-    const int64_t v_bulk_hi = v_hi <= v_end ? v_hi : (v_end & ~(int64_t)1);
+    const int64_t v_bulk_hi = v_hi <= v_end ? v_hi : (v_end & ~(AL - 1));
     const int64_t c_lo = (int64_t)s_a - (s_a & 3);
     const int64_t c_hi = ((int64_t)s_b + 3) & ~(int64_t)3;
     const int64_t c_bulk_hi = c_hi <= n_blocks ? c_hi : (n_blocks & ~(int64_t)3);
-    const uint32_t vbytes = v_bulk_hi > v_lo ? (uint32_t)((v_bulk_hi - v_lo) * 8) : 0u;
+    const uint32_t vbytes =
+        v_bulk_hi > v_lo ? (uint32_t)((v_bulk_hi - v_lo) * (int64_t)sizeof(V)) : 0u;
     const uint32_t cbytes = c_bulk_hi > c_lo ? (uint32_t)((c_bulk_hi - c_lo) * 4) : 0u;
     // tails that would run past the arrays: plain loads (at most 1 / 3 items)
     for (int64_t k = (v_bulk_hi > v_lo ? v_bulk_hi : v_lo); k < (int64_t)9 * s_b; ++k)
@@ -131,19 +143,19 @@ __device__ __forceinline__ void issue_tile(
   }
 }
 
-template <bool DOT>
+template <bool DOT, typename V = double>
 __global__ void __launch_bounds__(kBlock, 2)
     spmv_bsr3_tma_kernel(int64_t n_nodes, int64_t n_blocks,
                          const int32_t *__restrict__ node_ptr,
                          const int32_t *__restrict__ node_col,
-                         const double *__restrict__ vals,
+                         const V *__restrict__ vals,
                          const double *__restrict__ x, double *__restrict__ y,
                          const double *__restrict__ dotv, double *partials,
                          unsigned int *ticket, double *dot_out,
                          const PcgScalars *S, const JacobiEpi J) {
   if (S && S->rr <= S->tol2) return;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t *full = (uint64_t *)(smem + (size_t)kStages * kStageBytes);
+  uint64_t *full = (uint64_t *)(smem + (size_t)kStages * TmaCfg<V>::kStageBytes);
   uint64_t *empty = full + kStages;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t n_tiles = (n_nodes + kTile - 1) / kTile;
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kBlock, 2)
     uint32_t parity = 1;  // a fresh barrier passes a wait on the previous phase
     for (int64_t tile = t_lo; tile < t_hi; ++tile) {
       mbar_wait(&empty[stage], parity);
-      issue_tile(smem, full, stage, tile, n_nodes, n_blocks, node_ptr, node_col, vals);
+      issue_tile<V>(smem, full, stage, tile, n_nodes, n_blocks, node_ptr, node_col, vals);
       if (++stage == kStages) {
         stage = 0;
         parity ^= 1u;
@@ -181,11 +193,11 @@ __global__ void __launch_bounds__(kBlock, 2)
     uint32_t parity = 0;
     for (int64_t tile = t_lo; tile < t_hi; ++tile) {
       mbar_wait(&full[stage], parity);
-      StagePtrs sp = stage_ptrs(smem, stage);
+      StagePtrs<V> sp = stage_ptrs<V>(smem, stage);
       const int64_t n_a = tile * kTile;
       const int nn = (int)((n_a + kTile < n_nodes ? n_a + kTile : n_nodes) - n_a);
       const int32_t s_a = sp.nptr[0];
-      const int64_t v_lo = (int64_t)9 * s_a - (s_a & 1);
+      const int64_t v_lo = ((int64_t)9 * s_a) & ~((int64_t)TmaCfg<V>::kAlign - 1);
       const int64_t c_lo = (int64_t)s_a - (s_a & 3);
       double acc = 0.0;
       if (ln < nn) {
@@ -193,16 +205,16 @@ __global__ void __launch_bounds__(kBlock, 2)
         const int32_t deg = sp.nptr[ln + 1] - s0;
         const int32_t b0 = (deg * quarter) >> 2;
         const int32_t b1 = (deg * (quarter + 1)) >> 2;
-        const double *vp = sp.vals + ((int64_t)9 * s0 - v_lo) + (int64_t)ri * 3 * deg;
+        const V *vp = sp.vals + ((int64_t)9 * s0 - v_lo) + (int64_t)ri * 3 * deg;
         const int32_t *cp = sp.cols + ((int64_t)s0 - c_lo);
         double acc1 = 0.0, acc2 = 0.0;
 #pragma unroll 4
         for (int32_t b = b0; b < b1; ++b) {
           const double *xb = x + (int64_t)3 * cp[b];
-          const double *vb = vp + 3 * b;
-          acc += vb[0] * __ldg(&xb[0]);
-          acc1 += vb[1] * __ldg(&xb[1]);
-          acc2 += vb[2] * __ldg(&xb[2]);
+          const V *vb = vp + 3 * b;
+          acc += (double)vb[0] * __ldg(&xb[0]);
+          acc1 += (double)vb[1] * __ldg(&xb[1]);
+          acc2 += (double)vb[2] * __ldg(&xb[2]);
         }
         acc += acc1 + acc2;
       }
@@ -230,39 +242,39 @@ __global__ void __launch_bounds__(kBlock, 2)
   }
 }
 
-bool g_attr_set[2] = {false, false};
+bool g_attr_set[4] = {false, false, false, false};
 
 }  // namespace
 
 // returns 0 on success, -1 if the layout is not eligible (caller falls back)
+template <typename V>
 static int launch_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                       const int32_t *node_ptr, const int32_t *node_col,
-                      const double *vals, const double *x, double *y,
+                      const V *vals, const double *x, double *y,
                       const double *dotv, ReduceScratch *rs, double *dot_out,
                       const PcgScalars *S, const JacobiEpi &epi, cudaStream_t st) {
   if (max_deg > kMaxDeg || n_nodes < 8 * kTile) return -1;
+  constexpr int kSmem = TmaCfg<V>::kSmemBytes;
   const int64_t n_tiles = (n_nodes + kTile - 1) / kTile;
   int64_t g = (int64_t)kNumSM * 2;
   if (g > n_tiles) g = n_tiles;
   const int grid = (int)g;
-  const int which = dotv ? 1 : 0;
+  const int which = (dotv ? 1 : 0) + (sizeof(V) == 4 ? 2 : 0);
   if (!g_attr_set[which]) {
     if (dotv)
-      SKTB_CUDA_OK(cudaFuncSetAttribute(spmv_bsr3_tma_kernel<true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
+      SKTB_CUDA_OK(cudaFuncSetAttribute(spmv_bsr3_tma_kernel<true, V>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     else
-      SKTB_CUDA_OK(cudaFuncSetAttribute(spmv_bsr3_tma_kernel<false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
+      SKTB_CUDA_OK(cudaFuncSetAttribute(spmv_bsr3_tma_kernel<false, V>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     g_attr_set[which] = true;
   }
   if (dotv)
-    spmv_bsr3_tma_kernel<true><<<grid, kBlock, kSmemBytes, st>>>(
+    spmv_bsr3_tma_kernel<true, V><<<grid, kBlock, kSmem, st>>>(
         n_nodes, n_blocks, node_ptr, node_col, vals, x, y, dotv, rs->partials,
         rs->ticket, dot_out, S, epi);
   else
-    spmv_bsr3_tma_kernel<false><<<grid, kBlock, kSmemBytes, st>>>(
+    spmv_bsr3_tma_kernel<false, V><<<grid, kBlock, kSmem, st>>>(
         n_nodes, n_blocks, node_ptr, node_col, vals, x, y, nullptr, nullptr,
         nullptr, nullptr, S, epi);
   SKTB_KERNEL_OK();
@@ -274,16 +286,63 @@ int launch_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
                          const double *vals, const double *x, double *y,
                          const double *dotv, ReduceScratch *rs, double *dot_out,
                          const PcgScalars *S, cudaStream_t st) {
-  return launch_tma(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y, dotv, rs,
-                    dot_out, S, JacobiEpi(), st);
+  return launch_tma<double>(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y, dotv,
+                            rs, dot_out, S, JacobiEpi(), st);
 }
 
 int launch_spmv_bsr3_tma_jacobi(int64_t n_nodes, int64_t n_blocks, int max_deg,
                                 const int32_t *node_ptr, const int32_t *node_col,
                                 const double *vals, const double *x, double *y,
                                 const JacobiEpi &epi, cudaStream_t st) {
-  return launch_tma(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y, nullptr,
-                    nullptr, nullptr, nullptr, epi, st);
+  return launch_tma<double>(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y,
+                            nullptr, nullptr, nullptr, nullptr, epi, st);
+}
+
+// single-precision values (multigrid levels): plain product, or a fused Jacobi
+// sweep when epi.b is set
+int launch_spmv_bsr3_tma_f32(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                             const int32_t *node_ptr, const int32_t *node_col,
+                             const float *vals, const double *x, double *y,
+                             const JacobiEpi &epi, cudaStream_t st) {
+  return launch_tma<float>(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y,
+                           nullptr, nullptr, nullptr, nullptr, epi, st);
+}
+
+// out[i] = (float) in[i]
+__global__ void __launch_bounds__(kBlock)
+    f64_to_f32_kernel(int64_t n, const double *__restrict__ in, float *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+    if (i + 1 < n) {
+      const double2 v = *reinterpret_cast<const double2 *>(in + i);
+      *reinterpret_cast<float2 *>(out + i) = make_float2((float)v.x, (float)v.y);
+    } else {
+      out[i] = (float)in[i];
+    }
+  }
+}
+
+extern "C" int sktb_f64_to_f32(int64_t n, const double *in, float *out, void *stream) {
+  SKTB_REQUIRE(in && out && n >= 0, "null argument");
+  SKTB_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, "unaligned buffer");
+  if (n == 0) return 0;
+  f64_to_f32_kernel<<<grid_for((n + 1) / 2), kBlock, 0, (cudaStream_t)stream>>>(n, in, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
+
+extern "C" int sktb_spmv_bsr3_tma_f32(int64_t n_nodes, int64_t n_blocks, int max_deg,
+                                      const int32_t *node_ptr, const int32_t *node_col,
+                                      const float *vals, const double *x, double *y,
+                                      void *stream) {
+  SKTB_REQUIRE(node_ptr && node_col && vals && x && y, "null argument");
+  int rc = launch_spmv_bsr3_tma_f32(n_nodes, n_blocks, max_deg, node_ptr, node_col, vals, x, y,
+                                    JacobiEpi(), (cudaStream_t)stream);
+  if (rc == -1) {
+    sktb::set_error("layout not eligible for the bulk-async SpMV (max_deg > 27 or tiny)");
+    return 2;
+  }
+  return rc;
 }
 
 extern "C" int sktb_spmv_bsr3_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,

@@ -422,6 +422,26 @@ def spmv_bsr3_tma(node_ptr, node_col, vals, x, max_deg, out=None):
     return out
 
 
+def to_f32(v, out=None):
+    """Single-precision copy of an fp64 device vector (``sktb_f64_to_f32``)."""
+    if out is None:
+        out = torch.empty(v.numel(), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().sktb_f64_to_f32(int(v.numel()), _ptr(v), C.c_void_p(out.data_ptr()),
+                                           _stream()))
+    return out
+
+
+def spmv_bsr3_tma_f32(node_ptr, node_col, vals32, x, max_deg, out=None):
+    """``spmv_bsr3_tma`` with single-precision values (fp64 x, y, accumulation)."""
+    n_nodes = node_ptr.numel() - 1
+    if out is None:
+        out = torch.empty(3 * n_nodes, dtype=F64, device="cuda")
+    _lib.check(
+        _lib.load().sktb_spmv_bsr3_tma_f32(n_nodes, int(node_col.numel()), int(max_deg), _ptr(node_ptr), _ptr(node_col), C.c_void_p(vals32.data_ptr()), _ptr(x), _ptr(out), _stream())
+    )
+    return out
+
+
 def csr_enforce(row_ptr, col_idx, vals, mask_u8):
     n = row_ptr.numel() - 1
     _lib.check(

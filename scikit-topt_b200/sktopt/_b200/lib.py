@@ -85,6 +85,9 @@ SIGNATURES = {
     "sktb_mg_set_level_cheby": [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p],
     "sktb_mg_factor_coarsest": [C.c_void_p, c_stream],
     "sktb_mg_share_coarsest": [C.c_void_p, C.c_void_p],
+    "sktb_mg_set_level_vals32": [C.c_void_p, i32, C.c_void_p],
+    "sktb_f64_to_f32": [i64, c_f64p, C.c_void_p, c_stream],
+    "sktb_spmv_bsr3_tma_f32": [i64, i64, i32, c_i32p, c_i32p, C.c_void_p, c_f64p, c_f64p, c_stream],
     "sktb_mg_set_level0_grid": [C.c_void_p, C.c_void_p, i64, c_f64p, c_u8p],
     "sktb_elem_combine": [i64, c_i32p, c_u8p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],
     "sktb_elem_restrict": [i64, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_f64p, c_f64p, c_stream],

@@ -269,6 +269,7 @@ class Multigrid:
 
     MIN_FINE_NODES = 1500
     DENSE_MAX_DOFS = 160
+    FP32_LEVEL_MIN_NODES = 50000
 
     def __init__(self, engine, axes, omega: float | None = None, nu_coarse: int = 30,
                  coarsest_max_cells: int = 6, algebraic: bool = False):
@@ -315,6 +316,13 @@ class Multigrid:
         # so it is opt-in
         self.fused_tail = os.environ.get("SKTOPT_B200_MG_FUSED_TAIL", "0") == "1"
         _lib.check(self.lib.sktb_mg_set_fused_tail(h, int(self.fused_tail)))
+        # assembled levels with at least FP32_LEVEL_MIN_NODES nodes keep a
+        # single-precision copy of their values for the V-cycle's products: such a
+        # level is an HBM stream (C2 level 1: 0.26 GB read twice per cycle), the
+        # copy halves it; accumulation, diagonal and damping stay fp64
+        # (SKTOPT_B200_MG_FP32_LEVELS=0 disables)
+        self.fp32_levels = (self.fp32
+                            and os.environ.get("SKTOPT_B200_MG_FP32_LEVELS", "1") != "0")
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
@@ -360,6 +368,8 @@ class Multigrid:
                 inv_diag=torch.empty(3 * (n1 - n0), dtype=dev.F64, device="cuda"),
                 mask=dev.to_dev(mask_c, dev.U8),
             )
+            if self.fp32_levels and (n1 - n0) >= self.FP32_LEVEL_MIN_NODES:
+                lvl["vals32"] = torch.empty(9 * ci_loc.size, dtype=torch.float32, device="cuda")
             if not self.algebraic:
                 lvl.update(ke=torch.empty((n_ke, 576), dtype=dev.F64, device="cuda"),
                            child=dev.to_dev(child, dev.I32), ptype=dev.to_dev(ptype, dev.U8))
@@ -535,6 +545,19 @@ class Multigrid:
             cnt = np.diff(gp["cuts"]) * gp["plane_elems"] * 576
             eng.comm.allgatherv(lv["ke"].view(-1), cnt, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
 
+    def _push_vals32(self, l: int, handle=None, convert: bool = True):
+        """Refresh the single-precision copy of level ``l`` and hand it to the
+        hierarchy (after ``sktb_mg_set_level``, which forgets it)."""
+        lv = self.levels[l]
+        v32 = lv.get("vals32")
+        if v32 is None:
+            return
+        if convert:
+            _lib.check(self.lib.sktb_f64_to_f32(int(v32.numel()), dev._ptr(lv["vals"]),
+                                                C.c_void_p(v32.data_ptr()), dev._stream()))
+        _lib.check(self.lib.sktb_mg_set_level_vals32(
+            self.handle if handle is None else handle, l, C.c_void_p(v32.data_ptr())))
+
     def _galerkin_algebraic(self, l: int, st):
         """vals of level ``l`` = P^T A_{l-1} P, matrix to matrix."""
         eng, lv, tr = self.eng, self.levels[l], self.transfers[l - 1]
@@ -582,6 +605,7 @@ class Multigrid:
                     self.handle, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()),
                     lv["max_deg"], dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]),
                     dev._ptr(lv["vals"]), dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+                self._push_vals32(l)
                 continue
             self._galerkin_level(l, st)
             if sh is not None:
@@ -601,6 +625,7 @@ class Multigrid:
                 self.handle, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()),
                 lv["max_deg"], dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]),
                 dev._ptr(lv["vals"]), dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+            self._push_vals32(l)
         _lib.check(lib.sktb_mg_factor_coarsest(self.handle, st))
         if self.omega_auto and self.setup_count == 0:
             # per-level damping: omega_l * lambda_max_l ~ 1.75, inside the
@@ -683,6 +708,7 @@ class MultigridWorkspace:
                 h, l, lv["node1"] - lv["node0"], int(lv["node_col"].numel()), lv["max_deg"],
                 dev._ptr(lv["node_ptr"]), dev._ptr(lv["node_col"]), dev._ptr(lv["vals"]),
                 dev._ptr(lv["inv_diag"]), dev._ptr(lv["mask"])))
+            par._push_vals32(l, handle=h, convert=False)
         _lib.check(lib.sktb_mg_share_coarsest(h, par.handle))
         if par.lambda_max is not None:
             for l, lam in enumerate(par.lambda_max):

@@ -256,3 +256,55 @@ def test_multigrid_pcg_at_late_stage_contrast(gpu):
     assert it_mg <= 120 and 10 * it_mg < it_j
     assert abs(c_mg[0] - c_j[0]) <= 1e-6 * abs(c_j[0])
     assert np.abs(u_mg - u_j).max() <= 1e-5 * np.abs(u_j).max()
+
+
+def test_single_precision_level_values(gpu, monkeypatch):
+    """Large multigrid levels keep an fp32 copy of their values for the V-cycle's
+    products (csrc/spmv_bsr_tma.cu, V = float): the product must agree with the fp64
+    one to single-precision rounding on ragged rows (boundary nodes: 8 / 12 / 18 /
+    27 blocks), and a hierarchy that uses it must converge like the fp64 one."""
+    sktopt, dev = gpu
+    monkeypatch.setenv("SKTOPT_B200_MATFREE", "0")
+    mesh, basis, D, eng = _engine(sktopt, dims=(4.0, 3.0, 2.0), h=0.125)   # 32 x 24 x 16
+    rho = np.random.default_rng(4).uniform(0.01, 1.0, mesh.nelements)
+    eng.set_modulus(dev.to_dev(rho), 210e3, 210.0, 3.0)
+    eng.assemble(enforce=True)
+    x = dev.to_dev(np.random.default_rng(5).standard_normal(eng.n_dof))
+    v32 = dev.to_f32(eng.vals)
+    assert torch.equal(v32, eng.vals.to(torch.float32))
+    y64 = dev.spmv_bsr3_tma(eng.node_ptr_loc, eng.node_col_loc, eng.vals, x, eng.max_deg)
+    y32 = dev.spmv_bsr3_tma_f32(eng.node_ptr_loc, eng.node_col_loc, v32, x, eng.max_deg)
+    # against the same rounded values in fp64 arithmetic: exact up to summation order
+    yr = dev.spmv_bsr3_tma(eng.node_ptr_loc, eng.node_col_loc, v32.to(torch.float64), x,
+                           eng.max_deg)
+    scale = float(y64.abs().max())
+    assert float((y32 - yr).abs().max()) <= 1e-13 * scale
+    assert float((y32 - y64).abs().max()) <= 1e-6 * scale
+    # odd length / conversion tail
+    w = dev.to_dev(np.random.default_rng(6).standard_normal(1001))
+    assert torch.equal(dev.to_f32(w), w.to(torch.float32))
+    # a hierarchy with fp32 level values: 64 x 48 x 32 cells, level 1 = 14,025 nodes
+    # (above the bulk-async kernel's threshold; the copy's own threshold is lowered)
+    from sktopt.fea._multigrid import Multigrid
+    monkeypatch.delenv("SKTOPT_B200_MATFREE")
+    its = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SKTOPT_B200_MG_FP32_LEVELS", flag)
+        monkeypatch.setattr(Multigrid, "FP32_LEVEL_MIN_NODES", 10000)
+        mesh2, _, D2, e2 = _engine(sktopt, dims=(4.0, 3.0, 2.0), h=0.0625)
+        assert e2.precond == "mg" and e2.matrix_free
+        assert ("vals32" in e2.mg.levels[1]) == (flag == "1")
+        assert "vals32" not in e2.mg.levels[2]
+        rho2 = np.random.default_rng(4).uniform(0.01, 1.0, mesh2.nelements)
+        e2.set_modulus(dev.to_dev(rho2), 210e3, 210.0, 3.0)
+        e2.prepare()
+        f = np.zeros(e2.n_dof)
+        tip = np.nonzero(mesh2.p[0] == mesh2.p[0].max())[0]
+        f[3 * tip + 2] = -1.0
+        f[D2] = 0.0
+        e2.warm_start = False
+        u = e2.solve(dev.to_dev(f), 0, 1e-9, None).cpu().numpy().copy()
+        assert e2.pcg_log[-1][1]
+        its[flag] = (e2.pcg_log[-1][0], u)
+    assert abs(its["1"][0] - its["0"][0]) <= 2, (its["1"][0], its["0"][0])
+    assert np.max(np.abs(its["1"][1] - its["0"][1])) <= 1e-6 * np.abs(its["0"][1]).max()
