@@ -1233,7 +1233,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     } else {
       for (int s = 1; s < l.nu; ++s) {  // extra pre-smoothing sweeps
         if (level_halo(l, l.x, dist, st)) return 1;
-        if (k > 0 && m->fused_sweeps) {
+        if (m->fused_sweeps && (k > 0 || !l.gop)) {
           const int rc = level_sweep(l, b, om, st);
           if (rc == 0) continue;
           if (rc != -1) return rc;
@@ -1275,7 +1275,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
     }
     for (int s = 1; s < l.nu; ++s) {  // extra post-smoothing sweeps
       if (level_halo(l, l.x, dist, st)) return 1;
-      if (k > 0 && m->fused_sweeps) {
+      if (m->fused_sweeps && (k > 0 || !l.gop)) {
         const int rc = level_sweep(l, b, om, st);
         if (rc == 0) continue;
         if (rc != -1) return rc;
@@ -1285,7 +1285,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       SKTB_COUNT(1);
     }
     if (level_halo(l, l.x, dist, st)) return 1;
-    if (k > 0 && m->fused_sweeps) {  // last post-smoothing sweep
+    if (m->fused_sweeps && (k > 0 || !l.gop)) {  // last post-smoothing sweep
       const int rc = level_sweep(l, b, om, st);
       if (rc == 0) {
         phase_mark(l.sharded ? PH_VC_UP1 : PH_VC_COARSE, st);

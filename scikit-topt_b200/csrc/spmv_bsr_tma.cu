@@ -143,8 +143,12 @@ __device__ __forceinline__ void issue_tile(
   }
 }
 
+// CTAs per SM: the single-precision stages are half the size and the kernel is
+// bound by the latency of the x gathers, so a third CTA per SM pays there
+template <typename V> constexpr int tma_ctas_per_sm() { return sizeof(V) == 4 ? 3 : 2; }
+
 template <bool DOT, typename V = double>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, tma_ctas_per_sm<V>())
     spmv_bsr3_tma_kernel(int64_t n_nodes, int64_t n_blocks,
                          const int32_t *__restrict__ node_ptr,
                          const int32_t *__restrict__ node_col,
@@ -256,7 +260,7 @@ static int launch_tma(int64_t n_nodes, int64_t n_blocks, int max_deg,
   if (max_deg > kMaxDeg || n_nodes < 8 * kTile) return -1;
   constexpr int kSmem = TmaCfg<V>::kSmemBytes;
   const int64_t n_tiles = (n_nodes + kTile - 1) / kTile;
-  int64_t g = (int64_t)kNumSM * 2;
+  int64_t g = (int64_t)kNumSM * tma_ctas_per_sm<V>();
   if (g > n_tiles) g = n_tiles;
   const int grid = (int)g;
   const int which = (dotv ? 1 : 0) + (sizeof(V) == 4 ? 2 : 0);

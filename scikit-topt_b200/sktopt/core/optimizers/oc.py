@@ -54,18 +54,50 @@ def bisection_with_physical_volume(
     lmid = 0.5 * (l1 + l2)
     vol_error = 0.0
     steps = 0
+    # Two shortcuts that leave every evaluated quantity as it is:
+    # * The bracket starts at [1e-7, 1e7]: for the first ~20 midpoints EVERY scaling
+    #   rate (-dC/lmid)^eta sits on its lower clip, so the candidate -- and with it
+    #   the filtered / projected field and the volume error -- is bit-identical to
+    #   the one just evaluated.  max(-dC) tells that on the host (with a relative
+    #   margin of 1e-9 on both sides of the comparison); such a step is counted and
+    #   takes its bisection decision, but launches nothing.
+    # * candidate = clip(rho_e c_e t) with t = (lmid + eps)^-eta is piecewise LINEAR
+    #   in t and the filter is linear, so the filter's solution is too: filters that
+    #   accept a ``hint`` start their solve from the secant through the last two
+    #   solutions in t (exact while no element changes its clip status).  Their
+    #   solves also stop at the filter's bisection tolerance (1e-9): the filtered
+    #   candidate only decides the sign of a volume error against 1e-4 thresholds and
+    #   never enters the next iteration (the accepted design is filtered again, at the
+    #   filter's full tolerance, when the iteration starts).
+    neg_dc_max = -dev.reduce_stats(dC)[0]
+    sat_factor = float(scaling_rate_min) ** (1.0 / float(eta)) if eta > 0 else 0.0
+    hinted = bool(getattr(filter_obj, "accepts_hint", False))
+    if hinted:
+        filter_obj.reset_hint()          # the last bisection's secant is stale
+    last_eval_saturated = None
+    evaluated = 0
     while True:
         steps += 1
-        dev.oc_candidate(dC, rho_e, lmid, eps, eta, move_limit, rho_min, rho_max,
-                         scaling_rate_min, scaling_rate_max, design_elements,
-                         scaling_rate, rho_design_eles, rho_full_candidate)
-        filter_obj.forward(rho_full_candidate, out=rho_filtered_candidate)
-        projection.heaviside_projection_inplace(
-            rho_filtered_candidate, beta=beta, eta=beta_eta,
-            out=rho_projected_candidate)
-        vol_error = dev.reduce_wsum(
-            rho_projected_candidate, design_elements, elements_volume
-        ) / elements_volume_sum - vol_frac
+        saturated = bool(sat_factor > 0.0 and neg_dc_max >= 0.0 and
+                         neg_dc_max * (1.0 + 1e-9) <= sat_factor * (lmid + eps) * (1.0 - 1e-9))
+        if not (saturated and last_eval_saturated):
+            dev.oc_candidate(dC, rho_e, lmid, eps, eta, move_limit, rho_min, rho_max,
+                             scaling_rate_min, scaling_rate_max, design_elements,
+                             scaling_rate, rho_design_eles, rho_full_candidate)
+            if hinted:
+                filter_obj.forward(rho_full_candidate, out=rho_filtered_candidate,
+                                   hint=(lmid + eps) ** (-float(eta)),
+                                   rtol=filter_obj.bisection_rtol)
+            else:
+                filter_obj.forward(rho_full_candidate, out=rho_filtered_candidate)
+            projection.heaviside_projection_inplace(
+                rho_filtered_candidate, beta=beta, eta=beta_eta,
+                out=rho_projected_candidate)
+            vol_error = dev.reduce_wsum(
+                rho_projected_candidate, design_elements, elements_volume
+            ) / elements_volume_sum - vol_frac
+            last_eval_saturated = saturated
+            evaluated += 1
 
         if abs(vol_error) < vol_tol:
             break
@@ -82,10 +114,12 @@ def bisection_with_physical_volume(
     # candidate evaluations of this call (the return value keeps the reference's
     # two-tuple); read by OC_Optimizer.rho_update for its bisection_steps log
     bisection_with_physical_volume.last_steps = steps
+    bisection_with_physical_volume.last_evaluated = evaluated
     return lmid, vol_error
 
 
 bisection_with_physical_volume.last_steps = 0
+bisection_with_physical_volume.last_evaluated = 0
 
 
 @dataclass

@@ -323,6 +323,7 @@ class Multigrid:
         # (SKTOPT_B200_MG_FP32_LEVELS=0 disables)
         self.fp32_levels = (self.fp32
                             and os.environ.get("SKTOPT_B200_MG_FP32_LEVELS", "1") != "0")
+        self._vals32_l0 = None
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
@@ -558,6 +559,25 @@ class Multigrid:
         _lib.check(self.lib.sktb_mg_set_level_vals32(
             self.handle if handle is None else handle, l, C.c_void_p(v32.data_ptr())))
 
+    def _push_vals32_level0(self, handle=None, convert: bool = True):
+        """Assembled level 0 (one GPU): the V-cycle's sweeps and residual products
+        stream a single-precision copy of K, the PCG's own product stays fp64."""
+        eng = self.eng
+        if (not self.fp32_levels or eng.sharded
+                or (eng.node1 - eng.node0) < self.FP32_LEVEL_MIN_NODES):
+            return
+        v = eng.vals
+        if self._vals32_l0 is None or self._vals32_l0.numel() != v.numel():
+            self._vals32_l0 = torch.empty(v.numel(), dtype=torch.float32, device="cuda")
+            convert = True
+        if convert:
+            _lib.check(self.lib.sktb_f64_to_f32(int(v.numel()), dev._ptr(v),
+                                                C.c_void_p(self._vals32_l0.data_ptr()),
+                                                dev._stream()))
+        _lib.check(self.lib.sktb_mg_set_level_vals32(
+            self.handle if handle is None else handle, 0,
+            C.c_void_p(self._vals32_l0.data_ptr())))
+
     def _galerkin_algebraic(self, l: int, st):
         """vals of level ``l`` = P^T A_{l-1} P, matrix to matrix."""
         eng, lv, tr = self.eng, self.levels[l], self.transfers[l - 1]
@@ -595,6 +615,7 @@ class Multigrid:
                 self.handle, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()),
                 int(eng.max_deg), dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc),
                 dev._ptr(eng.vals), dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+            self._push_vals32_level0()
         for l in range(1, self.n_levels):
             lv = self.levels[l]
             sh = self.shard[l]
@@ -702,6 +723,7 @@ class MultigridWorkspace:
             h, 0, int(eng.node1 - eng.node0), int(eng.node_col_loc.numel()), int(eng.max_deg),
             dev._ptr(eng.node_ptr_loc), dev._ptr(eng.node_col_loc), dev._ptr(eng.vals),
             dev._ptr(eng.inv_diag), dev._ptr(eng.dir_mask)))
+        par._push_vals32_level0(handle=h, convert=False)
         for l in range(1, par.n_levels):
             lv = par.levels[l]
             _lib.check(lib.sktb_mg_set_level(

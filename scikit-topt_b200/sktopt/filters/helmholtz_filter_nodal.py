@@ -49,7 +49,16 @@ def infer_element_from_mesh(mesh):
 class _HelmholtzDevice:
     """Device state shared by forward / gradient of one filter object."""
 
-    RTOL = 1e-11
+    # The reference solves the filter systems with a sparse LU (exact to rounding).
+    # The PCG's tolerance is what separates this path from it: over BASELINE config
+    # 1's 50 OC iterations the optimiser amplifies the filter's solve error ~1e4-fold
+    # (measured against the oracle fixture: rtol 1e-11 -> compliance history 1.0e-6,
+    # densities 8e-5; rtol 1e-13 -> 7.6e-8 and 2.7e-6), so the solves whose result
+    # enters the iteration run at 1e-13.  Inside the OC bisection the filtered field
+    # only decides the sign of a volume error against thresholds of 1e-4, so those
+    # solves stop at RTOL_BISECTION (``forward(..., rtol=...)``).
+    RTOL = 1e-13
+    RTOL_BISECTION = 1e-9
     MAXITER = 5000
 
     def __init__(self, mesh, elements_volume, design_mask):
@@ -110,6 +119,8 @@ class _HelmholtzDevice:
         self.rhs = torch.empty(n, dtype=dev.F64, device="cuda")
         self.x_fwd = torch.zeros(n, dtype=dev.F64, device="cuda")
         self.x_adj = torch.zeros(n, dtype=dev.F64, device="cuda")
+        self._fwd_pool, self._fwd_hist = None, []     # secant start vectors (_start_vector)
+        self._secant = os.environ.get("SKTOPT_B200_FILTER_SECANT", "1") != "0"
         # several GPUs (one process each): the grid systems are solved by a
         # z-slab-sharded PCG (halo planes + dot all-reduces, csrc/pcg.cu), every
         # rank then holds the whole filtered field again (all-gather), so the
@@ -179,7 +190,8 @@ class _HelmholtzDevice:
             return self.gop_M.apply(v, out=out)
         return dev.spmv(self.row_ptr, self.col_idx, self.M, v, 1, out=out)
 
-    def _solve(self, enforced: bool, rhs, x):
+    def _solve(self, enforced: bool, rhs, x, rtol=None):
+        rtol = self.RTOL if rtol is None else float(rtol)
         minv = self.minv_fwd if enforced else self.minv
         if self.fd is not None and not enforced:
             self.solve_iters.append(0)                    # direct solve
@@ -187,14 +199,14 @@ class _HelmholtzDevice:
         if self.grid is not None:
             self.gop_A.set_scale(None, dmask=self.flags_fixed if enforced else self.flags_free)
             lo, hi = self.lo, self.hi
-            self.pcg.solve_grid(self.gop_A, minv[lo:hi], rhs[lo:hi], x[lo:hi], rtol=self.RTOL,
+            self.pcg.solve_grid(self.gop_A, minv[lo:hi], rhs[lo:hi], x[lo:hi], rtol=rtol,
                                 maxiter=self.MAXITER, use_x0=True, check_every=8)
             if self.comm is not None:
                 self.comm.allgatherv(x, np.diff(self.cuts), self.cuts[:-1])
         else:
             A = self.A_fwd if enforced else self.A
             self.pcg.solve(self.row_ptr, self.col_idx, A, minv, rhs, x, dpn_hint=1,
-                           rtol=self.RTOL, maxiter=self.MAXITER, use_x0=True,
+                           rtol=rtol, maxiter=self.MAXITER, use_x0=True,
                            check_every=8)
         self.solve_iters.append(self.pcg.last_iters)
         if not self.pcg.last_converged:
@@ -203,14 +215,51 @@ class _HelmholtzDevice:
                 f"(relres={self.pcg.last_relres:.3e})")
         return x
 
-    def forward(self, rho, out=None):
+    def _start_vector(self, hint):
+        """Buffer the next forward solve starts from (and solves in).  Without a
+        hint: the previous solution (plain warm start).  With ``hint`` = the value t
+        of a scalar parameter the right-hand side is (piecewise) linear in -- the OC
+        bisection, ``core/optimizers/oc.py`` --: the secant through the last two
+        hinted solutions, x1 + (t - t1)/(t1 - t2) (x1 - x2), written into the third
+        buffer of a ring so that nothing is copied.  A start vector only changes the
+        iteration count of the PCG (rtol 1e-11), not what it converges to."""
+        direct = self.fd is not None and not self.has_fixed
+        if hint is None or direct or not self._secant:
+            self._fwd_hist = []
+            return self.x_fwd
+        if self._fwd_pool is None:
+            self._fwd_pool = [self.x_fwd, torch.empty_like(self.x_fwd),
+                              torch.empty_like(self.x_fwd)]
+        hist = self._fwd_hist
+        if not hist:
+            hist.append((None, self.x_fwd))           # the un-hinted solve before this one
+        busy = [h[1].data_ptr() for h in hist[-2:]]
+        tgt = next(b for b in self._fwd_pool if b.data_ptr() not in busy)
+        t1, x1 = hist[-1]
+        t2, x2 = hist[-2] if len(hist) >= 2 else (None, None)
+        s = None
+        if t1 is not None and t2 is not None and t1 != t2:
+            s = (float(hint) - t1) / (t1 - t2)
+            if not np.isfinite(s) or abs(s) > 2.0:
+                s = None
+        if s is None:
+            tgt.copy_(x1)
+        else:
+            dev.affine(1.0 + s, x1, -s, x2, 0.0, tgt)
+        hist.append((float(hint), tgt))
+        del hist[:-2]
+        self.x_fwd = tgt
+        return tgt
+
+    def forward(self, rho, out=None, hint=None, rtol=None):
         self.dm.e2n(self.w, rho, self.design_u8, 1.0, self.wsum, out=self.node)
         self._mass_times(self.node, self.b)
+        x0 = self._start_vector(hint)
         if self.has_fixed:
             dev.enforce_rhs(self.b, self.c, self.fixed_u8, self.x_fixed, out=self.rhs)
-            x = self._solve(True, self.rhs, self.x_fwd)
+            x = self._solve(True, self.rhs, x0, rtol)
         else:
-            x = self._solve(False, self.b, self.x_fwd)
+            x = self._solve(False, self.b, x0, rtol)
         return self.dm.n2e_mean(x, clamp_max0=False, out=out)
 
     def gradient(self, v, out=None):
@@ -239,11 +288,23 @@ class HelmholtzFilterNodal(BaseFilter):
         st.set_radius(float(self.radius))
         return st
 
-    def forward(self, rho_element, out=None):
+    # ``forward`` takes the OC bisection's secant hint (see _HelmholtzDevice._start_vector)
+    accepts_hint = True
+
+    def reset_hint(self):
+        st = self.__dict__.get("_dev_state")
+        if st is not None:
+            st._fwd_hist = []
+
+    def forward(self, rho_element, out=None, hint=None, rtol=None):
         st = self._device()
         if isinstance(rho_element, torch.Tensor) and rho_element.is_cuda:
-            return st.forward(rho_element, out=out)
-        return st.forward(dev.to_dev(rho_element)).cpu().numpy()
+            return st.forward(rho_element, out=out, hint=hint, rtol=rtol)
+        return st.forward(dev.to_dev(rho_element), hint=hint, rtol=rtol).cpu().numpy()
+
+    @property
+    def bisection_rtol(self) -> float:
+        return _HelmholtzDevice.RTOL_BISECTION
 
     def gradient(self, v_ele, out=None):
         st = self._device()

@@ -62,7 +62,8 @@ for s in opt.timer.summary():
     print(f"{s.name:60s} {s.total/n*1e3:9.2f} ms/step  n={s.count//n}")
 print("precond", opt.fem.engine.precond, "pcg", opt.fem.engine.pcg_log[-2 * n:])
 try:
-    print("filter iters", opt.filter._dev_state.solve_iters[-8:])
+    si = opt.filter._dev_state.solve_iters
+    print("filter iters", si[-8:], "solves", len(si), "total iterations", sum(si))
 except Exception as e:
     print("filter iters: n/a", type(e).__name__)
 if world > 1:
