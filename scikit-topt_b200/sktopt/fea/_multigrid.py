@@ -324,6 +324,8 @@ class Multigrid:
         self.fp32_levels = (self.fp32
                             and os.environ.get("SKTOPT_B200_MG_FP32_LEVELS", "1") != "0")
         self._vals32_l0 = None
+        self._fp32_min_nodes = int(os.environ.get("SKTOPT_B200_MG_FP32_MIN_NODES",
+                                                  self.FP32_LEVEL_MIN_NODES))
         self.levels = [None]          # level 0 lives in the engine
         self.transfers = []
         mask_f = engine.dir_mask.cpu().numpy()
@@ -369,7 +371,7 @@ class Multigrid:
                 inv_diag=torch.empty(3 * (n1 - n0), dtype=dev.F64, device="cuda"),
                 mask=dev.to_dev(mask_c, dev.U8),
             )
-            if self.fp32_levels and (n1 - n0) >= self.FP32_LEVEL_MIN_NODES:
+            if self.fp32_levels and (n1 - n0) >= self._fp32_min_nodes:
                 lvl["vals32"] = torch.empty(9 * ci_loc.size, dtype=torch.float32, device="cuda")
             if not self.algebraic:
                 lvl.update(ke=torch.empty((n_ke, 576), dtype=dev.F64, device="cuda"),
@@ -564,7 +566,7 @@ class Multigrid:
         stream a single-precision copy of K, the PCG's own product stays fp64."""
         eng = self.eng
         if (not self.fp32_levels or eng.sharded
-                or (eng.node1 - eng.node0) < self.FP32_LEVEL_MIN_NODES):
+                or (eng.node1 - eng.node0) < self._fp32_min_nodes):
             return
         v = eng.vals
         if self._vals32_l0 is None or self._vals32_l0.numel() != v.numel():

@@ -42,6 +42,10 @@ def main():
     c = fem.objectives_multi_load(rho, 3.0, u)
     iters_sharded = eng.pcg_log[-1][0]
     n_sharded_levels = 0 if eng.mg is None else sum(s is not None for s in eng.mg.shard)
+    # sharded levels whose V-cycle products stream single-precision values
+    n_fp32_sharded = 0 if eng.mg is None else sum(
+        1 for l in range(1, eng.mg.n_levels)
+        if eng.mg.shard[l] is not None and "vals32" in eng.mg.levels[l])
     slab = eng.slab is not None
 
     # single-GPU engine on the same rank (replicated), same inputs
@@ -117,6 +121,7 @@ def main():
         print(f"DIST_P2P p2p={p2p} arena_bytes={arena[0]} exchanges={arena[1]} err={arena[2]}")
         assert arena[2] == 0
         print(f"DIST_RESULT world={world} slab={slab} sharded_mg_levels={n_sharded_levels} "
+              f"fp32_sharded_levels={n_fp32_sharded} "
               f"err_u={err_u:.3e} err_c={err_c:.3e} rows_equal={rows_equal} "
               f"iters={iters_sharded}/{iters_single} filter_sharded={filter_sharded} "
               f"err_filter={err_f:.3e} same_rho={same} loop_rel={rel:.3e} "

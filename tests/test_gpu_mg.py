@@ -290,7 +290,7 @@ def test_single_precision_level_values(gpu, monkeypatch):
     its = {}
     for flag in ("1", "0"):
         monkeypatch.setenv("SKTOPT_B200_MG_FP32_LEVELS", flag)
-        monkeypatch.setattr(Multigrid, "FP32_LEVEL_MIN_NODES", 10000)
+        monkeypatch.setenv("SKTOPT_B200_MG_FP32_MIN_NODES", "10000")
         mesh2, _, D2, e2 = _engine(sktopt, dims=(4.0, 3.0, 2.0), h=0.0625)
         assert e2.precond == "mg" and e2.matrix_free
         assert ("vals32" in e2.mg.levels[1]) == (flag == "1")
