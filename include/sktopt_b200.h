@@ -575,6 +575,8 @@ int sktb_affine(int64_t n, double a, const double *x, double b,
                 const double *y, double c, double *out, void *stream);
 int sktb_hadamard(int64_t n, double a, const double *x, const double *y,
                   double *out, void *stream);
+/* out = |x| (x != NULL), else out = value                                      */
+int sktb_fill_abs(int64_t n, const double *x, double value, double *out, void *stream);
 /* KKT residual (core/optimizers/oc.py:230-240, logmoc.py:227-236):
  * out_h[0] = max |g + coef*dv| over lo < rho < hi, out_h[1] = how many such.  */
 int sktb_kkt_residual_h(int64_t n, const double *rho, const double *g,

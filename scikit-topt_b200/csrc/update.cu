@@ -249,6 +249,21 @@ extern "C" int sktb_hadamard(int64_t n, double a, const double *x,
   SKTB_KERNEL_OK();
   return 0;
 }
+__global__ void __launch_bounds__(kBlock)
+    fill_abs_kernel(int64_t n, const double *__restrict__ x, double value,
+                    double *__restrict__ out) {
+  GRID_STRIDE(i, n) out[i] = x ? fabs(x[i]) : value;
+}
+// out = |x| (x != NULL) or out = value: the two elementwise steps of the loop that
+// would otherwise be framework kernels (recorder statistics of |dV|, zeroing the
+// full-length sensitivity before the design entries are scattered into it)
+extern "C" int sktb_fill_abs(int64_t n, const double *x, double value, double *out,
+                             void *stream) {
+  SKTB_REQUIRE(out, "null argument");
+  fill_abs_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(n, x, value, out);
+  SKTB_KERNEL_OK();
+  return 0;
+}
 extern "C" int sktb_enforce_rhs(int64_t n, const double *b, const double *t,
                                 const uint8_t *mask, const double *xD,
                                 double *out, void *stream) {

@@ -804,6 +804,20 @@ def affine(a, x, b, y, c, out):
     return out
 
 
+def fill(out, value: float = 0.0):
+    """out[:] = value (contiguous fp64 tensor)."""
+    _lib.check(_lib.load().sktb_fill_abs(out.numel(), None, float(value), _ptr(out), _stream()))
+    return out
+
+
+def absval(x, out=None):
+    """out = |x|."""
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().sktb_fill_abs(x.numel(), _ptr(x), 0.0, _ptr(out), _stream()))
+    return out
+
+
 def hadamard(a, x, y, out):
     """out = a*x*y."""
     _lib.check(_lib.load().sktb_hadamard(x.numel(), float(a), _ptr(x), _ptr(y), _ptr(out), _stream()))

@@ -138,6 +138,7 @@ SIGNATURES = {
     "sktb_axpby": [i64, f64, c_f64p, f64, c_f64p, c_stream],
     "sktb_affine": [i64, f64, c_f64p, f64, c_f64p, f64, c_f64p, c_stream],
     "sktb_hadamard": [i64, f64, c_f64p, c_f64p, c_f64p, c_stream],
+    "sktb_fill_abs": [i64, c_f64p, f64, c_f64p, c_stream],
     "sktb_kkt_residual_h": [i64, c_f64p, c_f64p, c_f64p, f64, f64, f64, C.c_void_p, c_stream],
     "sktb_reduce_maxdiff_h": [i64, c_f64p, c_f64p, c_i32p, C.c_void_p, c_stream],
     "sktb_enforce_rhs": [i64, c_f64p, c_f64p, c_u8p, c_f64p, c_f64p, c_stream],

@@ -522,7 +522,7 @@ class DensityMethod(DensityMethodBase):
                 projection.heaviside_projection_inplace(
                     st.rho_filtered, beta=beta, eta=cfg.beta_eta, out=st.rho_projected)
 
-            st.dC_drho_full.zero_()
+            dev.fill(st.dC_drho_full, 0.0)
             u_max = []
             # optimisers whose update needs filter solves that depend only on the
             # filtered field (LogMOC's volume chain) may start them now, on a side
@@ -542,7 +542,7 @@ class DensityMethod(DensityMethodBase):
                     if n_tasks == 1:
                         st.energy_mean.copy_(energy[:, 0])
                     else:
-                        st.energy_mean.zero_()
+                        dev.fill(st.energy_mean, 0.0)
                         for i in range(n_tasks):
                             dev.axpby(1.0 / n_tasks, energy[:, i].contiguous(), 1.0,
                                       st.energy_mean)

@@ -219,7 +219,7 @@ class LogMOC_Optimizer(common_density.DensityMethod):
         dev.affine(1.0, self._dC_raw_buffer, constraint_coeff, self._dV_chain_design,
                    0.0, self._dL_buffer)
         if cfg.filter_lagrangian:
-            self._dL_full.zero_()
+            dev.fill(self._dL_full, 0.0)
             dev.scatter(self._dL_buffer, design, self._dL_full)
             filtered = self.filter.forward(self._dL_full)
             dev.gather(filtered, design, out=self._dL_buffer)
@@ -252,7 +252,7 @@ class LogMOC_Optimizer(common_density.DensityMethod):
         elif mx <= 0.0:
             rec.feed_data("dV_chain", ArrayStats(-mx, -mean, -mn, sd))
         else:
-            rec.feed_data("dV_chain", torch.abs(self._dV_chain_design))
+            rec.feed_data("dV_chain", dev.absval(self._dV_chain_design))
         rec.feed_data("volume_chain_scale", volume_chain_scale)
         rec.feed_data("dL", self._dL_buffer)
         rec.feed_data("kkt_residual", self.kkt_residual)
