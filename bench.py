@@ -32,6 +32,26 @@ C2_MESH_SIZE = 0.0577          # toy_base(0.0577): 139x104x70 = 1,011,920 hex
 C5_MESH_SIZE = 0.0288          # toy_base(0.0288): 278x209x139 = 8,076,178 hex (BASELINE configs[4])
 
 
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries below us write there too
+    (NCCL prints its version banner on fd 1 when the box sets NCCL_DEBUG), so fd 1
+    is pointed at stderr for the run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 def workload_name(mesh_size: float) -> str:
     tag = ("C2" if abs(mesh_size - C2_MESH_SIZE) < 1e-12 else
            "C5" if abs(mesh_size - C5_MESH_SIZE) < 1e-12 else
@@ -195,7 +215,7 @@ def run_reference(args):
     }
     if not args.no_c1:
         line["same_config_c1"] = same_config_c1_cpu()
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------- GPU arm --
@@ -556,7 +576,7 @@ def run_b200(args):
                 c1["compliance_max_rel_diff"] = float(np.max(np.abs(gc - cc) / np.abs(cc)))
         if c1 is not None:
             line["same_config_c1"] = c1
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -625,7 +645,7 @@ def run_workload(args):
                      "peak_source": peak_src},
         "gpu_launches": int(launches), "dtype": "f64", "data": "synthetic",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -649,6 +669,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2: the headline (default); c3 / c4: BASELINE configs 3 / 4 at size")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload != "c2":
