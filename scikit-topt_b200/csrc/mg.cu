@@ -74,6 +74,9 @@ struct sktb_mg {
   bool fp32_level0 = false;  // single-precision products on a matrix-free level 0
   bool fused_tail = false;   // levels <= kTailMaxNodes nodes in one cooperative kernel
   bool fused_sweeps = true;  // Jacobi sweeps of levels >= 1 fused into the product kernel
+  // the restriction into a replicated level also writes that level's first Jacobi step
+  // (SKTB_MG_FUSE_RESTRICT_JACOBI=0 keeps the separate kernel)
+  bool fuse_restrict_jacobi = true;
 };
 
 extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
@@ -83,6 +86,8 @@ extern "C" int sktb_mg_create(sktb_mg **out, int n_levels, int device) {
   m->lv.resize(n_levels);
   const char *env = getenv("SKTB_MG_FUSED_SWEEPS");
   m->fused_sweeps = !(env && env[0] == '0');
+  const char *env2 = getenv("SKTB_MG_FUSE_RESTRICT_JACOBI");
+  m->fuse_restrict_jacobi = !(env2 && env2[0] == '0');
   *out = m;
   return 0;
 }
@@ -515,7 +520,9 @@ __global__ void __launch_bounds__(kBlock)
                               const double *__restrict__ Axf,
                               const uint8_t *__restrict__ mask_c,
                               double *__restrict__ bc, int64_t f_lo, int64_t f_hi,
-                              int64_t c_lo, int64_t c_hi, int64_t c_base) {
+                              int64_t c_lo, int64_t c_hi, int64_t c_base,
+                              const double *__restrict__ jd, double jom,
+                              double *__restrict__ jx) {
   // coarse nodes [c_lo, c_hi) are produced, written at bc[3 (I - c_base)];
   // bf / Axf hold the fine rows [f_lo, f_hi) (Axf may be null: bf is a residual)
   const int tot = cnx + cny + cnz;
@@ -553,9 +560,17 @@ __global__ void __launch_bounds__(kBlock)
       }
     }
     const int64_t o = 3 * I, q = 3 * (I - c_base);
-    bc[q] = (mask_c && mask_c[o]) ? 0.0 : a0;
-    bc[q + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
-    bc[q + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+    a0 = (mask_c && mask_c[o]) ? 0.0 : a0;
+    a1 = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+    a2 = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+    bc[q] = a0;
+    bc[q + 1] = a1;
+    bc[q + 2] = a2;
+    if (jx) {  // first damped-Jacobi step of the coarse level from a zero iterate
+      jx[q] = jom * jd[q] * a0;
+      jx[q + 1] = jom * jd[q + 1] * a1;
+      jx[q + 2] = jom * jd[q + 2] * a2;
+    }
   }
 }
 
@@ -576,7 +591,8 @@ __global__ void __launch_bounds__(kBlock)
                        const double *__restrict__ Axf,
                        const uint8_t *__restrict__ mask_c,
                        double *__restrict__ bc, int64_t f_lo, int64_t f_hi,
-                       int64_t c_lo, int64_t c_hi, int64_t c_base) {
+                       int64_t c_lo, int64_t c_hi, int64_t c_base,
+                       const double *__restrict__ jd, double jom, double *__restrict__ jx) {
   const int tot = cnx + cny + cnz;
   const int lane = threadIdx.x & 31;
   const int sy = lane % 3, sx = (lane / 3) % 3, sz = lane / 9;  // lanes >= 27 idle
@@ -608,9 +624,17 @@ __global__ void __launch_bounds__(kBlock)
     a2 = warp_sum(a2);
     if (lane == 0) {
       const int64_t o = 3 * I, q = 3 * (I - c_base);
-      bc[q] = (mask_c && mask_c[o]) ? 0.0 : a0;
-      bc[q + 1] = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
-      bc[q + 2] = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+      a0 = (mask_c && mask_c[o]) ? 0.0 : a0;
+      a1 = (mask_c && mask_c[o + 1]) ? 0.0 : a1;
+      a2 = (mask_c && mask_c[o + 2]) ? 0.0 : a2;
+      bc[q] = a0;
+      bc[q + 1] = a1;
+      bc[q + 2] = a2;
+      if (jx) {  // first damped-Jacobi step of the coarse level from a zero iterate
+        jx[q] = jom * jd[q] * a0;
+        jx[q + 1] = jom * jd[q + 1] * a1;
+        jx[q + 2] = jom * jd[q + 2] * a2;
+      }
     }
   }
 }
@@ -1130,8 +1154,11 @@ static int level_halo(const MgLevel &l, double *vfull, sktb_pcg *dist, cudaStrea
 }
 
 // b_c = mask_c P^T (b_f - A x_f) for the coarse level c of fine level l
+// x0_done (may be null): set when the kernel also wrote the coarse level's first
+// Jacobi step x_c = om_c D_c^-1 b_c (one launch less per level and cycle); only for a
+// replicated coarse level whose right-hand side is final after this kernel
 static int level_restrict(MgLevel &l, MgLevel &c, const double *b, sktb_pcg *dist,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool *x0_done = nullptr, double om_c = 0.0) {
   const bool part = l.node0 != 0 || l.n_global != l.n_nodes;  // fine rows are a slab
   const double *bf = b, *Axf = l.tmp;
   int64_t f_lo = part ? l.node0 : 0, f_hi = part ? l.node0 + l.n_nodes : l.n_nodes;
@@ -1155,15 +1182,21 @@ static int level_restrict(MgLevel &l, MgLevel &c, const double *b, sktb_pcg *dis
     c_base = c.node0;
   }
   const int64_t nc = c_hi - c_lo;
+  const bool reduce_after = part && !c.sharded && dist;
+  const bool fuse = x0_done && !c.sharded && !reduce_after && !c.cheb && c.inv_diag && c.x &&
+                    c.dense_n != 3 * c.n_nodes && om_c > 0.0;
+  const double *jd = fuse ? c.inv_diag : nullptr;
+  double *jx = fuse ? c.x : nullptr;
   if (nc > 20000)
     mg_restrict_thread_kernel<<<grid_for(nc), kBlock, 0, st>>>(
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f, l.axT_w, bf, Axf,
-        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base);
+        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base, jd, om_c, jx);
   else
     mg_restrict_kernel<<<grid_for(nc * 32, kBlock, 16), kBlock, 0, st>>>(
         l.cnp[0], l.cnp[1], l.cnp[2], l.fnp[0], l.fnp[1], l.fnp[2], l.axT_f, l.axT_w, bf, Axf,
-        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base);
+        c.mask, c.b, f_lo, f_hi, c_lo, c_hi, c_base, jd, om_c, jx);
   SKTB_COUNT(1);
+  if (x0_done) *x0_done = fuse;
   // sharded fine level, replicated coarse level: every rank summed its own fine
   // rows into the whole coarse vector
   if (part && !c.sharded && dist) {
@@ -1182,6 +1215,13 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
   const int L = (int)m->lv.size();
   const int k_tail = tail_start(m);
   MgLevel &l0 = m->lv[0];
+  bool x0_done = false;   // the restriction into level k already wrote its first Jacobi step
+  // damping of level k + 1 when the restriction into it may do so (0: it may not)
+  auto om_next = [&](int k) {
+    if (k + 1 >= L || k + 1 == k_tail || !m->fuse_restrict_jacobi) return 0.0;
+    const MgLevel &c = m->lv[k + 1];
+    return c.omega > 0.0 ? c.omega : m->omega;
+  };
   // downward sweep
   for (int k = 0; k < L; ++k) {
     if (k == k_tail) {
@@ -1212,11 +1252,14 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
         SKTB_COUNT(1);
       }
       if (level_spmv(l, l.x, l.tmp, st)) return 1;
-      if (level_restrict(l, m->lv[k + 1], b, dist, st)) return 1;
+      if (level_restrict(l, m->lv[k + 1], b, dist, st, &x0_done, om_next(k))) return 1;
       continue;
     }
-    mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, XOWN);
-    SKTB_COUNT(1);
+    if (!x0_done) {
+      mg_jacobi0_kernel<<<g, kBlock, 0, st>>>(n, om, l.inv_diag, b, XOWN);
+      SKTB_COUNT(1);
+    }
+    x0_done = false;
     if (k == L - 1 && k > 0 && l.n_nodes <= 4096) {
       // (jacobi0 above is redone inside; harmless and keeps the code uniform)
       mg_coarse_solve_kernel<<<1, 1024, 0, st>>>((int)l.n_nodes, l.node_ptr,
@@ -1244,7 +1287,7 @@ int mg_vcycle(sktb_mg *m, const double *r, double *z, cudaStream_t st,
       }
       if (level_halo(l, l.x, dist, st)) return 1;
       if (level_spmv(l, l.x, l.tmp, st, k == 0 && m->fp32_level0)) return 1;
-      if (level_restrict(l, m->lv[k + 1], b, dist, st)) return 1;
+      if (level_restrict(l, m->lv[k + 1], b, dist, st, &x0_done, om_next(k))) return 1;
       phase_mark(k == 0 ? PH_VC_L0 : (l.sharded ? PH_VC_L1 : PH_VC_COARSE), st);
     }
   }
