@@ -32,6 +32,20 @@ from sktopt.tools.logconf import mylogger
 logger = mylogger(__name__)
 
 
+def rates_all_on_lower_clip(neg_dc_max: float, lmid: float, eps: float, eta: float,
+                            scaling_rate_min: float) -> bool:
+    """True when (-dC_e / (lmid + eps))^eta <= scaling_rate_min for EVERY element, i.e.
+    the OC candidate does not depend on ``lmid`` any more (all scaling rates sit on
+    their lower clip; elements with -dC_e < 0 give NaN for any lmid).  ``neg_dc_max`` =
+    max_e(-dC_e).  A relative margin of 1e-9 on both sides keeps the answer False
+    anywhere near the boundary, where ``pow`` rounding could differ by an ulp, so a
+    True answer means the candidate is bit-identical to any other such midpoint's."""
+    if not (eta > 0.0 and scaling_rate_min > 0.0 and neg_dc_max >= 0.0):
+        return False
+    bound = float(scaling_rate_min) ** (1.0 / float(eta)) * (lmid + eps)
+    return bool(neg_dc_max * (1.0 + 1e-9) <= bound * (1.0 - 1e-9))
+
+
 def bisection_with_physical_volume(
     dC, rho_e, rho_full, design_elements, filter_obj, rho_min, rho_max,
     move_limit, eta, eps, vol_frac, beta, beta_eta, scaling_rate,
@@ -70,7 +84,6 @@ def bisection_with_physical_volume(
     #   never enters the next iteration (the accepted design is filtered again, at the
     #   filter's full tolerance, when the iteration starts).
     neg_dc_max = -dev.reduce_stats(dC)[0]
-    sat_factor = float(scaling_rate_min) ** (1.0 / float(eta)) if eta > 0 else 0.0
     hinted = bool(getattr(filter_obj, "accepts_hint", False))
     if hinted:
         filter_obj.reset_hint()          # the last bisection's secant is stale
@@ -78,8 +91,8 @@ def bisection_with_physical_volume(
     evaluated = 0
     while True:
         steps += 1
-        saturated = bool(sat_factor > 0.0 and neg_dc_max >= 0.0 and
-                         neg_dc_max * (1.0 + 1e-9) <= sat_factor * (lmid + eps) * (1.0 - 1e-9))
+        saturated = rates_all_on_lower_clip(neg_dc_max, lmid, eps, float(eta),
+                                            float(scaling_rate_min))
         if not (saturated and last_eval_saturated):
             dev.oc_candidate(dC, rho_e, lmid, eps, eta, move_limit, rho_min, rho_max,
                              scaling_rate_min, scaling_rate_max, design_elements,

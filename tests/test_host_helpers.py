@@ -94,3 +94,51 @@ def test_task_statistics_and_converters(capsys):
     with pytest.raises(Exception):
         misc.str2bool("maybe")
     assert misc.float_or_none("None") is None and misc.float_or_none("1.5") == 1.5
+
+
+def test_oc_bisection_saturation_predicate_is_exact():
+    """``rates_all_on_lower_clip`` (core/optimizers/oc.py) lets the device bisection
+    skip midpoints whose candidate cannot differ from the one just evaluated.  Against
+    the reference's candidate formula (oc.py:50-68, restated in NumPy): whenever the
+    predicate is True for two midpoints, the two candidates are bit-identical; and over
+    the reference's bracket [1e-7, 1e7] it fires for the first 10-20 midpoints."""
+    pytest.importorskip("torch")
+    from sktopt.core.optimizers.oc import rates_all_on_lower_clip
+    rng = np.random.default_rng(0)
+    n = 4000
+    eps, move, rmin, rmax, smin, smax = 1e-12, 0.2, 1e-3, 1.0, 0.7, 1.3
+
+    def candidate(dC, rho, lmid, eta):
+        with np.errstate(invalid="ignore"):
+            sr = np.clip(np.power(-dC / (lmid + eps), eta), smin, smax)
+        lo = np.maximum(rho - move, rmin)
+        hi = np.minimum(rho + move, rmax)
+        return np.clip(rho * sr, lo, hi)
+
+    for eta in (0.5, 0.3, 1.0):
+        dC = -rng.lognormal(0.0, 2.0, n)            # sensitivities are negative
+        dC[::97] = 0.0
+        rho = rng.uniform(rmin, rmax, n)
+        neg_max = float(np.max(-dC))
+        l1, l2, fired, ref = 1e-7, 1e7, 0, None
+        for _ in range(60):
+            lmid = 0.5 * (l1 + l2)
+            if rates_all_on_lower_clip(neg_max, lmid, eps, eta, smin):
+                fired += 1
+                c = candidate(dC, rho, lmid, eta)
+                if ref is None:
+                    ref = c
+                assert np.array_equal(c, ref)       # bit-identical, not just close
+                assert np.array_equal(c, np.clip(rho * smin, np.maximum(rho - move, rmin),
+                                                 np.minimum(rho + move, rmax)))
+            l2 = lmid                               # walk down, as while the volume is short
+        assert fired >= 8, (eta, fired)      # 5e6 -> max(-dC) / smin^(1/eta) in halvings
+        # just inside / outside the boundary the predicate stays on the safe side
+        lam_star = neg_max / smin ** (1.0 / eta) - eps
+        assert not rates_all_on_lower_clip(neg_max, lam_star, eps, eta, smin)
+        assert not rates_all_on_lower_clip(neg_max, lam_star * (1 - 1e-6), eps, eta, smin)
+        assert rates_all_on_lower_clip(neg_max, lam_star * (1 + 1e-6), eps, eta, smin)
+    # degenerate inputs never skip
+    assert not rates_all_on_lower_clip(-1.0, 1.0, eps, 0.5, smin)
+    assert not rates_all_on_lower_clip(float("nan"), 1.0, eps, 0.5, smin)
+    assert not rates_all_on_lower_clip(1.0, 1.0, eps, 0.0, smin)
