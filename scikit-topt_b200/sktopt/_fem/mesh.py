@@ -68,7 +68,14 @@ def _unique_columns(sorted_cols: np.ndarray):
     Lexicographic order with row 0 as the primary key, as ``np.unique(axis=1)``.
     """
     k, n = sorted_cols.shape
-    order = np.lexsort(sorted_cols[::-1])
+    if k == 4 and sorted_cols.dtype == np.int64 and n and 0 <= sorted_cols.min() \
+            and sorted_cols.max() < 2 ** 31:
+        # two packed keys sort like the four rows (non-negative ids below 2^31)
+        hi = (sorted_cols[0] << 32) | sorted_cols[1]
+        lo = (sorted_cols[2] << 32) | sorted_cols[3]
+        order = np.lexsort((lo, hi))
+    else:
+        order = np.lexsort(sorted_cols[::-1])
     s = sorted_cols[:, order]
     new = np.ones(n, dtype=bool)
     if n > 1:
@@ -172,7 +179,10 @@ class Mesh:
         return np.nonzero(self.f2t[1] == -1)[0].astype(np.int32)
 
     def facets_satisfying(self, test, boundaries_only: bool = False):
-        midp = self.p[:, self.facets].mean(axis=1)
+        # the midpoints are shared by every query on this mesh (clamp, load, ...)
+        if getattr(self, "_facet_midp", None) is None:
+            self._facet_midp = self.p[:, self.facets].mean(axis=1)
+        midp = self._facet_midp
         facets = np.nonzero(test(midp))[0]
         if boundaries_only:
             facets = np.intersect1d(facets, self.boundary_facets())
@@ -187,6 +197,7 @@ class Mesh:
         m._facets, m._f2t, m._t2f, m._f2lf = (
             self._facets, self._f2t, self._t2f, self._f2lf
         )
+        m._facet_midp = getattr(self, "_facet_midp", None)
         return m
 
     def with_boundaries(self, boundaries: dict, boundaries_only: bool = True):

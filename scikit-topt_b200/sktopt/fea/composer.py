@@ -49,22 +49,31 @@ _HEX_TETS = ((0, 1, 3, 4), (1, 2, 3, 6), (1, 5, 6, 4), (3, 6, 7, 4),
              (1, 3, 6, 4), (1, 6, 5, 4))
 
 
-def _abs_tet_volume(p, t, quad):
+def _abs_tet_volume(P, quad):
+    """|det(v1, v2, v3)| / 6 of the tetrahedron on the local vertices ``quad``;
+    ``P[k]`` = coordinates (3, n_elem) of local vertex k.  The cross product is
+    written out with NumPy's own operation order (product, product, difference:
+    no fused multiply-add), so the bits equal ``np.cross``'s."""
     i0, i1, i2, i3 = quad
-    v1 = p[:, t[i1]] - p[:, t[i0]]
-    v2 = p[:, t[i2]] - p[:, t[i0]]
-    v3 = p[:, t[i3]] - p[:, t[i0]]
-    c = np.cross(v1, v2, axis=0)
-    return np.abs(c[0] * v3[0] + c[1] * v3[1] + c[2] * v3[2]) / 6.0
+    v1 = P[i1] - P[i0]
+    v2 = P[i2] - P[i0]
+    v3 = P[i3] - P[i0]
+    c0 = v1[1] * v2[2] - v1[2] * v2[1]
+    c1 = v1[2] * v2[0] - v1[0] * v2[2]
+    c2 = v1[0] * v2[1] - v1[1] * v2[0]
+    return np.abs(c0 * v3[0] + c1 * v3[1] + c2 * v3[2]) / 6.0
 
 
 def _get_elements_volume_hex(t_conn, p_coords) -> np.ndarray:
     """Literal restatement of the reference's six-tetrahedra sum on the local
     index quadruples of ``fea/composer.py:191-248`` (under
-    skfem's local vertex order the fifth term is degenerate; kept as is)."""
+    skfem's local vertex order the fifth term is degenerate; kept as is).  The
+    coordinates of the seven local vertices the quadruples use are gathered once."""
+    used = sorted({k for quad in _HEX_TETS for k in quad})
+    P = {k: p_coords[:, t_conn[k]] for k in used}
     vol = np.zeros(t_conn.shape[1])
     for quad in _HEX_TETS:
-        vol += _abs_tet_volume(p_coords, t_conn, quad)
+        vol += _abs_tet_volume(P, quad)
     return vol
 
 
