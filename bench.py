@@ -323,6 +323,7 @@ def run_b200(args):
     ev1 = torch.cuda.Event(enable_timing=True)
     rho_h.copy_(st.rho)
     comp_last = None
+    n_solves_e2e = len(eng.pcg_log)
     barrier()
     w0 = time.perf_counter()
     ev0.record()
@@ -340,6 +341,7 @@ def run_b200(args):
     barrier()
     t_e2e_wall = time.perf_counter() - w0
     t_e2e = max(ev0.elapsed_time(ev1) * 1e-3, t_e2e_wall)
+    pcg_iters_e2e = [l[0] for l in eng.pcg_log[n_solves_e2e:]]
     clocks = sampler.stop() if rank == 0 else None
 
     t_step, t_e2e, t_wall = max_over_ranks([t_step, t_e2e, t_wall])
@@ -408,6 +410,10 @@ def run_b200(args):
                       % ",".join(str(v) for v in eng.mg.sweeps)
                       if eng.precond == "mg" else "Jacobi")),
         "pcg_iters_per_step": pcg_iters,
+        # the e2e region is the NEXT K optimiser iterations of the same run (it cannot
+        # repeat the timed ones: the state has moved on); later iterations need fewer
+        # PCG iterations, which is why e2e can exceed `value` despite its copies
+        "pcg_iters_per_step_e2e": pcg_iters_e2e,
         "l2": ("inputs larger than L2: one step streams the level-1 operator (0.27 GB) ~4x per PCG "
                "iteration plus ~20 work vectors of 25 MB against the 126 MB L2; nothing is "
                "flushed explicitly"),
