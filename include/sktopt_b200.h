@@ -575,6 +575,24 @@ int sktb_affine(int64_t n, double a, const double *x, double b,
                 const double *y, double c, double *out, void *stream);
 int sktb_hadamard(int64_t n, double a, const double *x, const double *y,
                   double *out, void *stream);
+/* ---- host-side helpers of the task construction (HOST pointers, multi-threaded
+ * C++, no device work).  Each reproduces its NumPy counterpart
+ * in sktopt/ bit for bit.
+ * sktb_host_hex_volumes: get_elements_volume for hexahedra (fea/composer.py:191-248):
+ *   sum of six |tetrahedron volumes| on the reference's local quadruples;
+ *   t = connectivity [8][n_elem], p = coordinates [3][n_nodes].
+ * sktb_host_lattice_facets: facets / t2f / f2t / f2lf (what skfem's Mesh provides and
+ *   mesh/task_common.py:105-270 reads) of a hexahedral mesh whose elements are cells
+ *   of a lattice numbered like init_tensor (npy = nodes along y, P = npy*npx), in two
+ *   passes: facets == NULL validates, fills key [6][n_elem] and *n_facets (-1: not
+ *   such a mesh); the second call fills facets [4][n], t2f [6][n_elem], f2t [2][n],
+ *   f2lf [2][n] (lexicographic facet order, slot 0 = first occurrence).              */
+int sktb_host_hex_volumes(int64_t n_elem, int64_t n_nodes, const int32_t *t, const double *p,
+                          double *vol);
+int sktb_host_lattice_facets(int64_t n_elem, int64_t n_nodes, const int32_t *t,
+                             const int32_t *lf, int64_t npy, int64_t P, int64_t *key,
+                             int64_t *n_facets, int32_t *facets, int32_t *t2f, int32_t *f2t,
+                             int8_t *f2lf);
 /* out = |x| (x != NULL), else out = value                                      */
 int sktb_fill_abs(int64_t n, const double *x, double value, double *out, void *stream);
 /* KKT residual (core/optimizers/oc.py:230-240, logmoc.py:227-236):

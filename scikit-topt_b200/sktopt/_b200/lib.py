@@ -139,6 +139,9 @@ SIGNATURES = {
     "sktb_affine": [i64, f64, c_f64p, f64, c_f64p, f64, c_f64p, c_stream],
     "sktb_hadamard": [i64, f64, c_f64p, c_f64p, c_f64p, c_stream],
     "sktb_fill_abs": [i64, c_f64p, f64, c_f64p, c_stream],
+    "sktb_host_hex_volumes": [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p],
+    "sktb_host_lattice_facets": [i64, i64, C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "sktb_kkt_residual_h": [i64, c_f64p, c_f64p, c_f64p, f64, f64, f64, C.c_void_p, c_stream],
     "sktb_reduce_maxdiff_h": [i64, c_f64p, c_f64p, c_i32p, C.c_void_p, c_stream],
     "sktb_enforce_rhs": [i64, c_f64p, c_f64p, c_u8p, c_f64p, c_f64p, c_stream],

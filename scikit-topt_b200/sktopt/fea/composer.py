@@ -13,6 +13,7 @@ from typing import Callable
 import numpy as np
 import scipy.sparse as sp
 
+from sktopt._b200 import lib as _lib_mod
 from sktopt._fem import MeshHex, MeshTet
 
 
@@ -64,11 +65,34 @@ def _abs_tet_volume(P, quad):
     return np.abs(c0 * v3[0] + c1 * v3[1] + c2 * v3[2]) / 6.0
 
 
+def _hex_volumes_native(t_conn, p_coords):
+    """The same sum in multi-threaded C++ (``sktb_host_hex_volumes``, csrc/host_setup.cu:
+    host pointers, same operation order, no fused multiply-add: bit-identical); None
+    when the library is not built."""
+    import ctypes as C
+    try:
+        lib = _lib_mod.load()
+    except Exception:
+        return None
+    t = np.ascontiguousarray(t_conn, dtype=np.int32)
+    p = np.ascontiguousarray(p_coords, dtype=np.float64)
+    if t.ndim != 2 or t.shape[0] != 8 or p.shape[0] != 3:
+        return None
+    vol = np.empty(t.shape[1])
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    if lib.sktb_host_hex_volumes(t.shape[1], p.shape[1], ptr(t), ptr(p), ptr(vol)) != 0:
+        return None
+    return vol
+
+
 def _get_elements_volume_hex(t_conn, p_coords) -> np.ndarray:
     """Literal restatement of the reference's six-tetrahedra sum on the local
     index quadruples of ``fea/composer.py:191-248`` (under
     skfem's local vertex order the fifth term is degenerate; kept as is).  The
     coordinates of the seven local vertices the quadruples use are gathered once."""
+    vol = _hex_volumes_native(t_conn, p_coords)
+    if vol is not None:
+        return vol
     used = sorted({k for quad in _HEX_TETS for k in quad})
     P = {k: p_coords[:, t_conn[k]] for k in used}
     vol = np.zeros(t_conn.shape[1])

@@ -142,3 +142,91 @@ def test_oc_bisection_saturation_predicate_is_exact():
     assert not rates_all_on_lower_clip(-1.0, 1.0, eps, 0.5, smin)
     assert not rates_all_on_lower_clip(float("nan"), 1.0, eps, 0.5, smin)
     assert not rates_all_on_lower_clip(1.0, 1.0, eps, 0.0, smin)
+
+
+def test_lattice_facet_table_equals_the_sort_based_one():
+    """``MeshHex._build_facets_lattice`` (O(n) closed form for lattice-numbered grids)
+    must reproduce the generic lexicographic construction exactly -- facets, t2f, f2t,
+    f2lf, dtypes included -- for any geometry and any valid local vertex order, and
+    must decline everything else (permuted numbering, one-cell-thick grids)."""
+    from sktopt._fem.mesh import Mesh, MeshHex
+    rng = np.random.default_rng(0)
+    keys = ("_facets", "_t2f", "_f2t", "_f2lf")
+
+    def generic(mesh):
+        g = MeshHex(mesh.p, mesh.t)
+        Mesh._build_facets(g)
+        return g
+
+    mirror = np.array([1, 0, 4, 5, 2, 3, 7, 6])       # reflect the reference cube along Z
+    for dims in ((4, 5, 3), (7, 4, 9), (3, 3, 3), (12, 9, 8), (5, 4, 2)):
+        m = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in dims])
+        p = m.p + rng.uniform(-0.01, 0.01, m.p.shape)
+        t2 = m.t.copy()
+        flip = rng.uniform(size=t2.shape[1]) < 0.5
+        t2[:, flip] = t2[mirror][:, flip]
+        for t in (m.t, t2):
+            a = MeshHex(p, t)
+            assert a._build_facets_lattice(), dims
+            g = generic(a)
+            for k in keys:
+                assert np.array_equal(getattr(a, k), getattr(g, k)), (dims, k)
+                assert getattr(a, k).dtype == getattr(g, k).dtype, (dims, k)
+            # the public properties go through the fast path
+            b = MeshHex(p, t)
+            assert np.array_equal(b.facets, g._facets) and np.array_equal(b.f2t, g._f2t)
+            assert np.array_equal(b.boundary_facets(), np.nonzero(g._f2t[1] == -1)[0])
+    m = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in (5, 4, 6)])
+    perm = rng.permutation(m.p.shape[1])
+    scrambled = MeshHex(m.p[:, np.argsort(perm)], perm[m.t].astype(np.int32))
+    assert not scrambled._build_facets_lattice()
+    g = generic(scrambled)
+    assert np.array_equal(scrambled.facets, g._facets)       # falls back to the generic path
+    for dims in ((2, 5, 4), (5, 2, 4)):
+        thin = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in dims])
+        assert not thin._build_facets_lattice()
+        assert np.array_equal(thin.facets, generic(thin)._facets)
+
+
+def test_native_host_helpers_reproduce_numpy_bit_for_bit():
+    """csrc/host_setup.cu (multi-threaded C++ on HOST pointers, no device work): the
+    hexahedral element volumes and the lattice facet table must equal the NumPy
+    constructions bit for bit, on jittered geometry, mirrored local vertex orders and a
+    mesh large enough to run on several threads; meshes without the lattice structure
+    are declined."""
+    from sktopt._b200 import lib as _lib
+    try:
+        _lib.load()
+    except RuntimeError:
+        pytest.skip("library not built")
+    from sktopt._fem.mesh import Mesh, MeshHex
+    from sktopt.fea import composer
+    rng = np.random.default_rng(1)
+    mirror = np.array([1, 0, 4, 5, 2, 3, 7, 6])
+    for dims in ((4, 5, 3), (7, 4, 9), (3, 3, 3), (5, 4, 2), (70, 60, 45)):
+        m = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in dims])
+        p = m.p + rng.uniform(-0.002, 0.002, m.p.shape)
+        t2 = m.t.copy()
+        flip = rng.uniform(size=t2.shape[1]) < 0.5
+        t2[:, flip] = t2[mirror][:, flip]
+        for t in (m.t, t2):
+            a = MeshHex(p, t)
+            assert a._build_facets_native(), dims
+            g = MeshHex(p, t)
+            Mesh._build_facets(g)
+            for k in ("_facets", "_t2f", "_f2t", "_f2lf"):
+                assert np.array_equal(getattr(a, k), getattr(g, k)), (dims, k)
+                assert getattr(a, k).dtype == getattr(g, k).dtype, (dims, k)
+            v_nat = composer._hex_volumes_native(t, p)
+            used = sorted({k for quad in composer._HEX_TETS for k in quad})
+            P = {k: p[:, t[k]] for k in used}
+            v_np = np.zeros(t.shape[1])
+            for quad in composer._HEX_TETS:
+                v_np += composer._abs_tet_volume(P, quad)
+            assert np.array_equal(v_nat, v_np), dims
+            assert np.array_equal(composer.get_elements_volume(a), v_np)
+    perm = rng.permutation(m.p.shape[1])
+    scrambled = MeshHex(m.p[:, np.argsort(perm)], perm[m.t].astype(np.int32))
+    assert not scrambled._build_facets_native()
+    thin = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in (2, 5, 4)])
+    assert not thin._build_facets_native()
