@@ -89,6 +89,18 @@ def _unique_columns(sorted_cols: np.ndarray):
     return s[:, first_sorted], first_index, inverse
 
 
+def _mean_of_vertices(p: np.ndarray, conn: np.ndarray) -> np.ndarray:
+    """``p[:, conn].mean(axis=1)`` without the (3, k, n) temporary: the reduction over
+    the k vertices of a row adds them in order and divides by k, which is what NumPy's
+    mean does along a non-contiguous axis of that length (bit-identical; checked in
+    tests/test_host_helpers.py)."""
+    acc = p[:, conn[0]]                       # fancy indexing: a fresh array
+    for k in range(1, conn.shape[0]):
+        acc += p[:, conn[k]]
+    acc /= float(conn.shape[0])
+    return acc
+
+
 class Mesh:
     """Base class; see module docstring."""
 
@@ -181,7 +193,7 @@ class Mesh:
     def facets_satisfying(self, test, boundaries_only: bool = False):
         # the midpoints are shared by every query on this mesh (clamp, load, ...)
         if getattr(self, "_facet_midp", None) is None:
-            self._facet_midp = self.p[:, self.facets].mean(axis=1)
+            self._facet_midp = _mean_of_vertices(self.p, self.facets)
         midp = self._facet_midp
         facets = np.nonzero(test(midp))[0]
         if boundaries_only:
@@ -189,7 +201,7 @@ class Mesh:
         return facets.astype(np.int32)
 
     def elements_satisfying(self, test):
-        midp = self.p[:, self.t].mean(axis=1)
+        midp = _mean_of_vertices(self.p, self.t)
         return np.nonzero(test(midp))[0].astype(np.int32)
 
     def _clone(self, boundaries, subdomains):

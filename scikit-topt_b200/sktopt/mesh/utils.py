@@ -59,10 +59,11 @@ def fix_elements_orientation(mesh):
 def get_elements_by_nodes(mesh, target_nodes) -> np.ndarray:
     """Sorted unique int32 ids of elements touching any of the given nodes
     (``mesh/utils.py:180-228``)."""
+    # (duplicates and order are irrelevant for the membership mask: no np.unique)
     if isinstance(target_nodes, np.ndarray):
-        nodes = np.unique(target_nodes)
+        nodes = target_nodes.ravel()
     else:
-        nodes = np.unique(np.concatenate([np.asarray(a).ravel() for a in target_nodes]))
+        nodes = np.concatenate([np.asarray(a).ravel() for a in target_nodes])
     nodes = nodes.astype(np.int64)
     hit = np.zeros(mesh.nvertices, dtype=bool)
     hit[nodes[(nodes >= 0) & (nodes < mesh.nvertices)]] = True

@@ -230,3 +230,12 @@ def test_native_host_helpers_reproduce_numpy_bit_for_bit():
     assert not scrambled._build_facets_native()
     thin = MeshHex.init_tensor(*[np.linspace(0, 1, d) for d in (2, 5, 4)])
     assert not thin._build_facets_native()
+
+
+def test_mean_of_vertices_equals_numpy_mean_bitwise():
+    from sktopt._fem.mesh import _mean_of_vertices
+    rng = np.random.default_rng(2)
+    p = rng.standard_normal((3, 5000)) * np.array([[1.0], [1e3], [1e-3]])
+    for k in (3, 4, 8):
+        conn = rng.integers(0, p.shape[1], (k, 20000)).astype(np.int32)
+        assert np.array_equal(_mean_of_vertices(p, conn), p[:, conn].mean(axis=1))
