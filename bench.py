@@ -136,6 +136,10 @@ def cpu_port_run(mesh_size, method, max_iters, n_warm, n_timed, vol_frac, budget
     Returns a dict with the measured seconds per step (mean over the timed
     steps actually run), the step count, CG iterations and the thread count."""
     from oracle import cport, mesh as omesh, optim
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to
+    # its workers, but in the reference arm rank 0 is the only rank that works
+    n_thr = int(os.environ.get("SKTOPT_BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    cport.lib().cport_set_threads(n_thr)
     t0 = time.perf_counter()
     o = omesh.toy_base(mesh_size)
     pr = optim.Problem(o["p"], o["t"], o["dirichlet_dofs"], o["force"], o["design"],
